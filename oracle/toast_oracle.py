@@ -386,7 +386,7 @@ class Problem:
 
 def amp_dot(a, b, aflags):
     """templates/amplitudes.py:523-571: dot over unflagged local amplitudes."""
-    return float(np.dot(np.where(aflags == 0, a, 0), np.where(aflags == 0, b, 0)))
+    return np.float64(np.dot(np.where(aflags == 0, a, 0), np.where(aflags == 0, b, 0)))
 
 
 def expand_pointing(pb, K):

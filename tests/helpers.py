@@ -1,0 +1,70 @@
+"""Shared helpers for the parity tests."""
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import toast_oracle as O  # noqa: E402  (the checker; never the thing under test)
+from toast_b200 import synthetic as S  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# north_star tolerance: fp64 results within 1e-10 relative of the reference COMPILED path.
+# Element-wise relative error is meaningless for weights/maps that cross zero (cos 2a -> 0), so
+# the bar is norm-wise: max|a - b| <= RTOL * max|b|  (hard part 2).
+RTOL = 1.0e-10
+
+
+def assert_close_norm(actual, expected, rtol=RTOL, what=""):
+    actual = np.asarray(actual, dtype=np.float64)
+    expected = np.asarray(expected, dtype=np.float64)
+    assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
+    scale = np.max(np.abs(expected)) if expected.size else 0.0
+    err = np.max(np.abs(actual - expected)) if expected.size else 0.0
+    assert np.all(np.isfinite(actual)), f"{what}: non-finite values"
+    assert err <= rtol * max(scale, 1e-300), f"{what}: max|diff| {err:.3e} > {rtol:g} * {scale:.3e}"
+
+
+def checker():
+    """The parity checker: the compiled REFERENCE if oracle/_ref is present, else the C port."""
+    ref = O.load_ref()
+    return ref if ref is not None else O
+
+
+def scan_fn(K, dtype="float64"):
+    return getattr(K, f"ops_scan_map_{dtype}", None) or K.scan_map
+
+
+def iso_quat(theta, phi, psi):
+    """qa.from_iso_angles: Rz(phi) Ry(theta) Rz(psi)."""
+    return S.q_mult(S.q_rotation(S.ZAXIS, phi),
+                    S.q_mult(S.q_rotation(S.YAXIS, theta), S.q_rotation(S.ZAXIS, psi)))
+
+
+def healpix_angle_sets():
+    """The eps-perturbed pole / meridian angles and the regular grid of
+    tests/healpix.py:29-74 (healpy replaced by the compiled reference as the authority)."""
+    eps32 = np.finfo(np.float32).eps
+    eps64 = np.finfo(np.float64).eps
+    theta = [0.0, eps64, eps32, np.radians(90.0) - eps32, np.radians(90.0) - eps64,
+             np.radians(90.0), np.radians(90.0) + eps64, np.radians(90.0) + eps32,
+             np.radians(180.0) - eps32, np.radians(180.0) - eps64, np.radians(180.0)]
+    phi = []
+    for pts in [0.0, 90.0, 180.0, 270.0, 360.0]:
+        phi += [np.radians(pts) - eps32, np.radians(pts) - eps64, np.radians(pts),
+                np.radians(pts) + eps64, np.radians(pts) + eps32]
+    ext = np.array([(t, p) for t in theta for p in phi])
+    nreg = 100
+    reg = np.array([(np.radians(t * 180.0 / nreg), np.radians(p * 360.0 / nreg))
+                    for t in range(nreg) for p in range(nreg)])
+    both = np.vstack([ext, reg])
+    return np.ascontiguousarray(both[:, 0]), np.ascontiguousarray(both[:, 1])
+
+
+def ang_to_quat(theta, phi):
+    return np.ascontiguousarray(iso_quat(theta, phi, np.zeros_like(theta)))

@@ -1,0 +1,395 @@
+// tb_math.cuh -- per-sample arithmetic of the TOAST pointing chain, written for sm_100a.
+//
+// Compiled with -fmad=false (device) / -ffp-contract=off (host test build) so that every
+// a*b+c below rounds twice exactly like the reference's baseline-x86-64 build; the only FMAs
+// are the explicit fma() calls inside the double-double helpers.
+//
+// Reference behaviour being reproduced (file:line relative to
+// /root/reference/src/toast/_libtoast):
+//   quaternion product                ops_pointing_detector.cpp:21-31
+//   rotation of z^ / x^ by a quat     ops_pixels_healpix.cpp:50-76, ops_stokes_weights.cpp:21-49
+//   vec -> (z, phi, region)           ops_pixels_healpix.cpp:104-121
+//   (z, phi) -> NEST / RING pixel     ops_pixels_healpix.cpp:123-208, :210-274
+//   detector angle and IQU weights    ops_stokes_weights.cpp:50-140
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define TB_HD __host__ __device__ __forceinline__
+#else
+#define TB_HD inline
+#endif
+
+namespace tbm {
+
+// ------------------------------------------------------------------------------------------
+// quaternions (scalar last)
+// ------------------------------------------------------------------------------------------
+struct Quat {
+    double x, y, z, w;
+};
+
+// r = p (x) q
+TB_HD Quat qmul(const Quat &p, const Quat &q) {
+    Quat r;
+    r.x = p.x * q.w + p.y * q.z - p.z * q.y + p.w * q.x;
+    r.y = -p.x * q.z + p.y * q.w + p.z * q.x + p.w * q.y;
+    r.z = p.x * q.y - p.y * q.x + p.z * q.w + p.w * q.z;
+    r.w = -p.x * q.x - p.y * q.y - p.z * q.z + p.w * q.w;
+    return r;
+}
+
+// Line of sight R(q) z^ .  The reference runs the general rotation formula on (0,0,1); the
+// products with 0.0 are signed zeros, adding them is exact, and its trailing "+ v_in[i]"
+// (+0.0 here) turns any -0 into +0 -- so this reduced form is bit-identical.
+TB_HD void rot_zaxis(const Quat &q, double &dx, double &dy, double &dz) {
+    double xw = q.w * q.x, yw = q.w * q.y;
+    double x2 = -q.x * q.x, y2 = -q.y * q.y;
+    double xz = q.x * q.z, yz = q.y * q.z;
+    dx = 2 * (yw + xz) + 0.0;
+    dy = 2 * (yz - xw) + 0.0;
+    dz = 2 * (x2 + y2) + 1.0;
+}
+
+// Polarisation-sensitive direction R(q) x^ .
+TB_HD void rot_xaxis(const Quat &q, double &ox, double &oy, double &oz) {
+    double yw = q.w * q.y, zw = q.w * q.z;
+    double xy = q.x * q.y, xz = q.x * q.z;
+    double y2 = -q.y * q.y, z2 = -q.z * q.z;
+    ox = 2 * (y2 + z2) + 1.0;
+    oy = 2 * (zw + xy) + 0.0;
+    oz = 2 * (xz - yw) + 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// double-double arithmetic and a (practically) correctly rounded atan2
+//
+// CUDA's atan2 is accurate to 2 ulp, glibc's to < 1 ulp (0.52 ulp bound after the 2.35
+// slow-path removal), so the two can disagree in the last bit.  That only matters for the
+// pixel NUMBER when a pre-truncation value lands within a few ulp of an integer.  Those
+// samples (about 1e-10 of all samples at nside 2048) are re-evaluated with this routine,
+// whose result equals the correctly rounded value and therefore glibc's except when the true
+// angle lies within ~2^-60 relative of a rounding midpoint.
+// ------------------------------------------------------------------------------------------
+struct dd {
+    double hi, lo;
+};
+
+TB_HD dd two_sum(double a, double b) {
+    double s = a + b;
+    double bb = s - a;
+    double e = (a - (s - bb)) + (b - bb);
+    return dd{s, e};
+}
+TB_HD dd quick_two_sum(double a, double b) {
+    double s = a + b;
+    double e = b - (s - a);
+    return dd{s, e};
+}
+TB_HD dd two_prod(double a, double b) {
+    double p = a * b;
+    double e = fma(a, b, -p);
+    return dd{p, e};
+}
+TB_HD dd dd_add(dd a, dd b) {
+    dd s = two_sum(a.hi, b.hi);
+    dd t = two_sum(a.lo, b.lo);
+    s.lo += t.hi;
+    s = quick_two_sum(s.hi, s.lo);
+    s.lo += t.lo;
+    return quick_two_sum(s.hi, s.lo);
+}
+TB_HD dd dd_neg(dd a) { return dd{-a.hi, -a.lo}; }
+TB_HD dd dd_sub(dd a, dd b) { return dd_add(a, dd_neg(b)); }
+TB_HD dd dd_add_d(dd a, double b) {
+    dd s = two_sum(a.hi, b);
+    s.lo += a.lo;
+    return quick_two_sum(s.hi, s.lo);
+}
+TB_HD dd dd_mul(dd a, dd b) {
+    dd p = two_prod(a.hi, b.hi);
+    p.lo += a.hi * b.lo + a.lo * b.hi;
+    return quick_two_sum(p.hi, p.lo);
+}
+TB_HD dd dd_mul_d(dd a, double b) {
+    dd p = two_prod(a.hi, b);
+    p.lo += a.lo * b;
+    return quick_two_sum(p.hi, p.lo);
+}
+TB_HD dd dd_div(dd a, dd b) {
+    double q1 = a.hi / b.hi;
+    dd r = dd_sub(a, dd_mul_d(b, q1));
+    double q2 = r.hi / b.hi;
+    r = dd_sub(r, dd_mul_d(b, q2));
+    double q3 = r.hi / b.hi;
+    dd q = quick_two_sum(q1, q2);
+    return dd_add_d(q, q3);
+}
+TB_HD dd dd_sqrt(dd a) {
+    // Karp & Markstein: sqrt(a) ~= a*x + (a - (a*x)^2) * x / 2 with x = 1/sqrt(a.hi)
+    if (a.hi <= 0.0) return dd{0.0, 0.0};
+    double x = 1.0 / sqrt(a.hi);
+    double ax = a.hi * x;
+    dd t = dd_sub(a, two_prod(ax, ax));
+    return two_sum(ax, t.hi * (x * 0.5));
+}
+
+// atan of a dd argument in [0, 1]: three angle halvings, then the alternating series.
+TB_HD dd dd_atan_unit(dd q) {
+    const dd one = dd{1.0, 0.0};
+    dd t = q;
+    for (int i = 0; i < 3; ++i) {
+        dd den = dd_add(one, dd_sqrt(dd_add(one, dd_mul(t, t))));
+        t = dd_div(t, den);
+    }
+    // |t| <= tan(pi/32) ~ 0.0985 : 18 terms reach 2^-113
+    dd t2 = dd_mul(t, t);
+    const int K = 18;
+    dd s = dd_div(one, dd{(double)(2 * K + 1), 0.0});
+    for (int k = K - 1; k >= 0; --k) {
+        dd c = dd_div(one, dd{(double)(2 * k + 1), 0.0});
+        s = dd_sub(c, dd_mul(t2, s));
+    }
+    dd a = dd_mul(t, s);
+    return dd{a.hi * 8.0, a.lo * 8.0};
+}
+
+TB_HD double atan2_cr(double y, double x) {
+    const dd pi = dd{3.141592653589793116e+00, 1.224646799147353207e-16};
+    const dd pio2 = dd{1.570796326794896558e+00, 6.123233995736766036e-17};
+    double ay = fabs(y), ax = fabs(x);
+    if (ay == 0.0 && ax == 0.0) return signbit(x) ? copysign(pi.hi, y) : y;
+    dd a;
+    if (ay <= ax) {
+        a = dd_atan_unit(dd_div(dd{ay, 0.0}, dd{ax, 0.0}));
+    } else {
+        a = dd_sub(pio2, dd_atan_unit(dd_div(dd{ax, 0.0}, dd{ay, 0.0})));
+    }
+    if (signbit(x)) a = dd_sub(pi, a);
+    double r = a.hi + a.lo;
+    return signbit(y) ? -r : r;
+}
+
+// ------------------------------------------------------------------------------------------
+// HEALPix
+// ------------------------------------------------------------------------------------------
+struct PixCtx {
+    int64_t nside;
+    int64_t nm1;       // nside - 1
+    int64_t fournside; // 4 nside
+    int64_t ncap;      // 2 (nside^2 - nside)
+    int64_t npix;      // 12 nside^2
+    int factor;        // log2(nside)
+    double dnside;     // (double) nside
+    double halfnside;  // 0.5 nside
+    double tqnside;    // 0.75 nside
+    double guard;      // half-width of the "ambiguous" band around integers, units of jp/jm
+    double guard_tt;   // same, in units of tt
+};
+
+TB_HD PixCtx make_pix_ctx(int64_t nside, double guard_scale) {
+    PixCtx c;
+    c.nside = nside;
+    c.nm1 = nside - 1;
+    c.fournside = 4 * nside;
+    c.ncap = 2 * (nside * nside - nside);
+    c.npix = 12 * nside * nside;
+    int f = 0;
+    while (((int64_t)1 << f) < nside) ++f;
+    c.factor = f;
+    c.dnside = (double)nside;
+    c.halfnside = 0.5 * c.dnside;
+    c.tqnside = 0.75 * c.dnside;
+    // |delta tt| <= 2 ulp(phi) * 2/pi + a few roundings < 2e-15; use 4x that.
+    c.guard_tt = 8.0e-15 * guard_scale;
+    c.guard = c.guard_tt * c.dnside;
+    return c;
+}
+
+// Spread the low 32 bits of v onto the even bit positions (the reference's 8-bit utab
+// lookups, ops_pixels_healpix.cpp:20-27,78-85, done with masks instead of a table).
+TB_HD uint64_t spread_bits(uint64_t v) {
+    uint64_t x = v & 0xffffffffull;
+    x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+    x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+TB_HD int64_t xy2pix(int64_t x, int64_t y) {
+    return (int64_t)(spread_bits((uint64_t)x) | (spread_bits((uint64_t)y) << 1));
+}
+
+TB_HD bool near_integer(double v, double tol) { return fabs(v - rint(v)) <= tol; }
+
+// phi -> tt in [0, 4)  (hpix_fmod + snap + quadrant shift, ops_pixels_healpix.cpp:44-48,132-139)
+TB_HD double phi_to_tt(double phi, bool &ambiguous) {
+    const double eps = 2.220446049250313e-16;
+    const double tol = 10.0 * eps;
+    const double twopi = 2 * 3.14159265358979323846;
+    const double two_over_pi = 0.63661977236758134308;
+    double div = phi / twopi;
+    double phi_mod = twopi * (div - (double)((int64_t)div));
+    double aphi = fabs(phi_mod);
+    if (fabs(aphi - tol) <= tol * 1.0e-13) ambiguous = true;
+    if ((phi_mod < tol) && (phi_mod > -tol)) phi_mod = 0.0;
+    return (phi_mod >= 0.0) ? phi_mod * two_over_pi : phi_mod * two_over_pi + 4.0;
+}
+
+// (z, phi) -> pixel.  Sets `ambiguous` when a 2-ulp change of phi could alter the result.
+template <bool NEST>
+TB_HD int64_t zphi2pix(const PixCtx &c, double phi, double z, bool &ambiguous) {
+    const double twothirds = 0.66666666666666666667;
+    double za = fabs(z);
+    double tt = phi_to_tt(phi, ambiguous);
+    if (za <= twothirds) {
+        double t1 = c.halfnside + c.dnside * tt;
+        double t2 = c.tqnside * z;
+        double vp = t1 - t2;
+        double vm = t1 + t2;
+        if (near_integer(vp, c.guard) || near_integer(vm, c.guard)) ambiguous = true;
+        int64_t jp = (int64_t)vp;
+        int64_t jm = (int64_t)vm;
+        if (NEST) {
+            int64_t ifp = jp >> c.factor;
+            int64_t ifm = jm >> c.factor;
+            int64_t face;
+            if (ifp == ifm) {
+                face = (ifp == 4) ? (int64_t)4 : ifp + 4;
+            } else if (ifp < ifm) {
+                face = ifp;
+            } else {
+                face = ifm + 8;
+            }
+            int64_t x = jm & c.nm1;
+            int64_t y = c.nm1 - (jp & c.nm1);
+            return xy2pix(x, y) + (face << (2 * c.factor));
+        } else {
+            int64_t ir = (c.nside + 1) + jp - jm;
+            int64_t kshift = 1 - (ir & 1);
+            int64_t ip = (jp + jm - c.nside + kshift + 1) >> 1;
+            ip = ip % c.fournside;
+            return c.ncap + ((ir - 1) * c.fournside + ip);
+        }
+    } else {
+        double rtz = sqrt(3.0 * (1.0 - za));
+        if (near_integer(tt, c.guard_tt)) ambiguous = true;
+        double t1 = c.dnside * rtz;
+        if (NEST) {
+            int64_t ntt = (int64_t)tt;
+            double tp = tt - (double)ntt;
+            double vp = tp * t1;
+            double vm = (1.0 - tp) * t1;
+            if (near_integer(vp, c.guard) || near_integer(vm, c.guard)) ambiguous = true;
+            int64_t jp = (int64_t)vp;
+            int64_t jm = (int64_t)vm;
+            if (jp >= c.nside) jp = c.nm1;
+            if (jm >= c.nside) jm = c.nm1;
+            int64_t face, x, y;
+            if (z >= 0) {
+                face = ntt;
+                x = c.nm1 - jm;
+                y = c.nm1 - jp;
+            } else {
+                face = ntt + 8;
+                x = jp;
+                y = jm;
+            }
+            return xy2pix(x, y) + (face << (2 * c.factor));
+        } else {
+            double tp = tt - floor(tt);
+            double vp = tp * t1;
+            double vm = (1.0 - tp) * t1;
+            if (near_integer(vp, c.guard) || near_integer(vm, c.guard)) ambiguous = true;
+            int64_t jp = (int64_t)vp;
+            int64_t jm = (int64_t)vm;
+            int64_t ir = jp + jm + 1;
+            double vi = tt * (double)ir;
+            if (near_integer(vi, c.guard)) ambiguous = true;
+            int64_t ip = (int64_t)vi;
+            int64_t longpart = (int64_t)(ip / (4 * ir));
+            ip -= longpart;
+            return (z > 0.0) ? (2 * ir * (ir - 1) + ip) : (c.npix - 2 * ir * (ir + 1) + ip);
+        }
+    }
+}
+
+// Direction vector -> pixel, two-tier: library atan2 first, exact atan2 only if ambiguous.
+// `n_exact` (may be null) counts the samples that took the exact path.
+template <bool NEST>
+TB_HD int64_t vec2pix(const PixCtx &c, double dx, double dy, double dz, int *took_exact) {
+    bool amb = false;
+    double phi = atan2(dy, dx);
+    int64_t p = zphi2pix<NEST>(c, phi, dz, amb);
+    if (amb) {
+        bool dummy = false;
+        phi = atan2_cr(dy, dx);
+        p = zphi2pix<NEST>(c, phi, dz, dummy);
+        if (took_exact) *took_exact = 1;
+    }
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stokes weights
+//
+// The reference forms ang_xy = atan2(vd.y, vd.x), vm = (vd.z cos, vd.z sin, -sqrt(1-vd.z^2)),
+// alpha = atan2(vd.(vm x vo), vm.vo) and then cos/sin(2 alpha).  (cos, sin)(ang_xy) is
+// (vd.x, vd.y)/hypot and (cos, sin)(2 alpha) is a rational function of (alpha_x, alpha_y), so
+// no transcendental call is needed: the result differs from the libm chain by ~1e-15 absolute
+// (tests/test_oracle_math.py), five orders inside the 1e-10 parity bar.
+// ------------------------------------------------------------------------------------------
+TB_HD void detector_cs2alpha(double dx, double dy, double dz, double ox, double oy, double oz,
+                             double &c2a, double &s2a) {
+    double r2 = dx * dx + dy * dy;
+    double cx = 1.0, sx = 0.0; // atan2(0, 0) = 0 in the reference
+    if (r2 > 0.0) {
+        double rinv = 1.0 / sqrt(r2);
+        cx = dx * rinv;
+        sx = dy * rinv;
+    }
+    double vm_x = dz * cx;
+    double vm_y = dz * sx;
+    double vm_z = -sqrt(1.0 - dz * dz);
+    double ay = (dx * (vm_y * oz - vm_z * oy) - dy * (vm_x * oz - vm_z * ox) +
+                 dz * (vm_x * oy - vm_y * ox));
+    double ax = (vm_x * ox + vm_y * oy + vm_z * oz);
+    double n2 = ax * ax + ay * ay;
+    c2a = 1.0;
+    s2a = 0.0; // atan2(0, 0) = 0
+    if (n2 > 0.0) {
+        double inv = 1.0 / n2;
+        c2a = (ax * ax - ay * ay) * inv;
+        s2a = (2.0 * ax * ay) * inv;
+    }
+}
+
+// IQU weights of one sample.  `eta_cal` = eta*cal, hwp4 = 4*(gamma - hwp[s]) (ignored if !HWP).
+template <bool HWP>
+TB_HD void stokes_iqu(const Quat &q, double cal, double eta, double U_sign, double gamma,
+                      double hwp, double &w0, double &w1, double &w2) {
+    double dx, dy, dz, ox, oy, oz;
+    rot_zaxis(q, dx, dy, dz);
+    rot_xaxis(q, ox, oy, oz);
+    double c2a, s2a;
+    detector_cs2alpha(dx, dy, dz, ox, oy, oz, c2a, s2a);
+    w0 = cal;
+    if (!HWP) {
+        w1 = c2a * eta * cal;
+        w2 = s2a * eta * cal * U_sign;
+    } else {
+        // ang = 2 (2 (gamma - hwp) - alpha) = b - 2 alpha,  b = 4 (gamma - hwp)
+        double b = 2.0 * (2.0 * (gamma - hwp));
+        double sb, cb;
+        sincos(b, &sb, &cb);
+        double cang = cb * c2a + sb * s2a;
+        double sang = sb * c2a - cb * s2a;
+        w1 = cang * eta * cal;
+        w2 = -sang * eta * cal * U_sign;
+    }
+}
+
+} // namespace tbm

@@ -1,0 +1,320 @@
+"""Device-resident destriping solver: the fused form of the reference's
+``SolverRHS`` / ``SolverLHS`` / ``solve()`` (``ops/mapmaker_solve.py:107-229, 342-506, 524-755``)
+for the ``templates.Offset`` template.
+
+Everything an iteration touches stays in HBM: expanded pointing (or just the boresight when
+``regen=True``), solver flags, the noise-weighted map, the pixel covariance and the five
+amplitude vectors of the PCG.  One iteration is
+
+    zmap = 0;  pass 1 per observation            (tb_lhs_pass1)
+    all-reduce zmap over ranks (NCCL)            -- the reference's PixelData.sync_allreduce
+    binned = cov * zmap                          (tb_cov_apply_diag)
+    q = 0;  pass 2 per observation               (tb_lhs_pass2)
+    d.q -> alpha;  x, r, s updates;  r.r, s.r    (tb_amp_dot, tb_pcg_update)
+    d = s + beta d                               (tb_pcg_direction)
+
+with the scalars left on the device; the host reads back one float per iteration (the relative
+residual, which the reference logs at ``mapmaker_solve.py:701-706``) to test convergence.
+
+torch is used for device allocations and ``torch.distributed`` for the collectives only.
+"""
+
+import ctypes as ct
+
+import numpy as np
+import torch
+
+from . import lib as L
+from . import kernels as K
+
+
+def _dev_tensor(a, device, dtype=None):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class DeviceObservation:
+    """One observation resident on the device, in the reference's buffer layouts
+    (``detdata`` [n_det, n_samp, ...], ``shared`` [n_samp, ...]) plus the Offset amplitude
+    layout (``templates/offset/offset.py:245-253``: detector-major, ceil(len/step) per view)."""
+
+    def __init__(self, *, focalplane, boresight, intervals, det_scale, step_length, nside, nest,
+                 n_pix_submap, n_submap, global2local, amp_offset=0, epsilon=None, gamma=None,
+                 cal=None, IAU=False, shared_flags=None, shared_flag_mask=0, solver_flags=None,
+                 solver_flag_mask=255, pixels=None, weights=None, hwp=None, device="cuda"):
+        self.device = torch.device(device)
+        self.lib = L.load()
+        self.n_det = int(focalplane.shape[0])
+        self.n_samp = int(boresight.shape[0])
+        self.intervals = np.ascontiguousarray(intervals)
+        self.step_length = int(step_length)
+        self.focalplane = np.ascontiguousarray(focalplane, dtype=np.float64)
+        self.epsilon = np.zeros(self.n_det) if epsilon is None else np.ascontiguousarray(epsilon)
+        self.gamma = np.zeros(self.n_det) if gamma is None else np.ascontiguousarray(gamma)
+        self.cal = np.ones(self.n_det) if cal is None else np.ascontiguousarray(cal)
+        self.det_scale = np.ascontiguousarray(det_scale, dtype=np.float64)
+        self.nside, self.nest, self.IAU = int(nside), bool(nest), bool(IAU)
+        self.n_pix_submap, self.n_submap = int(n_pix_submap), int(n_submap)
+        self.global2local = np.ascontiguousarray(global2local, dtype=np.int64)
+        self.shared_flag_mask = int(shared_flag_mask)
+        self.solver_flag_mask = int(solver_flag_mask)
+
+        # Offset amplitude layout
+        nav = []
+        for iv in self.intervals:
+            ln = int(iv["last"] - iv["first"])
+            n = ln // self.step_length
+            if n * self.step_length < ln:
+                n += 1
+            nav.append(n)
+        self.n_amp_views = np.array(nav, dtype=np.int64)
+        self.n_amp_det = int(self.n_amp_views.sum())
+        self.amp_offsets = amp_offset + np.arange(self.n_det, dtype=np.int64) * self.n_amp_det
+        self.n_amp = self.n_amp_det * self.n_det
+
+        dev = self.device
+        self.boresight = _dev_tensor(boresight, dev, torch.float64)
+        self.shared_flags = _dev_tensor(shared_flags, dev, torch.uint8)
+        self.solver_flags = _dev_tensor(solver_flags, dev, torch.uint8)
+        self.pixels = _dev_tensor(pixels, dev, torch.int64)
+        self.weights = _dev_tensor(weights, dev, torch.float64)
+        self.hwp = _dev_tensor(hwp, dev, torch.float64)
+        self._handle = None
+
+    # -- pointing -----------------------------------------------------------------------------
+    def expand_pointing(self, hit_submaps=None):
+        """PointingDetectorSimple -> PixelsHealpix -> StokesWeights in one fused kernel; fills
+        ``pixels`` / ``weights`` on the device and ORs the hit-submap mask (host uint8)."""
+        dev = self.device
+        if self.pixels is None:
+            self.pixels = torch.zeros((self.n_det, self.n_samp), dtype=torch.int64, device=dev)
+        if self.weights is None:
+            self.weights = torch.zeros((self.n_det, self.n_samp, 3), dtype=torch.float64,
+                                       device=dev)
+        idx = np.arange(self.n_det, dtype=np.int32)
+        K.pointing_fused(self.focalplane, self.boresight, self.shared_flags,
+                         self.shared_flag_mask, None, None, idx, self.pixels, idx, self.weights,
+                         self.hwp, self.intervals, hit_submaps, self.n_pix_submap, self.nside,
+                         self.nest, self.epsilon, self.gamma, self.cal, self.IAU)
+        self._handle = None
+
+    def hit_submaps(self):
+        hits = np.zeros(self.n_submap, dtype=np.uint8)
+        idx = np.arange(self.n_det, dtype=np.int32)
+        K.pointing_fused(self.focalplane, self.boresight, self.shared_flags,
+                         self.shared_flag_mask, None, None, idx, self._scratch_pixels(), None,
+                         None, None, self.intervals, hits, self.n_pix_submap, self.nside,
+                         self.nest, self.epsilon, self.gamma, self.cal, self.IAU)
+        return hits
+
+    def _scratch_pixels(self):
+        if self.pixels is None:
+            self.pixels = torch.zeros((self.n_det, self.n_samp), dtype=torch.int64,
+                                      device=self.device)
+        return self.pixels
+
+    def set_global2local(self, g2l):
+        self.global2local = np.ascontiguousarray(g2l, dtype=np.int64)
+        self._handle = None
+
+    # -- native handle ------------------------------------------------------------------------
+    def handle(self):
+        if self._handle is not None:
+            return self._handle
+        d = L.tb_obs_desc()
+        d.n_det, d.n_samp, d.n_view = self.n_det, self.n_samp, len(self.intervals)
+        self._keep = [self.intervals, self.focalplane, self.epsilon, self.gamma, self.cal,
+                      self.det_scale, self.amp_offsets, self.n_amp_views, self.global2local]
+        d.intervals = self.intervals.ctypes.data
+        d.focalplane = self.focalplane.ctypes.data
+        d.epsilon = self.epsilon.ctypes.data
+        d.gamma = self.gamma.ctypes.data
+        d.cal = self.cal.ctypes.data
+        d.det_scale = self.det_scale.ctypes.data
+        d.amp_offsets = self.amp_offsets.ctypes.data
+        d.n_amp_views = self.n_amp_views.ctypes.data
+        d.step_length = self.step_length
+        d.nside, d.n_pix_submap, d.n_submap = self.nside, self.n_pix_submap, self.n_submap
+        d.nest, d.IAU = int(self.nest), int(self.IAU)
+        d.global2local = self.global2local.ctypes.data
+        d.boresight = L.ptr(self.boresight)
+        d.shared_flags = L.ptr(self.shared_flags)
+        d.shared_flag_mask = self.shared_flag_mask
+        d.solver_flags = L.ptr(self.solver_flags)
+        d.solver_flag_mask = self.solver_flag_mask
+        d.pixels = L.ptr(self.pixels)
+        d.weights = L.ptr(self.weights)
+        d.hwp = L.ptr(self.hwp)
+        h = self.lib.tb_obs_create(ct.byref(d))
+        if not h:
+            raise RuntimeError(L.last_error())
+        self._handle = _ObsHandle(self.lib, h)
+        return self._handle
+
+    def bytes_per_sample_stored(self):
+        return 8 + 24 + (1 if self.solver_flags is not None else 0)
+
+
+class _ObsHandle:
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def __del__(self):
+        try:
+            self.lib.tb_obs_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Destriper:
+    """Fused SolverRHS / SolverLHS / solve() for one or more device observations.
+
+    ``cov`` is the inverse-of-inverse pixel covariance [n_local_submap, n_pix_submap, 6]
+    (upper triangle, row-major) as produced by ``covariance_invert``; ``regen=True``
+    recomputes pointing inside every pass instead of reading stored pixels/weights."""
+
+    def __init__(self, observations, n_local_submap, n_pix_submap, cov, offset_var, amp_flags,
+                 regen=False, group=None, device="cuda"):
+        self.obs = list(observations)
+        self.device = torch.device(device)
+        self.lib = L.load()
+        self.regen = 1 if regen else 0
+        self.group = group
+        self.n_local_submap, self.n_pix_submap = int(n_local_submap), int(n_pix_submap)
+        self.cov = _dev_tensor(cov, self.device, torch.float64)
+        self.offset_var = _dev_tensor(offset_var, self.device, torch.float64)
+        self.amp_flags = _dev_tensor(amp_flags, self.device, torch.uint8)
+        self.n_amp = int(self.offset_var.numel())
+        assert sum(o.n_amp for o in self.obs) == self.n_amp
+        self.zmap = torch.zeros((self.n_local_submap, self.n_pix_submap, 3), dtype=torch.float64,
+                                device=self.device)
+        self._scal = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(group)
+
+    # -- collectives ----------------------------------------------------------------------------
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    # -- building blocks ------------------------------------------------------------------------
+    def bin_amplitudes(self, amps):
+        """binned = cov * allreduce(P^T N^-1 F a)   (BinMap with pre_process=TemplateMatrix)."""
+        self.zmap.zero_()
+        for o in self.obs:
+            L.check(self.lib.tb_lhs_pass1(o.handle().h, L.ptr(amps), L.ptr(self.amp_flags),
+                                          L.ptr(self.zmap), self.regen, None))
+        self._allreduce(self.zmap)
+        L.check(self.lib.tb_cov_apply_diag(self.n_local_submap, self.n_pix_submap, 3,
+                                           L.ptr(self.cov), L.ptr(self.zmap), L.TB_MEM_DEVICE,
+                                           None))
+        return self.zmap
+
+    def bin_signal(self, signals):
+        """binned = cov * allreduce(P^T N^-1 d) for stored timestreams (one tensor per obs)."""
+        self.zmap.zero_()
+        for o, sig in zip(self.obs, signals):
+            L.check(self.lib.tb_bin_signal(o.handle().h, L.ptr(sig), L.ptr(self.zmap), self.regen,
+                                           None))
+        self._allreduce(self.zmap)
+        L.check(self.lib.tb_cov_apply_diag(self.n_local_submap, self.n_pix_submap, 3,
+                                           L.ptr(self.cov), L.ptr(self.zmap), L.TB_MEM_DEVICE,
+                                           None))
+        return self.zmap
+
+    def lhs(self, amps_in, amps_out):
+        """SolverLHS: amps_out = F^T N^-1 Z F amps_in."""
+        binned = self.bin_amplitudes(amps_in)
+        amps_out.zero_()
+        for o in self.obs:
+            L.check(self.lib.tb_lhs_pass2(o.handle().h, L.ptr(amps_in), L.ptr(self.amp_flags),
+                                          L.ptr(binned), L.ptr(amps_out), self.regen, None))
+        return amps_out
+
+    def rhs(self, signals):
+        """SolverRHS: F^T N^-1 Z d."""
+        binned = self.bin_signal(signals)
+        out = torch.zeros(self.n_amp, dtype=torch.float64, device=self.device)
+        for o, sig in zip(self.obs, signals):
+            L.check(self.lib.tb_rhs_project(o.handle().h, L.ptr(sig), L.ptr(self.amp_flags),
+                                            L.ptr(binned), L.ptr(out), self.regen, None))
+        return out
+
+    def dot(self, a, b, out):
+        L.check(self.lib.tb_amp_dot(L.ptr(a), L.ptr(b), L.ptr(self.amp_flags), self.n_amp,
+                                    L.ptr(out), None))
+        self._allreduce(out)
+
+    # -- one PCG iteration (everything after the convergence test of the previous one) ------------
+    def iteration(self, st):
+        """Advance the PCG state ``st`` by one iteration; returns nothing, leaves
+        r.r in st.sums[0] on the device."""
+        self.lhs(st.d, st.q)
+        self.dot(st.d, st.q, st.dq)
+        L.check(self.lib.tb_pcg_update(L.ptr(st.delta), L.ptr(st.dq), L.ptr(st.x), L.ptr(st.r),
+                                       L.ptr(st.d), L.ptr(st.q), L.ptr(st.s),
+                                       L.ptr(self.offset_var), L.ptr(self.amp_flags), self.n_amp,
+                                       L.ptr(st.sums), None))
+        self._allreduce(st.sums)
+
+    def advance_direction(self, st):
+        # delta_new = s.r = sums[1];  beta = delta_new / delta_old;  d = s + beta d
+        L.check(self.lib.tb_pcg_direction(L.ptr(st.sums[1:]), L.ptr(st.delta), L.ptr(st.d),
+                                          L.ptr(st.s), self.n_amp, None))
+        st.delta.copy_(st.sums[1:2])
+
+    def solve(self, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, x0=None):
+        """The PCG of mapmaker_solve.py:524-755.  Returns (amplitudes, relative residuals)."""
+        dev = self.device
+        n = self.n_amp
+        st = _PCGState(n, dev)
+        if x0 is not None:
+            st.x.copy_(x0)
+        self.lhs(st.x, st.q)
+        st.r.copy_(rhs)
+        st.r.sub_(st.q)
+        L.check(self.lib.tb_template_offset_apply_diag_precond(
+            L.ptr(self.offset_var), L.ptr(st.r), L.ptr(self.amp_flags), L.ptr(st.s), n,
+            L.TB_MEM_DEVICE, None))
+        st.d.copy_(st.s)
+        tmp = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.dot(rhs, rhs, tmp)
+        sqsum = float(tmp.item())
+        sqsum_init = sqsum
+        sqsum_best = sqsum
+        last_best = sqsum
+        self.dot(st.d, st.r, st.delta)
+        history = []
+        for it in range(n_iter_max):
+            if not np.isfinite(sqsum):
+                raise RuntimeError("Residual is not finite")
+            self.iteration(st)
+            sqsum = float(st.sums[0].item())
+            relative = sqsum / sqsum_init
+            history.append(relative)
+            if relative < convergence or sqsum < 1e-30:
+                break
+            sqsum_best = min(sqsum, sqsum_best)
+            if it % 10 == 0 and it >= n_iter_min:
+                if last_best < sqsum_best * 2:
+                    break
+                last_best = sqsum_best
+            self.advance_direction(st)
+        return st.x, history
+
+
+class _PCGState:
+    def __init__(self, n, dev):
+        z = lambda: torch.zeros(n, dtype=torch.float64, device=dev)
+        self.x, self.r, self.d, self.q, self.s = z(), z(), z(), z(), z()
+        self.delta = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.dq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.sums = torch.zeros(2, dtype=torch.float64, device=dev)

@@ -68,7 +68,8 @@ def focalplane(n_det, rng, fov_deg=10.0, eps_max=0.0):
     n_pix = (n_det + 1) // 2
     theta = np.radians(fov_deg / 2) * np.sqrt(rng.random(n_pix))
     phi = 2 * np.pi * rng.random(n_pix)
-    psi_pix = np.where(rng.random(n_pix) < 0.5, 0.0, np.pi / 4)
+    rng.random(n_pix)  # (keeps the stream layout stable)
+    psi_pix = np.where(np.arange(n_pix) % 2 == 0, 0.0, np.pi / 4)
     quats = np.zeros((n_det, 4))
     for d in range(n_det):
         p = d // 2
