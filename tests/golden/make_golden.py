@@ -64,6 +64,7 @@ def main():
         ones = np.where(pb.amp_flags == 0, 1.0, 0.0)
         lhs1 = O.solver_lhs(pb, R, ones, covapply=R.cov_apply_diag)
         amps, hist = O.solve(pb, R, rhs, n_iter_max=12, covapply=R.cov_apply_diag)
+        amps2, _ = O.solve(pb, R, rhs, n_iter_max=2, covapply=R.cov_apply_diag)
         idx = np.arange(nd, dtype=np.int32)
         zmap = np.zeros((pb.n_local_submap, pb.n_pix_submap, 3))
         R.build_noise_weighted(pb.global2local, zmap, idx, pb.pixels, idx, pb.weights, idx,
@@ -78,7 +79,7 @@ def main():
             hit_submaps=pb.hit_submaps,
             zmap_index=nz.astype(np.int64),
             zmap_values=zmap.reshape(-1, 3)[nz],
-            rhs=rhs, lhs_of_ones=lhs1, amplitudes=amps, history=np.array(hist),
+            rhs=rhs, lhs_of_ones=lhs1, amplitudes=amps, amplitudes_iter2=amps2, history=np.array(hist),
         )
         print(name, "pixels", pb.pixels.shape, "hist", hist[:3], "->", hist[-1])
 

@@ -458,6 +458,8 @@ tb_obs *tb_obs_create(const tb_obs_desc *desc) {
             db[6 * nd + i] = d.gamma ? d.gamma[i] : 0.0;
             db[7 * nd + i] = d.det_scale[i];
         }
+        // keep the double block 32-byte aligned: fp quaternions are read as double2
+        while ((ib.size() * sizeof(int64_t)) % 32 != 0) ib.push_back(0);
         size_t ibytes = ib.size() * sizeof(int64_t), dbytes = db.size() * sizeof(double);
         TB_CUDA(cudaMalloc(&o->blob, ibytes + dbytes));
         TB_CUDA(cudaMemcpy(o->blob, ib.data(), ibytes, cudaMemcpyHostToDevice));
