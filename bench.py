@@ -53,8 +53,8 @@ BYTES_PER_SAMPLE_ITER = 66
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(SHARDS))
     ap.add_argument("--regen", action="store_true",
@@ -82,7 +82,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -297,7 +297,8 @@ def build_gpu_problem(args, rank, world, device):
     if world > 1:
         torch.distributed.all_reduce(invcov)
     rcond = torch.zeros(n_loc * nps, dtype=torch.float64, device=device)
-    K.cov_invert(n_loc * nps, 3, invcov, rcond, 1.0e-3)
+    # reference default: MapMaker.solve_rcond_threshold = 1e-8 (ops/mapmaker.py)
+    K.cov_invert(n_loc * nps, 3, invcov, rcond, 1.0e-8)
     # rcond mask -> solver flags (scan the bad-pixel map with the I weight = cal = 1)
     bad = torch.zeros((n_loc, nps, 3), dtype=torch.float64, device=device)
     bad[:, :, 0] = (rcond.reshape(n_loc, nps) == 0).to(torch.float64)
@@ -413,12 +414,12 @@ def main_gpu(args):
         history.append(float(st.sums[0].item()) / sqsum_init)  # host convergence test
         ds.advance_direction(st)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # sampled under load: warm-up + timed region + e2e region
     for _ in range(args.warmup):
         step()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     timers = []
     launches0 = lib.tb_launch_count()
     barrier()
@@ -429,7 +430,6 @@ def main_gpu(args):
     t_end.record()
     barrier()
     launches = lib.tb_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
     ms_step = ms_total / max(args.steps, 1)
     p1 = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))
@@ -458,6 +458,7 @@ def main_gpu(args):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks
     if world > 1:

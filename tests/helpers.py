@@ -93,6 +93,7 @@ def assert_history_matches(hist, hist_ref, env, what=""):
     assert len(hist) == len(hist_ref), (what, len(hist), len(hist_ref))
     dev = np.abs(hist - hist_ref) / hist_ref
     n = min(len(dev), len(env))
-    assert np.all(dev[:3] <= RTOL), f"{what}: early history deviates {dev[:3]}"
+    early = (np.arange(len(dev)) < 3) & (hist_ref > 1.0e-12)  # above the fp64 noise floor
+    assert np.all(dev[early] <= RTOL), f"{what}: early history deviates {dev[:3]}"
     bound = np.maximum(RTOL, 1.0e3 * env[:n])
     assert np.all(dev[:n] <= bound), f"{what}: history deviates {dev[:n]} > {bound}"

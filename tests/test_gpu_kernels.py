@@ -8,7 +8,7 @@ import pytest
 
 import helpers as H
 from helpers import O, S, assert_close_norm
-from toast_b200 import kernels as K
+from toast_b200 import kernels as KC
 from toast_b200 import lib as L
 
 pytestmark = pytest.mark.gpu
@@ -17,6 +17,28 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def ck():
     return H.checker()
+
+
+class _PybindFirst:
+    """The pybind11 `_libtoast` module (the reference-facing binding) for every function it
+    exports; the ctypes twin for the extras (batched / fused entry points)."""
+
+    def __init__(self):
+        from toast_b200 import _libtoast
+
+        self._m = _libtoast
+
+    def __getattr__(self, name):
+        if hasattr(self._m, name):
+            return getattr(self._m, name)
+        return getattr(KC, name)
+
+
+@pytest.fixture(scope="module", params=["ctypes", "pybind"])
+def K(request):
+    """Both routes into the C ABI: toast_b200.kernels (ctypes) and toast_b200._libtoast
+    (pybind11, the module TOAST's kernels.py files import)."""
+    return KC if request.param == "ctypes" else _PybindFirst()
 
 
 def _obs(name, n_det, n_samp, **kw):
@@ -37,7 +59,7 @@ CASES = [("c1", 4, 6000), ("c2", 5, 20000), ("c5", 3, 20000), ("c4", 2, 30000)]
 
 
 @pytest.mark.parametrize("name,n_det,n_samp", CASES)
-def test_pointing_detector_bit_exact(ck, name, n_det, n_samp):
+def test_pointing_detector_bit_exact(K, ck, name, n_det, n_samp):
     obs = _obs(name, n_det, n_samp)
     idx, q_ref = _quats(obs, ck)
     q = np.zeros_like(q_ref)
@@ -59,7 +81,7 @@ def test_pointing_detector_bit_exact(ck, name, n_det, n_samp):
 @pytest.mark.parametrize("name,n_det,n_samp", CASES)
 @pytest.mark.parametrize("nest", [True, False])
 @pytest.mark.parametrize("nside", [1, 64, 512, 2048, 16384])
-def test_pixels_healpix_bit_exact(ck, name, n_det, n_samp, nest, nside):
+def test_pixels_healpix_bit_exact(K, ck, name, n_det, n_samp, nest, nside):
     obs = _obs(name, n_det, n_samp)
     idx, quats = _quats(obs, ck)
     n_submap, nps = S.n_submap_for(nside, 16)
@@ -77,7 +99,7 @@ def test_pixels_healpix_bit_exact(ck, name, n_det, n_samp, nest, nside):
 
 
 @pytest.mark.parametrize("nest", [True, False])
-def test_pixels_exact_path_agrees(ck, nest):
+def test_pixels_exact_path_agrees(K, ck, nest):
     """Force every sample through the double-double atan2 path: pixels must not change."""
     obs = _obs("c4", 2, 20000)
     idx, quats = _quats(obs, ck)
@@ -106,7 +128,7 @@ def test_pixels_exact_path_agrees(ck, nest):
         lib.tb_set_pixel_guard_scale(1.0)
 
 
-def test_healpix_reference_angle_sets(ck):
+def test_healpix_reference_angle_sets(K, ck):
     """tests/healpix.py:95-184: eps-perturbed poles / meridians and a regular grid, at nside
     1 / 256 / 16384, NEST and RING -- against the committed reference outputs."""
     gold = np.load(H.GOLDEN + "/healpix_angles.npz")
@@ -133,7 +155,7 @@ def test_healpix_reference_angle_sets(ck):
             assert np.mean(pix[0] == g) > 0.97
 
 
-def test_pointing_matrix_bounds(ck):
+def test_pointing_matrix_bounds(K, ck):
     """tests/ops_pointing_healpix.py:25-96: phi in {-360..360} deg stays inside the map."""
     nside = 64
     npix = 12 * nside**2
@@ -157,7 +179,7 @@ def test_pointing_matrix_bounds(ck):
 
 
 @pytest.mark.parametrize("hwp", [False, True])
-def test_pointing_matrix_weights_analytic(hwp):
+def test_pointing_matrix_weights_analytic(K, hwp):
     """tests/ops_pointing_healpix.py:98-227: Q/U = (+-1, 0) at psi multiples of 45 deg."""
     psivec = np.radians([-180, -135, -90, -45, 0, 45, 90, 135, 180])
     expected_Q = np.array([1.0, 0.0, -1.0, 0.0, 1.0, 0.0, -1.0, 0.0, 1.0])
@@ -178,7 +200,7 @@ def test_pointing_matrix_weights_analytic(hwp):
 
 @pytest.mark.parametrize("name,n_det,n_samp", CASES)
 @pytest.mark.parametrize("hwp,IAU", [(False, False), (True, False), (False, True), (True, True)])
-def test_stokes_weights_IQU(ck, name, n_det, n_samp, hwp, IAU):
+def test_stokes_weights_IQU(K, ck, name, n_det, n_samp, hwp, IAU):
     obs = _obs(name, n_det, n_samp, eps_max=0.05)
     idx, quats = _quats(obs, ck)
     rng = np.random.default_rng(3)
@@ -197,7 +219,7 @@ def test_stokes_weights_IQU(ck, name, n_det, n_samp, hwp, IAU):
     assert np.max(np.abs(w - w_ref)) < 1e-13
 
 
-def test_stokes_weights_I(ck):
+def test_stokes_weights_I(K, ck):
     obs = _obs("c2", 4, 9000)
     idx = np.array([3, 1, 0, 2], dtype=np.int32)
     cal = np.array([1.0, 1.5, 0.5, 2.0])
@@ -209,7 +231,7 @@ def test_stokes_weights_I(ck):
 
 
 @pytest.mark.parametrize("name,n_det,n_samp", CASES)
-def test_pointing_fused_equals_chain(ck, name, n_det, n_samp):
+def test_pointing_fused_equals_chain(K, ck, name, n_det, n_samp):
     obs = _obs(name, n_det, n_samp, eps_max=0.05)
     idx, q_ref = _quats(obs, ck)
     nside, nest = obs["nside"], obs["nest"]
@@ -234,7 +256,7 @@ def test_pointing_fused_equals_chain(ck, name, n_det, n_samp):
     assert_close_norm(w, w_ref, what="fused weights")
 
 
-def test_noise_weight_bit_exact(ck):
+def test_noise_weight_bit_exact(K, ck):
     obs = _obs("c2", 4, 9000)
     idx = np.array([2, 0, 3, 1], dtype=np.int32)
     d_ref = obs["signal"].copy()
@@ -260,7 +282,7 @@ def _pointing(obs, ck):
 
 @pytest.mark.parametrize("name,n_det,n_samp", CASES)
 @pytest.mark.parametrize("use_det_flags,use_shared", [(True, True), (False, False), (True, False)])
-def test_build_noise_weighted(ck, name, n_det, n_samp, use_det_flags, use_shared):
+def test_build_noise_weighted(K, ck, name, n_det, n_samp, use_det_flags, use_shared):
     obs = _obs(name, n_det, n_samp, eps_max=0.03)
     pixels, weights, hits, local, g2l, nps = _pointing(obs, ck)
     idx = np.arange(n_det, dtype=np.int32)
@@ -280,7 +302,7 @@ def test_build_noise_weighted(ck, name, n_det, n_samp, use_det_flags, use_shared
 
 
 @pytest.mark.parametrize("nnz", [1, 2])
-def test_build_noise_weighted_other_nnz(ck, nnz):
+def test_build_noise_weighted_other_nnz(K, ck, nnz):
     obs = _obs("c2", 4, 12000)
     pixels, weights3, hits, local, g2l, nps = _pointing(obs, ck)
     idx = np.arange(4, dtype=np.int32)
@@ -297,7 +319,7 @@ def test_build_noise_weighted_other_nnz(ck, nnz):
 
 @pytest.mark.parametrize("dtype", ["float64", "float32", "int64", "int32"])
 @pytest.mark.parametrize("mode", ["add", "subtract", "scale", "zero_add"])
-def test_scan_map(ck, dtype, mode):
+def test_scan_map(K, ck, dtype, mode):
     obs = _obs("c2", 4, 12000)
     pixels, weights, hits, local, g2l, nps = _pointing(obs, ck)
     idx = np.arange(4, dtype=np.int32)
@@ -314,7 +336,7 @@ def test_scan_map(ck, dtype, mode):
     np.testing.assert_array_equal(d, d_ref)  # same operations in the same order: bit-exact
 
 
-def test_scan_map_add_then_subtract_is_zero(ck):
+def test_scan_map_add_then_subtract_is_zero(K, ck):
     """tests/ops_scan_map.py:99-172."""
     obs = _obs("c1", 4, 6000)
     pixels, weights, hits, local, g2l, nps = _pointing(obs, ck)
@@ -330,7 +352,7 @@ def test_scan_map_add_then_subtract_is_zero(ck):
 
 
 @pytest.mark.parametrize("name,n_det,n_samp", CASES)
-def test_offset_kernels(ck, name, n_det, n_samp):
+def test_offset_kernels(K, ck, name, n_det, n_samp):
     obs = _obs(name, n_det, n_samp)
     iv = obs["intervals"]
     step = obs["step_length"]
@@ -381,7 +403,7 @@ def test_offset_kernels(ck, name, n_det, n_samp):
     np.testing.assert_array_equal(p, p_ref)
 
 
-def test_offset_project_of_add_one_is_step_size():
+def test_offset_project_of_add_one_is_step_size(K):
     """tests/template_offset.py:26-92: project(add(1)) == number of samples per step."""
     n_samp, step = 1000, 37
     iv = S.make_intervals([(0, 400), (450, 1000)])
@@ -401,7 +423,7 @@ def test_offset_project_of_add_one_is_step_size():
     assert d[0, 400:450].sum() == 0.0
 
 
-def test_covariance_kernels(ck):
+def test_covariance_kernels(K, ck):
     obs = _obs("c2", 6, 20000, eps_max=0.03)
     pixels, weights, hits, local, g2l, nps = _pointing(obs, ck)
     n_det, n_loc = 6, len(local)
@@ -446,7 +468,7 @@ def test_covariance_kernels(ck):
     np.testing.assert_array_equal(v, v_ref)
 
 
-def test_accel_table_round_trip(ck):
+def test_accel_table_round_trip(K, ck):
     """tests/accelerator.py:106-389 (test_memory): create / update / reset / delete, and a kernel
     running on table-resident buffers (`use_accel=True`)."""
     obs = _obs("c1", 4, 6000)
@@ -479,7 +501,7 @@ def test_accel_table_round_trip(ck):
         K.accel_delete(quats, "quats")
 
 
-def test_argument_validation_raises():
+def test_argument_validation_raises(K):
     """common.hpp:50-122: wrong dtype / shape raise RuntimeError."""
     obs = _obs("c1", 4, 600)
     idx = np.arange(4, dtype=np.int32)
@@ -498,7 +520,7 @@ def test_argument_validation_raises():
                             bad_iv, obs["shared_flags"], 1, False)
 
 
-def test_empty_and_ragged_inputs(ck):
+def test_empty_and_ragged_inputs(K, ck):
     """No intervals => nothing is touched; ragged intervals incl. empty and 1-sample ones."""
     obs = _obs("c1", 4, 600)
     idx = np.arange(4, dtype=np.int32)

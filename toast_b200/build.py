@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libtoastb200.so")
+LIB = os.environ.get("TB_LIB_PATH", os.path.join(HERE, "libtoastb200.so"))
 SOURCES = ["tb_runtime.cu", "tb_ops.cu", "tb_solver.cu"]
 HEADERS = ["tb_math.cuh", "tb_device.cuh", "tb_runtime.cuh", "../../include/toast_b200.h"]
 
@@ -45,7 +45,8 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("TB_EXTRA_NVCC_FLAGS", "").split()
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:
@@ -55,5 +56,29 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_pybind(force=False):
+    """Compile the `_libtoast` pybind11 module (host C++ above the C ABI), linked against
+    libtoastb200.so in the same directory ($ORIGIN rpath)."""
+    import sysconfig
+
+    import pybind11
+
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    target = os.path.join(HERE, "_libtoast" + ext)
+    src = os.path.join(CSRC, "pybind_module.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "toast_b200.h"), LIB]
+    if not force and not _stale(target, deps):
+        return target
+    cmd = [
+        os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared",
+        "-fvisibility=hidden", "-o", target, src,
+        "-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include(),
+        "-L" + HERE, "-ltoastb200", "-Wl,-rpath,$ORIGIN",
+    ]
+    subprocess.check_call(cmd)
+    return target
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_pybind(force="--force" in sys.argv))

@@ -96,9 +96,14 @@ struct Runs {
     bool is_tail; // this lane is the last of its run
 };
 
+// CAP (power of two <= 32) bounds the run length: runs are additionally cut at lane multiples
+// of CAP so that log2(CAP) shuffle steps suffice.  Shuffles share the LSU/shared-memory data
+// pipe with the loads, so for short natural runs (a few samples per pixel) a small CAP is
+// cheaper than the extra atomics it causes.
+template <int CAP = 32>
 __device__ __forceinline__ Runs find_runs(int64_t key, int lane) {
     int64_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    bool head = (lane == 0) || (prev != key);
+    bool head = (lane == 0) || (prev != key) || ((CAP < 32) && ((lane & (CAP - 1)) == 0));
     unsigned heads = __ballot_sync(0xffffffffu, head);
     unsigned upto = heads & (0xffffffffu >> (31 - lane));
     int head_lane = 31 - __clz(upto);
@@ -109,9 +114,10 @@ __device__ __forceinline__ Runs find_runs(int64_t key, int lane) {
     return r;
 }
 
+template <int CAP = 32>
 __device__ __forceinline__ double seg_sum(double v, const Runs &r) {
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int off = 1; off < CAP; off <<= 1) {
         double u = __shfl_up_sync(0xffffffffu, v, off);
         if (r.dist >= off) v += u;
     }

@@ -54,6 +54,11 @@ struct ObsDev {
 
 __device__ unsigned long long g_exact_count_solver = 0ull;
 
+#ifndef TB_BIN_RUN_CAP
+#define TB_BIN_RUN_CAP 8
+#endif
+constexpr int kBinRunCap = TB_BIN_RUN_CAP; // see find_runs<CAP>
+
 // pixel + weights of one sample, either streamed from HBM or regenerated from the boresight
 template <bool REGEN, bool NEST>
 __device__ __forceinline__ void sample_pointing(const ObsDev &o, int det, int64_t s, bool need,
@@ -139,10 +144,10 @@ k_bin(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ afl
                 z2 = sd * w2;
             }
         }
-        Runs r = find_runs(key, lane);
-        z0 = seg_sum(z0, r);
-        z1 = seg_sum(z1, r);
-        z2 = seg_sum(z2, r);
+        Runs r = find_runs<kBinRunCap>(key, lane);
+        z0 = seg_sum<kBinRunCap>(z0, r);
+        z1 = seg_sum<kBinRunCap>(z1, r);
+        z2 = seg_sum<kBinRunCap>(z2, r);
         if (r.is_tail && key >= 0) {
             double *z = zmap + key * 3;
             atomicAdd(z, z0);

@@ -1,0 +1,288 @@
+"""TemplateMatrix and MapMaker (``ops/mapmaker_templates.py:27-357``, ``ops/mapmaker.py:
+28-787``, ``ops/mapmaker_solve.py``) with the Offset-template solve running on the fused,
+device-resident destriper (``toast_b200.solver``).
+
+``MapMaker._exec`` follows the stages of the reference:
+solver flags -> pixel distribution -> CovarianceAndHits -> rcond mask -> RHS -> PCG ->
+raw binned map -> template-cleaned binned map.  Every per-sample stage is a CUDA kernel; the
+host only orchestrates and reads back one scalar per PCG iteration.
+"""
+
+import numpy as np
+
+from .. import kernels as KC
+from ..pixels import PixelData, PixelDistribution
+from ..templates.amplitudes import AmplitudesMap
+from ..templates.offset import Offset
+from .operator import Operator
+
+
+class TemplateMatrix(Operator):
+    _defaults = dict(templates=None, amplitudes=None, transpose=False, view=None,
+                     det_data="signal", det_mask=1, det_flags=None, det_flag_mask=1)
+
+    def _init_templates(self, data, detectors):
+        if getattr(self, "_initialized", False):
+            return
+        for tmpl in self.templates:
+            tmpl.view = self.view if tmpl.view is None else tmpl.view
+            tmpl.det_data = self.det_data
+            tmpl.det_mask = self.det_mask
+            tmpl.det_flags = self.det_flags
+            tmpl.det_flag_mask = self.det_flag_mask
+            tmpl.initialize(data, detectors)
+        self._initialized = True
+
+    def reset(self):
+        self._initialized = False
+
+    def _exec(self, data, detectors=None, use_accel=False, **kwargs):
+        if self.templates is None or self.amplitudes is None:
+            raise RuntimeError("You must set the templates and amplitudes traits")
+        self._init_templates(data, None)
+        for tmpl in self.templates:
+            tmpl.det_data = self.det_data
+        if self.amplitudes not in data:
+            if not self.transpose:
+                raise RuntimeError(f"Template amplitudes '{self.amplitudes}' do not exist")
+            amps = AmplitudesMap()
+            for tmpl in self.templates:
+                amps[tmpl.name] = tmpl.zeros()
+            data[self.amplitudes] = amps
+        amps = data[self.amplitudes]
+        for det in data.all_local_detectors(selection=detectors, flagmask=self.det_mask):
+            for tmpl in self.templates:
+                if self.transpose:
+                    tmpl.project_signal(det, amps[tmpl.name], use_accel=use_accel)
+                else:
+                    tmpl.add_to_signal(det, amps[tmpl.name], use_accel=use_accel)
+
+    def apply_precond(self, amps_in, amps_out, use_accel=False):
+        for tmpl in self.templates:
+            tmpl.apply_precond(amps_in[tmpl.name], amps_out[tmpl.name], use_accel=use_accel)
+
+    def add_prior(self, amps_in, amps_out, use_accel=False):
+        for tmpl in self.templates:
+            tmpl.add_prior(amps_in[tmpl.name], amps_out[tmpl.name], use_accel=use_accel)
+
+    def _requires(self):
+        return {"detdata": [self.det_data], "global": [self.amplitudes]}
+
+    def _provides(self):
+        return {"detdata": [self.det_data]} if not self.transpose else {"global": [self.amplitudes]}
+
+
+class MapMaker(Operator):
+    """Generalised destriper restricted to what the hot path covers: HEALPix pointing, I/Q/U
+    weights, a diagonal noise model and ONE ``templates.Offset`` template.
+
+    Products placed in ``data`` (names as in ``ops/mapmaker.py:382-651``):
+    ``{name}_hits``, ``{name}_cov``, ``{name}_rcond``, ``{name}_binmap`` (raw binned map),
+    ``{name}_map`` (template-cleaned map) and the solved ``AmplitudesMap`` under
+    ``template_matrix.amplitudes``.  ``self.history`` is the PCG relative-residual history the
+    reference logs at ``mapmaker_solve.py:701-706``.
+    """
+
+    _defaults = dict(det_data="signal", det_mask=1, det_flags="flags", det_flag_mask=1,
+                     shared_flags="flags", shared_flag_mask=1, convergence=1.0e-12, iter_min=3,
+                     iter_max=100, solve_rcond_threshold=1.0e-8, map_rcond_threshold=1.0e-8,
+                     binning=None, template_matrix=None, map_binning=None,
+                     regenerate_pointing=False, keep_solver_products=False, device="cuda")
+
+    def _exec(self, data, detectors=None, use_accel=True, **kwargs):
+        import torch
+
+        from ..solver import DeviceObservation, Destriper
+
+        for trait in ("binning", "template_matrix"):
+            if getattr(self, trait) is None:
+                raise RuntimeError(f"You must set the '{trait}' trait before calling exec()")
+        binning = self.binning
+        pixels, weights = binning.pixel_pointing, binning.stokes_weights
+        if pixels is None or weights is None:
+            raise RuntimeError("binning must have pixel_pointing and stokes_weights set")
+        if weights.mode != "IQU":
+            raise NotImplementedError("the fused destriper implements mode='IQU'")
+        tmpls = self.template_matrix.templates
+        if len(tmpls) != 1 or not isinstance(tmpls[0], Offset):
+            raise NotImplementedError("MapMaker on the B200 path supports one Offset template")
+        tmpl = tmpls[0]
+        dp = pixels.detector_pointing
+        view = pixels.view if pixels.view is not None else dp.view
+        pixels._geometry()
+        dev = torch.device(self.device)
+        comm = data.comm
+
+        # --- template layout (host, O(n_amp)) ------------------------------------------------
+        self.template_matrix.view = view if self.template_matrix.view is None else \
+            self.template_matrix.view
+        self.template_matrix.det_data = self.det_data
+        self.template_matrix.det_flags = None  # solver flags are applied on the device below
+        self.template_matrix.reset()
+        self.template_matrix._init_templates(data, detectors)
+
+        # --- device observations, solver flags bit 0 (mapmaker_templates.py:764-810) -----------
+        dobs, signals = [], []
+        for iob, ob in enumerate(data.obs):
+            dets = [d for d in tmpl._all_dets if d in tmpl._obs_dets[iob]]
+            fp = ob[dp.focalplane_key]
+            iv = ob.intervals[view]
+            sflag = ob.shared[self.shared_flags] if self.shared_flags is not None else None
+            flags = np.zeros((len(dets), ob.n_local_samples), dtype=np.uint8)
+            if self.det_flags is not None:
+                fd = ob.detdata[self.det_flags]
+                flags |= ((fd.data[fd.indices(dets)] & self.det_flag_mask) != 0).astype(np.uint8)
+            if sflag is not None:
+                flags |= ((sflag & self.shared_flag_mask) != 0).astype(np.uint8)[None, :]
+            flags |= tmpl._obs_view_flags[iob][None, :]
+            noise = ob[binning.noise_model]
+            d = DeviceObservation(
+                focalplane=np.array([fp[x]["quat"] for x in dets]),
+                boresight=ob.shared[dp.boresight], intervals=iv,
+                det_scale=np.array([noise.detector_weight(x) for x in dets]),
+                step_length=tmpl._step_length(tmpl.step_time, tmpl._obs_rate[iob]),
+                nside=pixels.nside, nest=pixels.nest, n_pix_submap=pixels._n_pix_submap,
+                n_submap=pixels._n_submap,
+                global2local=np.zeros(pixels._n_submap, dtype=np.int64),
+                epsilon=np.array([fp[x]["epsilon"] for x in dets]),
+                gamma=np.array([fp[x]["gamma"] for x in dets]),
+                cal=np.array([fp[x]["cal"] for x in dets]), IAU=weights.IAU,
+                shared_flags=ob.shared[dp.shared_flags] if dp.shared_flags is not None else None,
+                shared_flag_mask=dp.shared_flag_mask, solver_flags=flags, solver_flag_mask=1,
+                hwp=ob.shared[weights.hwp_angle] if weights.hwp_angle is not None else None,
+                amp_offsets=np.array([tmpl._obs_amp_offset(x, iob) for x in dets],
+                                     dtype=np.int64),
+                device=dev)
+            dobs.append(d)
+            sd = ob.detdata[self.det_data]
+            signals.append(torch.from_numpy(
+                np.ascontiguousarray(sd.data[sd.indices(dets)])).to(dev))
+
+        # --- pointing expansion + pixel distribution --------------------------------------------
+        hits = np.zeros(pixels._n_submap, dtype=np.uint8)
+        for d in dobs:
+            d.expand_pointing(hits)
+            d.solver_flags |= (d.pixels < 0).to(torch.uint8)
+        if comm.comm_world is not None:
+            comm.allreduce_(hits, op="max")
+        local = np.flatnonzero(hits).astype(np.int64)
+        dist = PixelDistribution(pixels._n_pix, pixels._n_submap, local, comm=comm.comm_world)
+        dist.nest = bool(pixels.nest)
+        data[binning.pixel_dist] = dist
+        for d in dobs:
+            d.set_global2local(dist.global_submap_to_local)
+        n_loc, nps = dist.n_local_submap, dist.n_pix_submap
+
+        # --- CovarianceAndHits on the device (mapmaker_utils.py:1131-1270) ----------------------
+        def allreduce_dev(t):
+            if comm.comm_world is not None:
+                torch.distributed.all_reduce(t)
+
+        def covariance(threshold, want_hits):
+            hmap = torch.zeros(n_loc * nps, dtype=torch.int64, device=dev) if want_hits else None
+            inv = torch.zeros((n_loc, nps, 6), dtype=torch.float64, device=dev)
+            for d in dobs:
+                idx = np.arange(d.n_det, dtype=np.int32)
+                KC.cov_accum(dist.global_submap_to_local, n_loc, nps, 3, hmap, inv, idx, d.pixels,
+                             idx, d.weights, idx, d.solver_flags, d.det_scale, 1, d.intervals,
+                             None, 0)
+            if hmap is not None:
+                allreduce_dev(hmap)
+            allreduce_dev(inv)
+            rc = torch.zeros(n_loc * nps, dtype=torch.float64, device=dev)
+            KC.cov_invert(n_loc * nps, 3, inv, rc, float(threshold))
+            return hmap, inv, rc
+
+        hmap, cov, rcond = covariance(self.solve_rcond_threshold, True)
+
+        # rcond mask -> solver flags (mapmaker_templates.py:895-939 via ScanMask)
+        bad = torch.zeros((n_loc, nps, 3), dtype=torch.float64, device=dev)
+        bad[:, :, 0] = (rcond.reshape(n_loc, nps) == 0).to(torch.float64)
+        for d in dobs:
+            idx = np.arange(d.n_det, dtype=np.int32)
+            tmp = torch.zeros((d.n_det, d.n_samp), dtype=torch.float64, device=dev)
+            # I weight may differ from 1 (cal): scan with unit weights on the first component
+            w1 = torch.zeros((d.n_det, d.n_samp, 3), dtype=torch.float64, device=dev)
+            w1[:, :, 0] = 1.0
+            KC.ops_scan_map_float64(dist.global_submap_to_local, nps, bad, tmp, idx, d.pixels, idx,
+                                    w1, idx, d.intervals, 1.0, True, False, False)
+            d.solver_flags |= (tmp != 0).to(torch.uint8)
+            del w1, tmp
+        del bad
+
+        # --- amplitude flags / preconditioner: n_good = F^T (good-sample indicator) -------------
+        n_amp = tmpl._n_local
+        n_good = torch.zeros(n_amp, dtype=torch.float64, device=dev)
+        zero_flags = torch.zeros(n_amp, dtype=torch.uint8, device=dev)
+        amplen = np.zeros(n_amp)
+        detnoise = np.ones(n_amp)
+        for d in dobs:
+            idx = np.arange(d.n_det, dtype=np.int32)
+            ones = torch.ones((d.n_det, d.n_samp), dtype=torch.float64, device=dev)
+            KC.template_offset_project_signal_batch(idx, ones, idx, d.solver_flags, 1,
+                                                    d.step_length, d.amp_offsets, d.n_amp_views,
+                                                    n_good, zero_flags, d.intervals)
+            del ones
+            lens = np.concatenate([
+                np.minimum(d.step_length,
+                           int(v["last"] - v["first"]) - d.step_length * np.arange(na))
+                for v, na in zip(d.intervals, d.n_amp_views)])
+            for k, o in enumerate(d.amp_offsets):
+                amplen[o:o + d.n_amp_det] = lens
+                detnoise[o:o + d.n_amp_det] = d.det_scale[k]
+        ng = n_good.cpu().numpy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            keep = (np.where(amplen > 0, ng / amplen, 0.0) > tmpl.good_fraction) & (detnoise > 0)
+            offset_var = np.where(keep, 1.0 / (detnoise * ng), 0.0)
+        amp_flags = (~keep).astype(np.uint8)
+        tmpl._offsetvar = offset_var
+        tmpl._amp_flags = ~keep
+
+        # --- RHS, PCG ----------------------------------------------------------------------------
+        ds = Destriper(dobs, n_loc, nps, cov, offset_var, amp_flags,
+                       regen=self.regenerate_pointing, device=dev)
+        rhs = ds.rhs(signals)
+        amps_dev, self.history = ds.solve(rhs, convergence=self.convergence,
+                                          n_iter_max=self.iter_max, n_iter_min=self.iter_min)
+
+        # --- final products -------------------------------------------------------------------------
+        if self.map_rcond_threshold != self.solve_rcond_threshold:
+            _, cov_map, rcond_map = covariance(self.map_rcond_threshold, False)
+            ds.cov = cov_map
+        else:
+            rcond_map = rcond
+        binmap = ds.bin_signal(signals).clone()
+        neg = -amps_dev
+        for d, sig in zip(dobs, signals):
+            idx = np.arange(d.n_det, dtype=np.int32)
+            KC.template_offset_add_to_signal_batch(d.step_length, d.amp_offsets, d.n_amp_views,
+                                                   neg, ds.amp_flags, idx, sig, d.intervals)
+        destriped = ds.bin_signal(signals).clone()
+
+        def to_pixdata(t, dtype, nv):
+            p = PixelData(dist, dtype, n_value=nv)
+            p.data[:] = t.reshape(n_loc, nps, nv).cpu().numpy()
+            return p
+
+        data[f"{self.name}_hits"] = to_pixdata(hmap, np.int64, 1)
+        data[f"{self.name}_cov"] = to_pixdata(ds.cov, np.float64, 6)
+        data[f"{self.name}_rcond"] = to_pixdata(rcond_map, np.float64, 1)
+        data[f"{self.name}_binmap"] = to_pixdata(binmap, np.float64, 3)
+        data[f"{self.name}_map"] = to_pixdata(destriped, np.float64, 3)
+        amps = AmplitudesMap()
+        amps[tmpl.name] = tmpl.zeros()
+        amps[tmpl.name].local[:] = amps_dev.cpu().numpy()
+        data[self.template_matrix.amplitudes] = amps
+        # the cleaned timestream is what the reference leaves in det_data (mapmaker.py:531-574)
+        for iob, (ob, d, sig) in enumerate(zip(data.obs, dobs, signals)):
+            dets = [x for x in tmpl._all_dets if x in tmpl._obs_dets[iob]]
+            sd = ob.detdata[self.det_data]
+            sd.data[sd.indices(dets)] = sig.cpu().numpy()
+        if self.keep_solver_products:
+            self.destriper = ds
+
+    def _requires(self):
+        return {"detdata": [self.det_data]}
+
+    def _provides(self):
+        return {"global": [f"{self.name}_map", f"{self.name}_binmap", f"{self.name}_hits"]}

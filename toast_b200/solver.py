@@ -48,7 +48,8 @@ class DeviceObservation:
     def __init__(self, *, focalplane, boresight, intervals, det_scale, step_length, nside, nest,
                  n_pix_submap, n_submap, global2local, amp_offset=0, epsilon=None, gamma=None,
                  cal=None, IAU=False, shared_flags=None, shared_flag_mask=0, solver_flags=None,
-                 solver_flag_mask=255, pixels=None, weights=None, hwp=None, device="cuda"):
+                 solver_flag_mask=255, pixels=None, weights=None, hwp=None, amp_offsets=None,
+                 device="cuda"):
         self.device = torch.device(device)
         self.lib = L.load()
         self.n_det = int(focalplane.shape[0])
@@ -76,7 +77,10 @@ class DeviceObservation:
             nav.append(n)
         self.n_amp_views = np.array(nav, dtype=np.int64)
         self.n_amp_det = int(self.n_amp_views.sum())
-        self.amp_offsets = amp_offset + np.arange(self.n_det, dtype=np.int64) * self.n_amp_det
+        if amp_offsets is not None:
+            self.amp_offsets = np.ascontiguousarray(amp_offsets, dtype=np.int64)
+        else:
+            self.amp_offsets = amp_offset + np.arange(self.n_det, dtype=np.int64) * self.n_amp_det
         self.n_amp = self.n_amp_det * self.n_det
 
         dev = self.device

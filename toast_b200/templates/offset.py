@@ -1,0 +1,209 @@
+"""templates.Offset (``templates/offset/offset.py:28-1030``) without the noise prior: step-wise
+constant baselines per detector and view.
+
+Amplitude layout (``offset.py:166-176, 245-253``): detector-major; per observation and view
+``ceil(view_len / step_length)`` amplitudes with ``step_length = rint(step_time * rate)``
+(``:723-724``).  An amplitude is flagged when its good-sample fraction is <= ``good_fraction``
+or the detector noise weight is <= 0, and ``offset_var = 1 / (detweight * n_good)``
+(``:283-344``) is the diagonal preconditioner.  Per-sample work is done by the CUDA kernels.
+"""
+
+import numpy as np
+
+from .. import _libtoast as K
+from .. import kernels as KC
+from .amplitudes import Amplitudes
+
+
+class Template:
+    """templates/template.py:24-263 (the parts Offset uses)."""
+
+    _defaults = dict(name=None, data=None, view=None, det_data="signal", det_mask=1,
+                     det_flags=None, det_flag_mask=1)
+
+    def __init__(self, **kwargs):
+        for klass in reversed(type(self).__mro__):
+            for k, v in getattr(klass, "_defaults", {}).items():
+                setattr(self, k, v)
+        data = kwargs.pop("data", None)
+        for k, v in kwargs.items():
+            if not hasattr(self, k):
+                raise AttributeError(f"{type(self).__name__} has no trait '{k}'")
+            setattr(self, k, v)
+        if self.name is None:
+            self.name = type(self).__name__
+        if data is not None:
+            self.initialize(data)
+
+    def initialize(self, data, detectors=None):
+        self.data = data
+        self._initialize(data, detectors)
+
+    def detectors(self):
+        return self._all_dets
+
+    def zeros(self):
+        return self._zeros()
+
+    def add_to_signal(self, detector, amplitudes, use_accel=False):
+        self._add_to_signal(detector, amplitudes, use_accel=use_accel)
+
+    def project_signal(self, detector, amplitudes, use_accel=False):
+        self._project_signal(detector, amplitudes, use_accel=use_accel)
+
+    def add_prior(self, amplitudes_in, amplitudes_out, use_accel=False):
+        self._add_prior(amplitudes_in, amplitudes_out, use_accel=use_accel)
+
+    def apply_precond(self, amplitudes_in, amplitudes_out, use_accel=False):
+        self._apply_precond(amplitudes_in, amplitudes_out, use_accel=use_accel)
+
+
+class Offset(Template):
+    _defaults = dict(step_time=10000.0, times="times", noise_model=None, good_fraction=0.5,
+                     use_noise_prior=False, precond_width=20)
+
+    def _step_length(self, stime, rate):
+        return int(np.rint(stime * rate))
+
+    def _initialize(self, new_data, detectors=None):
+        if self.use_noise_prior:
+            raise NotImplementedError("the Offset noise prior is not implemented (SURVEY 8f.3)")
+        self._obs_views, self._obs_view_flags = {}, {}
+        self._obs_rate, self._obs_dets = {}, {}
+        all_dets = {}
+        for iob, ob in enumerate(new_data.obs):
+            t = ob.shared[self.times]
+            rate = 1.0 / np.median(np.diff(t)) if len(t) > 1 else 1.0
+            self._obs_rate[iob] = rate
+            step = self._step_length(self.step_time, rate)
+            views = []
+            for vw in ob.intervals[self.view]:
+                ln = int(vw["last"] - vw["first"])
+                n = ln // step
+                if n * step < ln:
+                    n += 1
+                views.append(n)
+            self._obs_views[iob] = np.array(views, dtype=np.int64)
+            vf = np.ones(ob.n_local_samples, dtype=np.uint8)
+            for vw in ob.intervals[self.view]:
+                vf[vw["first"]:vw["last"]] = 0
+            self._obs_view_flags[iob] = vf
+            self._obs_dets[iob] = set()
+            for d in ob.select_local_detectors(selection=detectors, flagmask=self.det_mask):
+                if d not in ob.detdata[self.det_data].detectors:
+                    continue
+                self._obs_dets[iob].add(d)
+                all_dets.setdefault(d, None)
+        self._all_dets = list(all_dets)
+        self._det_start = {}
+        offset = 0
+        for det in self._all_dets:
+            self._det_start[det] = offset
+            for iob, ob in enumerate(new_data.obs):
+                if det in self._obs_dets[iob]:
+                    offset += int(np.sum(self._obs_views[iob]))
+        self._n_local = offset
+        self._n_global = offset
+        if new_data.comm.comm_world is not None:
+            buf = np.array([float(offset)])
+            new_data.comm.allreduce_(buf)
+            self._n_global = int(buf[0])
+
+        # amplitude flags and variance: n_good per step = F^T (good-sample indicator), computed
+        # with the projection kernel instead of the reference's Python loop (offset.py:283-344)
+        self._amp_flags = np.zeros(self._n_local, dtype=bool)
+        self._offsetvar = np.zeros(self._n_local)
+        if self._n_local == 0:
+            return
+        n_good = np.zeros(self._n_local)
+        amplen = np.zeros(self._n_local)
+        detnoise = np.ones(self._n_local)
+        zero_flags = np.zeros(self._n_local, dtype=np.uint8)
+        for iob, ob in enumerate(new_data.obs):
+            dets = [d for d in self._all_dets if d in self._obs_dets[iob]]
+            if len(dets) == 0:
+                continue
+            step = self._step_length(self.step_time, self._obs_rate[iob])
+            nav = self._obs_views[iob]
+            per_det = int(nav.sum())
+            offs = np.array([self._obs_amp_offset(d, iob) for d in dets], dtype=np.int64)
+            ones = np.ones((len(dets), ob.n_local_samples))
+            didx = np.arange(len(dets), dtype=np.int32)
+            if self.det_flags is not None:
+                fl = np.ascontiguousarray(
+                    ob.detdata[self.det_flags].data[ob.detdata[self.det_flags].indices(dets)])
+                KC.template_offset_project_signal_batch(didx, ones, didx, fl, self.det_flag_mask,
+                                                        step, offs, nav, n_good, zero_flags,
+                                                        ob.intervals[self.view])
+            else:
+                KC.template_offset_project_signal_batch(didx, ones, None, None, 0, step, offs,
+                                                        nav, n_good, zero_flags,
+                                                        ob.intervals[self.view])
+            lens = np.concatenate([
+                np.minimum(step, int(vw["last"] - vw["first"]) - step * np.arange(na))
+                for vw, na in zip(ob.intervals[self.view], nav)]) if per_det else np.zeros(0)
+            for d, o in zip(dets, offs):
+                amplen[o:o + per_det] = lens
+                if self.noise_model is not None:
+                    detnoise[o:o + per_det] = ob[self.noise_model].detector_weight(d)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            frac = np.where(amplen > 0, n_good / amplen, 0.0)
+            keep = (frac > self.good_fraction) & (detnoise > 0)
+            self._offsetvar[:] = np.where(keep, 1.0 / (detnoise * n_good), 0.0)
+        self._amp_flags[:] = ~keep
+
+    def _obs_amp_offset(self, det, iob):
+        off = self._det_start[det]
+        for j in range(iob):
+            if det in self._obs_dets[j]:
+                off += int(np.sum(self._obs_views[j]))
+        return off
+
+    def _zeros(self):
+        z = Amplitudes(self.data.comm, self._n_global, self._n_local)
+        z.local_flags[:] = np.where(self._amp_flags, 1, 0)
+        return z
+
+    def _add_to_signal(self, detector, amplitudes, use_accel=False):
+        if detector not in self._all_dets:
+            return
+        for iob, ob in enumerate(self.data.obs):
+            if detector not in self._obs_dets[iob]:
+                continue
+            step = self._step_length(self.step_time, self._obs_rate[iob])
+            K.template_offset_add_to_signal(
+                step, self._obs_amp_offset(detector, iob), self._obs_views[iob], amplitudes.local,
+                amplitudes.local_flags, int(ob.detdata[self.det_data].indices([detector])[0]),
+                ob.detdata[self.det_data].data, ob.intervals[self.view], use_accel)
+
+    def _project_signal(self, detector, amplitudes, use_accel=False):
+        if detector not in self._all_dets:
+            return
+        for iob, ob in enumerate(self.data.obs):
+            if detector not in self._obs_dets[iob]:
+                continue
+            step = self._step_length(self.step_time, self._obs_rate[iob])
+            if self.det_flags is not None:
+                # the reference ORs the view flags into a per-call host copy of the whole flag
+                # array (offset.py:829-832); the view is already what the kernel iterates over,
+                # so the registered flag buffer can be used directly (SURVEY 8b vi)
+                fidx = int(ob.detdata[self.det_flags].indices([detector])[0])
+                fdata = ob.detdata[self.det_flags].data
+            else:
+                fidx = -1
+                fdata = np.zeros((1, 1), dtype=np.uint8)
+            K.template_offset_project_signal(
+                int(ob.detdata[self.det_data].indices([detector])[0]),
+                ob.detdata[self.det_data].data, fidx, fdata, self.det_flag_mask, step,
+                self._obs_amp_offset(detector, iob), self._obs_views[iob], amplitudes.local,
+                amplitudes.local_flags, ob.intervals[self.view], use_accel)
+
+    def _add_prior(self, amplitudes_in, amplitudes_out, use_accel=False):
+        return  # offset.py:884-887: nothing without a noise prior
+
+    def _apply_precond(self, amplitudes_in, amplitudes_out, use_accel=False):
+        if self._n_local == 0:
+            return
+        K.template_offset_apply_diag_precond(self._offsetvar, amplitudes_in.local,
+                                             amplitudes_in.local_flags, amplitudes_out.local,
+                                             use_accel)
