@@ -56,6 +56,15 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _host_cxx():
+    """The system g++ (the compiler nvcc uses as host compiler).  $CXX is deliberately ignored:
+    this image sets it to a second GCC whose static libstdc++ breaks C++ exception unwinding
+    across the pybind11 boundary."""
+    for cand in ("/usr/bin/g++", "g++"):
+        if os.path.exists(cand) or cand == "g++":
+            return cand
+
+
 def build_pybind(force=False):
     """Compile the `_libtoast` pybind11 module (host C++ above the C ABI), linked against
     libtoastb200.so in the same directory ($ORIGIN rpath)."""
@@ -70,7 +79,7 @@ def build_pybind(force=False):
     if not force and not _stale(target, deps):
         return target
     cmd = [
-        os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared",
+        _host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared",
         "-fvisibility=hidden", "-o", target, src,
         "-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include(),
         "-L" + HERE, "-ltoastb200", "-Wl,-rpath,$ORIGIN",

@@ -57,6 +57,11 @@ class Operator:
         return copy.copy(self)
 
 
+def _ident(obj):
+    arr = getattr(obj, "arr", None)
+    return id(arr) if arr is not None else id(obj)
+
+
 def _merge(a, b):
     for k, v in b.items():
         a.setdefault(k, [])
@@ -73,45 +78,66 @@ class Pipeline(Operator):
 
     def _exec(self, data, detectors=None, use_accel=False, **kwargs):
         ops = list(self.operators or [])
-        staged = []
+        self._req, self._prov, self._pre = dict(), dict(), set()
         if use_accel:
-            req = dict()
             for op in ops:
-                _merge(req, op.requires())
-                _merge(req, op.provides())
-            staged = self._stage(data, req)
-        try:
-            for dset in self.detector_sets:
-                if dset == "ALL":
+                _merge(self._req, op.requires())
+                _merge(self._prov, op.provides())
+            # buffers somebody else already put on the device stay there afterwards
+            self._pre = {_ident(o) for o, _ in self._device_objects(data, self._req, self._prov)
+                         if o.accel_exists()}
+            self._stage(data)
+        for dset in self.detector_sets:
+            if dset == "ALL":
+                for op in ops:
+                    op.exec(data, detectors=detectors, use_accel=use_accel)
+            elif dset == "SINGLE":
+                for det in data.all_local_detectors(selection=detectors):
                     for op in ops:
-                        op.exec(data, detectors=detectors, use_accel=use_accel)
-                elif dset == "SINGLE":
-                    for det in data.all_local_detectors(selection=detectors):
-                        for op in ops:
-                            op.exec(data, detectors=[det], use_accel=use_accel)
-                else:
-                    for op in ops:
-                        op.exec(data, detectors=dset, use_accel=use_accel)
-        finally:
-            self._staged = staged
+                        op.exec(data, detectors=[det], use_accel=use_accel)
+            else:
+                for op in ops:
+                    op.exec(data, detectors=dset, use_accel=use_accel)
 
     def _finalize(self, data, use_accel=False, **kwargs):
         result = None
         for op in self.operators or []:
             result = op.finalize(data, use_accel=use_accel)
-        for obj, nm in getattr(self, "_staged", []):
-            obj.accel_update_host(nm)
-            obj.accel_delete(nm)
-        self._staged = []
+        if use_accel:
+            # pipeline.py:266-303: copy provides() back, drop what this pipeline staged/created
+            prov_ids = {_ident(o) for o, _ in self._device_objects(data, self._prov, {})}
+            for obj, nm in self._device_objects(data, self._req, self._prov):
+                if not obj.accel_exists():
+                    continue
+                if _ident(obj) in prov_ids:
+                    obj.accel_update_host(nm)
+                if _ident(obj) not in self._pre:
+                    obj.accel_delete(nm)
         return result
 
+    def _stage(self, data):
+        for obj, nm in self._device_objects(data, self._req, {}):
+            if not obj.accel_exists():
+                obj.accel_create(nm)
+                obj.accel_update_device(nm)
+
     @staticmethod
-    def _stage(data, req):
+    def _device_objects(data, req, prov):
+        """(object, name) for every existing buffer named by the requires / provides dicts."""
         from .. import _libtoast as K
 
         class _Buf:
             def __init__(self, arr):
                 self.arr = arr
+
+            def accel_exists(self):
+                return K.accel_present(self.arr, "shared")
+
+            def accel_create(self, nm):
+                K.accel_create(self.arr, nm)
+
+            def accel_update_device(self, nm):
+                K.accel_update_device(self.arr, nm)
 
             def accel_update_host(self, nm):
                 K.accel_update_host(self.arr, nm)
@@ -119,21 +145,25 @@ class Pipeline(Operator):
             def accel_delete(self, nm):
                 K.accel_delete(self.arr, nm)
 
-        staged = []
+        keys = dict()
+        _merge(keys, req)
+        _merge(keys, prov)
+        out, seen = [], set()
+
+        def add(obj, nm):
+            ident = _ident(obj)
+            if ident not in seen:
+                seen.add(ident)
+                out.append((obj, nm))
+
         for ob in data.obs:
-            for key in req.get("detdata", []):
-                if key in ob.detdata and not ob.detdata[key].accel_exists():
-                    ob.detdata[key].accel_create(key)
-                    ob.detdata[key].accel_update_device(key)
-                    staged.append((ob.detdata[key], key))
-            for key in req.get("shared", []):
-                if key in ob.shared and not K.accel_present(ob.shared[key], key):
-                    K.accel_create(ob.shared[key], key)
-                    K.accel_update_device(ob.shared[key], key)
-                    staged.append((_Buf(ob.shared[key]), key))
-        for key in req.get("global", []):
-            if key in data and hasattr(data[key], "accel_create") and not data[key].accel_exists():
-                data[key].accel_create(key)
-                data[key].accel_update_device(key)
-                staged.append((data[key], key))
-        return staged
+            for key in keys.get("detdata", []):
+                if key is not None and key in ob.detdata:
+                    add(ob.detdata[key], key)
+            for key in keys.get("shared", []):
+                if key is not None and key in ob.shared:
+                    add(_Buf(ob.shared[key]), key)
+        for key in keys.get("global", []):
+            if key is not None and key in data and hasattr(data[key], "accel_create"):
+                add(data[key], key)
+        return out
