@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# The reference's CPU project_signal accumulates with OpenMP atomics (template_offset.cpp:
+# 301-327): only a single-threaded oracle is deterministic / bit-comparable.
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,0 +1,135 @@
+"""CPU tests of the host-side logic: synthetic workloads, data model, Offset layout, operator
+plumbing and argument validation (no GPU needed; compute entry points must fail loudly)."""
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import O, S
+from toast_b200 import kernels as KC
+from toast_b200 import lib as L
+from toast_b200.data import Data, DetDataManager, make_intervals, observation_from_synthetic
+from toast_b200.pixels import PixelData, PixelDistribution
+from toast_b200.templates import Amplitudes, AmplitudesMap
+
+
+def test_synthetic_workloads_are_deterministic_and_shardable():
+    a = S.make_observation("c4", n_det=4, n_samp=5000)
+    b = S.make_observation("c4", n_det=4, n_samp=5000)
+    for k in ("focalplane", "boresight", "signal", "det_flags", "shared_flags"):
+        np.testing.assert_array_equal(a[k], b[k])
+    # detector blocks of one focalplane: rank r of a sharded job draws detectors [r*n, (r+1)*n)
+    full = S.make_observation("c4", n_det=8, n_samp=100, with_signal=False)
+    lo = S.make_observation("c4", n_det=4, n_samp=100, det_first=0, with_signal=False)
+    hi = S.make_observation("c4", n_det=4, n_samp=100, det_first=4, with_signal=False)
+    np.testing.assert_array_equal(full["focalplane"][:4], lo["focalplane"])
+    np.testing.assert_array_equal(full["focalplane"][4:], hi["focalplane"])
+    np.testing.assert_array_equal(lo["boresight"], hi["boresight"])
+    assert np.allclose(np.linalg.norm(full["boresight"], axis=1), 1.0)
+    g = S.make_observation("c2", n_det=2, n_samp=40000, with_signal=False)
+    iv = g["intervals"]
+    assert len(iv) > 4 and np.all(iv["last"][:-1] <= iv["first"][1:])
+    cover = np.sum(iv["last"] - iv["first"]) / 40000
+    assert 0.85 < cover < 0.95
+    for name, cfg in S.CONFIGS.items():
+        n_submap, nps = S.n_submap_for(cfg["nside"])
+        assert n_submap * nps == 12 * cfg["nside"] ** 2
+
+
+def test_offset_layout_and_variance_match_reference_rules():
+    iv = make_intervals([(0, 250), (300, 1000)])
+    nav, det_start, n_amp = O.offset_layout(3, iv, 100)
+    np.testing.assert_array_equal(nav, [3, 7])
+    np.testing.assert_array_equal(det_start, [0, 10, 20])
+    assert n_amp == 30
+    flags = np.zeros((3, 1000), dtype=np.uint8)
+    flags[1, 0:60] = 1          # first step of det 1: 40 % good -> flagged
+    flags[2, 300:349] = 1       # 51 % good -> kept
+    var, fl = O.offset_variance(3, 1000, iv, 100, nav, np.array([2.0, 2.0, 0.0]), flags, 1)
+    assert fl[10] == 1 and var[10] == 0.0
+    assert fl[0] == 0 and var[0] == 1.0 / (2.0 * 100)
+    assert var[2] == 1.0 / (2.0 * 50)           # last, short step of the first view
+    assert np.all(fl[20:] == 1)                 # detector with zero noise weight is cut
+
+
+def test_detdata_ensure_semantics():
+    m = DetDataManager(100)
+    assert m.ensure("pixels", dtype=np.int64, detectors=["a", "b"]) is False
+    assert m["pixels"].data.shape == (2, 100)
+    assert m.ensure("pixels", dtype=np.int64, detectors=["b"]) is True   # exists => skip
+    with pytest.raises(RuntimeError):
+        m.ensure("pixels", dtype=np.int32, detectors=["a"])
+    np.testing.assert_array_equal(m["pixels"].indices(["b", "a"]), [1, 0])
+    assert m["pixels"].indices(["a"]).dtype == np.int32
+
+
+def test_pixel_distribution_and_amplitudes():
+    dist = PixelDistribution(12 * 64 * 64, 16, [3, 7, 8])
+    assert dist.n_pix_submap == 3072
+    np.testing.assert_array_equal(dist.global_submap_to_local[[3, 7, 8, 0]], [0, 1, 2, -1])
+    sm, lp = dist.global_pixel_to_submap(np.array([3 * 3072 + 5, -1, 8 * 3072]))
+    np.testing.assert_array_equal(sm, [0, -1, 2])
+    np.testing.assert_array_equal(lp, [5, -1, 0])
+    p = PixelData(dist, np.float64, n_value=3)
+    assert p.data.shape == (3, 3072, 3) and p.raw.base is not None
+
+    a = Amplitudes(None, 6, 6)
+    b = a.duplicate()
+    a.local[:] = np.arange(6)
+    b.local[:] = 2.0
+    a.local_flags[1] = 1
+    b.local_flags[:] = a.local_flags
+    assert a.dot(b) == 2.0 * (0 + 2 + 3 + 4 + 5)
+    m = AmplitudesMap()
+    m["x"] = a
+    m2 = m.duplicate()
+    m2 *= 2.0
+    m += m2
+    np.testing.assert_array_equal(m["x"].local, 3.0 * np.arange(6))
+
+
+def test_argument_validation_happens_before_the_device():
+    obs = S.make_observation("c1", n_det=4, n_samp=600)
+    idx = np.arange(4, dtype=np.int32)
+    from toast_b200 import _libtoast as KP
+
+    for K in (KC, KP):
+        with pytest.raises(RuntimeError, match="format|dtype"):
+            K.pointing_detector(obs["focalplane"], obs["boresight"].astype(np.float32), idx,
+                                np.zeros((4, 600, 4)), obs["intervals"], obs["shared_flags"], 1,
+                                False)
+        with pytest.raises(RuntimeError, match="shape|length"):
+            K.pointing_detector(obs["focalplane"], obs["boresight"], idx, np.zeros((4, 599, 4)),
+                                obs["intervals"], obs["shared_flags"], 1, False)
+        with pytest.raises(RuntimeError):
+            K.noise_weight(np.zeros((4, 600))[:, ::2], idx, obs["intervals"], np.ones(4), False)
+    if not L.accel_enabled():
+        # and with valid arguments the call refuses to compute without a GPU
+        with pytest.raises(RuntimeError, match="no usable CUDA device"):
+            KP.noise_weight(np.zeros((4, 600)), idx, obs["intervals"], np.ones(4), False)
+
+
+def test_operator_mirror_has_reference_names_and_traits():
+    from toast_b200 import ops, templates
+
+    for name in ("PointingDetectorSimple", "PixelsHealpix", "StokesWeights", "NoiseWeight",
+                 "BuildNoiseWeighted", "ScanMap", "BinMap", "MapMaker", "TemplateMatrix",
+                 "Pipeline", "BuildHitMap", "BuildInverseCovariance", "CovarianceAndHits"):
+        assert hasattr(ops, name)
+    assert hasattr(templates, "Offset")
+    dp = ops.PointingDetectorSimple(boresight="boresight_radec", shared_flag_mask=3)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=512, nside_submap=16, nest=False,
+                            create_dist="dist")
+    assert (pix.nside, pix.nest, dp.shared_flag_mask) == (512, False, 3)
+    with pytest.raises(AttributeError):
+        ops.PixelsHealpix(no_such_trait=1)
+    obs = S.make_observation("c1", n_det=4, n_samp=600)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    ob = data.obs[0]
+    assert ob.detdata["signal"].data.shape == (4, 600)
+    assert ob.select_local_detectors(["D00001"]) == ["D00001"]
+    t = templates.Offset(name="b", step_time=10.0, noise_model="noise_model")
+    assert t._step_length(10.0, 10.0) == 100
+    with pytest.raises(RuntimeError):
+        ops.MapMaker(name="mm").apply(data)      # binning / template_matrix traits missing
