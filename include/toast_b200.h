@@ -302,6 +302,20 @@ int tb_pcg_update(const double *delta, const double *dq, double *x, double *r,
 int tb_pcg_direction(const double *delta_new, const double *delta_old, double *d,
                      const double *s, int64_t n, void *stream);
 
+/* Build (or rebuild, after the flags / global2local changed) the solver's compact copy of the
+ * stored pointing: int32 local pixel with flags and global2local folded in + the (Q,U) weights as
+ * one 16-byte record = 20 B / det-sample instead of 33 B, bit-identical values.  The LHS passes
+ * use it when present.  If the I weight is not the per-detector constant cal[det] the copy is
+ * discarded and the general kernels keep running.                                           */
+int tb_obs_pack_pointing(tb_obs *obs, void *stream);
+int tb_obs_has_compact_pointing(const tb_obs *obs);
+
+/* Runtime options (A/B measurements, debugging):
+ *   "compact" (default 1)  use the compact pointing in the LHS passes when it has been packed
+ *   "tma"     (default 0)  stage the stored-pointing LHS passes through shared memory with
+ *                          cp.async.bulk + mbarrier (measured slower than direct loads)     */
+int tb_set_option(const char *name, int value);
+
 /* ---- test hooks ------------------------------------------------------------------------- */
 /* Scale the guard band that routes a sample to the exact (double-double atan2) pixel path;
  * 1.0 = production, 0.0 = fast path only, large = every sample takes the exact path.      */

@@ -29,6 +29,13 @@ struct tb_obs {
     const double *det_scale = nullptr;
     tb_obs_desc d; // copy of the descriptor (host pointers in it are NOT kept alive)
     int64_t n_amp_det = 0;
+    // per-interval tiles for the TMA-staged passes: [n_tiles] x {s0, off, cnt, view}
+    int64_t *tiles = nullptr;
+    int64_t n_tiles = 0;
+    // compact solver pointing (tb_obs_pack_pointing): local pixel (int32, <0 = nothing to do)
+    // and the two sample-dependent weights (Q, U) as one 16-byte record
+    int32_t *lpix = nullptr;
+    double2 *wqu = nullptr;
 };
 
 namespace {
@@ -50,6 +57,10 @@ struct ObsDev {
     const int64_t *pixels;
     const double *weights;
     const double *hwp;
+    const int64_t *tiles; // [n_tiles][4]
+    int64_t n_tiles;
+    const int32_t *lpix;
+    const double2 *wqu;
 };
 
 __device__ unsigned long long g_exact_count_solver = 0ull;
@@ -209,6 +220,345 @@ k_project(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__
     if (REGEN && n_exact) atomicAdd(&g_exact_count_solver, (unsigned long long)n_exact);
 }
 
+
+// =================================================================================================
+// TMA-staged LHS passes (stored pointing).
+//
+// ncu on the direct-load kernels above (profiles/r1_*): both passes sit at ~90 % / 70 % of the
+// L1/LSU wavefront rate but only ~60 % of DRAM bandwidth -- the 24-byte-stride weight loads cost
+// ~20 L1 wavefronts per warp.  Here one thread per CTA issues `cp.async.bulk` (TMA) copies of the
+// tile's pixels / weights / flags into shared memory (double buffered, mbarrier completion,
+// L2 evict-first so the streamed pointing does not displace the zmap / map tiles), and the
+// warps read conflict-free from shared memory: 9 wavefronts per warp instead of ~22, and the
+// memory-level parallelism no longer depends on occupancy.
+//
+// Tiles never straddle an interval (host-built table), so a tile is one contiguous sample range
+// of one detector.  Copies are 16-byte aligned by starting at the element index rounded down to a
+// multiple of 16 samples (`shift`) and clipped at the end of the buffer; the few samples that
+// fall outside the copied window are read directly.
+// =================================================================================================
+#ifndef TB_TMA_PER_THREAD
+#define TB_TMA_PER_THREAD 2
+#endif
+#ifndef TB_TMA_CTAS_PER_SM
+#define TB_TMA_CTAS_PER_SM 6
+#endif
+constexpr int kTmaPerThread = TB_TMA_PER_THREAD;      // samples per thread per tile
+constexpr int kTmaTile = kThreads * kTmaPerThread;    // samples per staged tile
+constexpr int kTmaCtasPerSm = TB_TMA_CTAS_PER_SM;     // 2 stages x 17 KB x 6 CTAs = 206 KB / SM
+constexpr int kPad = 16;
+constexpr int kStageSamples = kTmaTile + kPad;
+
+struct __align__(128) Stage {
+    int64_t pix[kStageSamples];
+    double w[3 * kStageSamples];
+    uint8_t fl[kStageSamples + 16];
+};
+constexpr int kStages = 2;
+constexpr size_t kTmaSmemBytes = kStages * sizeof(Stage) + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar,
+                                         uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+                 "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+struct TileWork {
+    int det;
+    int view;
+    int count;       // valid samples in the tile
+    int shift;       // first valid sample sits at stage index `shift`
+    int copied;      // samples present in the stage (multiple of 16, may be < shift + count)
+    int64_t s0;      // first sample
+    int64_t off;     // s0 - first[view]
+    int64_t ea;      // element index (det * n_samp + sample) of stage index 0
+};
+
+__device__ __forceinline__ TileWork tile_work(const ObsDev &o, int64_t w) {
+    TileWork t;
+    int64_t tile = w / o.n_det;
+    t.det = (int)(w - tile * o.n_det);
+    const int64_t *tt = o.tiles + 4 * tile;
+    t.s0 = __ldg(tt);
+    t.off = __ldg(tt + 1);
+    t.count = (int)__ldg(tt + 2);
+    t.view = (int)__ldg(tt + 3);
+    int64_t e0 = (int64_t)t.det * o.n_samp + t.s0;
+    t.ea = e0 & ~(int64_t)15;
+    t.shift = (int)(e0 - t.ea);
+    int64_t want = ((int64_t)t.shift + t.count + 15) & ~(int64_t)15;
+    int64_t avail = (o.n_det * o.n_samp - t.ea) & ~(int64_t)15;
+    t.copied = (int)(want < avail ? want : avail);
+    return t;
+}
+
+__device__ __forceinline__ void stage_issue(const ObsDev &o, const TileWork &t, Stage *st,
+                                            uint64_t *bar, uint64_t policy) {
+    if (t.copied > 0) {
+        unsigned n = (unsigned)t.copied;
+        unsigned bytes = n * 8u + n * 24u + (o.solver_flags ? n : 0u);
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(st->pix, o.pixels + t.ea, n * 8u, bar, policy);
+        bulk_g2s(st->w, o.weights + 3 * t.ea, n * 24u, bar, policy);
+        if (o.solver_flags) bulk_g2s(st->fl, o.solver_flags + t.ea, n, bar, policy);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
+template <bool PASS2>
+__global__ void __launch_bounds__(kThreads, kTmaCtasPerSm)
+k_lhs_tma(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ aflags,
+          const double *__restrict__ binned, double *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage *stages = reinterpret_cast<Stage *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kStages * sizeof(Stage));
+    const int lane = threadIdx.x & 31;
+    const int64_t n_work = o.n_tiles * o.n_det;
+    uint64_t policy = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    }
+    __syncthreads();
+    int64_t w = blockIdx.x;
+    if (threadIdx.x == 0 && w < n_work) {
+        TileWork t0 = tile_work(o, w);
+        stage_issue(o, t0, &stages[0], &bars[0], policy);
+    }
+    for (int it = 0; w < n_work; w += gridDim.x, ++it) {
+        const int cur = it & 1;
+        int64_t wn = w + gridDim.x;
+        if (threadIdx.x == 0 && wn < n_work) {
+            TileWork tn = tile_work(o, wn);
+            stage_issue(o, tn, &stages[cur ^ 1], &bars[cur ^ 1], policy);
+        }
+        TileWork t = tile_work(o, w);
+        const Stage *st = &stages[cur];
+        while (!mbar_try_wait(&bars[cur], (unsigned)((it >> 1) & 1))) {
+        }
+        const int64_t amp_base = __ldg(o.amp_offsets + t.det) + __ldg(o.amp_view_off + t.view);
+        const double scale = __ldg(o.det_scale + t.det);
+#pragma unroll
+        for (int k = 0; k < kTmaPerThread; ++k) {
+            const int i = k * kThreads + threadIdx.x;
+            int64_t key = -1;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            if (i < t.count) {
+                const int li = t.shift + i;
+                int64_t pix;
+                double w0, w1, w2;
+                bool ok = true;
+                if (li < t.copied) {
+                    pix = st->pix[li];
+                    w0 = st->w[3 * li];
+                    w1 = st->w[3 * li + 1];
+                    w2 = st->w[3 * li + 2];
+                    if (o.solver_flags) ok = (st->fl[li] & o.solver_mask) == 0;
+                } else { // clipped tail of the very last tile
+                    int64_t e = t.ea + li;
+                    pix = o.pixels[e];
+                    w0 = o.weights[3 * e];
+                    w1 = o.weights[3 * e + 1];
+                    w2 = o.weights[3 * e + 2];
+                    if (o.solver_flags) ok = (o.solver_flags[e] & o.solver_mask) == 0;
+                }
+                int64_t amp = amp_base + fast_div(t.off + i, o.inv_step);
+                bool amp_ok = __ldg(aflags + amp) == 0;
+                double tod = amp_ok ? __ldg(amps + amp) : 0.0;
+                if (!PASS2) {
+                    if (ok && pix >= 0) {
+                        int64_t gsm = fast_div(pix, o.inv_nps);
+                        key = __ldg(o.g2l + gsm) * o.n_pix_submap + (pix - gsm * o.n_pix_submap);
+                        double sd = tod * scale;
+                        v0 = sd * w0;
+                        v1 = sd * w1;
+                        v2 = sd * w2;
+                    }
+                } else {
+                    if (amp_ok) key = amp;
+                    if (amp_ok && ok) {
+                        if (pix >= 0) {
+                            int64_t gsm = fast_div(pix, o.inv_nps);
+                            const double *m = binned + 3 * (__ldg(o.g2l + gsm) * o.n_pix_submap +
+                                                            (pix - gsm * o.n_pix_submap));
+                            double sc = 0.0;
+                            sc += w0 * __ldg(m);
+                            sc += w1 * __ldg(m + 1);
+                            sc += w2 * __ldg(m + 2);
+                            tod -= sc;
+                        }
+                        v0 = tod * scale;
+                    }
+                }
+            }
+            if (!PASS2) {
+                Runs r = find_runs<kBinRunCap>(key, lane);
+                v0 = seg_sum<kBinRunCap>(v0, r);
+                v1 = seg_sum<kBinRunCap>(v1, r);
+                v2 = seg_sum<kBinRunCap>(v2, r);
+                if (r.is_tail && key >= 0) {
+                    double *z = out + key * 3;
+                    atomicAdd(z, v0);
+                    atomicAdd(z + 1, v1);
+                    atomicAdd(z + 2, v2);
+                }
+            } else {
+                Runs r = find_runs(key, lane);
+                v0 = seg_sum(v0, r);
+                if (r.is_tail && key >= 0) atomicAdd(out + key, v0);
+            }
+        }
+        __syncthreads(); // stage `cur` may be refilled by the next iteration's prefetch
+    }
+}
+
+int g_use_tma = 0; // tb_set_option("tma", 0/1): measured slower than the direct kernels
+
+// =================================================================================================
+// Compact solver pointing.
+//
+// The pointing is static across PCG iterations, so the solver keeps a derived copy that is
+// cheaper to stream than the operator-facing (int64 pixel, 3 x f64 weight, u8 flag) = 33 B:
+//   lpix  int32   local pixel index into the map (global2local and the flag test folded in):
+//                 >= 0 good sample; -1 flagged (contributes nothing); -2 unflagged but off the
+//                 map (pass 2 keeps the template value, nothing is scanned)
+//   wqu   double2 the Q and U weights, bit-identical copies; the I weight is the per-detector
+//                 constant cal[det] (ops_stokes_weights.cpp:99,130), verified while packing
+// = 20 B per det-sample, and both arrays are read with perfectly coalesced LDG.32 / LDG.128
+// (5 L1 wavefronts per warp instead of ~22 for the 24-byte-stride weight rows).
+// =================================================================================================
+__device__ unsigned int g_pack_mismatch = 0u;
+
+__global__ void __launch_bounds__(kThreads)
+k_pack_pointing(ObsDev o, int32_t *__restrict__ lpix, double2 *__restrict__ wqu) {
+    const int64_t total = o.n_det * o.n_samp;
+    unsigned bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int det = (int)(i / o.n_samp);
+        int64_t pix = ld_stream(o.pixels + i);
+        const double *w = o.weights + 3 * i;
+        double w0 = ld_stream(w), w1 = ld_stream(w + 1), w2 = ld_stream(w + 2);
+        bool ok = o.solver_flags ? ((ld_stream(o.solver_flags + i) & o.solver_mask) == 0) : true;
+        int32_t lp = -1;
+        if (ok) {
+            lp = -2;
+            if (pix >= 0) {
+                int64_t gsm = fast_div(pix, o.inv_nps);
+                int64_t lsm = __ldg(o.g2l + gsm);
+                if (lsm >= 0) {
+                    lp = (int32_t)(lsm * o.n_pix_submap + (pix - gsm * o.n_pix_submap));
+                    if (w0 != __ldg(o.cal + det)) bad = 1;
+                }
+            }
+        }
+        lpix[i] = lp;
+        wqu[i] = make_double2(w1, w2);
+    }
+    if (bad) atomicOr(&g_pack_mismatch, 1u);
+}
+
+#ifndef TB_COMPACT_CTAS
+#define TB_COMPACT_CTAS 8
+#endif
+template <bool PASS2>
+__global__ void __launch_bounds__(kThreads, TB_COMPACT_CTAS)
+k_lhs_compact(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ aflags,
+              const double *__restrict__ binned, double *__restrict__ out) {
+    TileId _tile = tile_of_block(blockIdx.x, o.n_det);
+    const int det = _tile.det;
+    const int lane = threadIdx.x & 31;
+    const double scale = __ldg(o.det_scale + det);
+    const double w0 = __ldg(o.cal + det);
+    const int64_t amp_det = __ldg(o.amp_offsets + det);
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+        int64_t t = _tile.t0 + (int64_t)k * kThreads + threadIdx.x;
+        int64_t key = -1;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (t < o.V.total) {
+            int view = (o.V.n_view > 1) ? find_view(o.V, t) : 0;
+            int64_t off = t - __ldg(o.V.prefix + view);
+            int64_t i = (int64_t)det * o.n_samp + __ldg(o.V.first + view) + off;
+            int32_t lp = __ldcs(o.lpix + i);
+            double2 wq = __ldcs(o.wqu + i);
+            int64_t amp = amp_det + __ldg(o.amp_view_off + view) + fast_div(off, o.inv_step);
+            bool amp_ok = __ldg(aflags + amp) == 0;
+            double tod = amp_ok ? __ldg(amps + amp) : 0.0;
+            if (!PASS2) {
+                if (lp >= 0) {
+                    key = lp;
+                    double sd = tod * scale;
+                    v0 = sd * w0;
+                    v1 = sd * wq.x;
+                    v2 = sd * wq.y;
+                }
+            } else {
+                if (amp_ok) key = amp;
+                if (amp_ok && lp != -1) {
+                    if (lp >= 0) {
+                        const double *m = binned + 3 * (int64_t)lp;
+                        double sc = 0.0; // ops_scan_map.cpp:59-64
+                        sc += w0 * __ldg(m);
+                        sc += wq.x * __ldg(m + 1);
+                        sc += wq.y * __ldg(m + 2);
+                        tod -= sc;
+                    }
+                    v0 = tod * scale;
+                }
+            }
+        }
+        if (!PASS2) {
+            Runs r = find_runs<kBinRunCap>(key, lane);
+            v0 = seg_sum<kBinRunCap>(v0, r);
+            v1 = seg_sum<kBinRunCap>(v1, r);
+            v2 = seg_sum<kBinRunCap>(v2, r);
+            if (r.is_tail && key >= 0) {
+                double *z = out + key * 3;
+                atomicAdd(z, v0);
+                atomicAdd(z + 1, v1);
+                atomicAdd(z + 2, v2);
+            }
+        } else {
+            Runs r = find_runs(key, lane);
+            v0 = seg_sum(v0, r);
+            if (r.is_tail && key >= 0) atomicAdd(out + key, v0);
+        }
+    }
+}
+
+int g_use_compact = 1; // tb_set_option("compact", 0/1)
+
+
 ObsDev make_dev(const tb_obs *obs, int regen) {
     const tb_obs_desc &d = obs->d;
     ObsDev o;
@@ -236,6 +586,10 @@ ObsDev make_dev(const tb_obs *obs, int regen) {
     o.pixels = d.pixels;
     o.weights = d.weights;
     o.hwp = d.hwp;
+    o.tiles = obs->tiles;
+    o.n_tiles = obs->n_tiles;
+    o.lpix = obs->lpix;
+    o.wqu = obs->wqu;
     if (regen) {
         TB_REQUIRE(d.boresight != nullptr && d.focalplane != nullptr,
                    "regen needs boresight and focalplane");
@@ -261,12 +615,44 @@ inline int64_t obs_blocks(const tb_obs *obs) {
         }                                                                                  \
     } while (0)
 
+// TMA needs 16-byte aligned bases (the per-tile offsets are aligned by construction)
+inline bool tma_ok(const ObsDev &o) {
+    auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return g_use_tma && o.n_tiles > 0 && al(o.pixels) && al(o.weights) &&
+           (o.solver_flags == nullptr || al(o.solver_flags));
+}
+
+template <bool PASS2>
+void launch_tma(const ObsDev &o, const double *amps, const uint8_t *aflags, const double *binned,
+                double *out, void *stream) {
+    static bool configured[2] = {false, false};
+    auto k = k_lhs_tma<PASS2>;
+    if (!configured[PASS2 ? 1 : 0]) {
+        TB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kTmaSmemBytes));
+        configured[PASS2 ? 1 : 0] = true;
+    }
+    int64_t n_work = o.n_tiles * o.n_det;
+    int64_t grid = (int64_t)tbr::sm_count() * kTmaCtasPerSm;
+    if (grid > n_work) grid = n_work;
+    if (grid <= 0) return;
+    k<<<(unsigned)grid, kThreads, kTmaSmemBytes, (cudaStream_t)stream>>>(o, amps, aflags, binned,
+                                                                          out);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+}
+
 template <bool FROM_SIGNAL>
 void launch_bin(const tb_obs *obs, const double *amps, const uint8_t *aflags, const double *signal,
                 double *zmap, int regen, void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen) {
+    if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
+        auto k = k_lhs_compact<false>;
+        TBS_LAUNCH(k, nb, stream, o, amps, aflags, nullptr, zmap);
+    } else if (!regen && !FROM_SIGNAL && tma_ok(o)) {
+        launch_tma<false>(o, amps, aflags, nullptr, zmap, stream);
+    } else if (!regen) {
         auto k = k_bin<false, true, FROM_SIGNAL>;
         TBS_LAUNCH(k, nb, stream, o, amps, aflags, signal, zmap);
     } else if (obs->d.nest) {
@@ -284,7 +670,12 @@ void launch_project(const tb_obs *obs, const double *amps, const uint8_t *aflags
                     void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen) {
+    if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
+        auto k = k_lhs_compact<true>;
+        TBS_LAUNCH(k, nb, stream, o, amps, aflags, binned, out);
+    } else if (!regen && !FROM_SIGNAL && tma_ok(o)) {
+        launch_tma<true>(o, amps, aflags, binned, out, stream);
+    } else if (!regen) {
         auto k = k_project<false, true, FROM_SIGNAL>;
         TBS_LAUNCH(k, nb, stream, o, amps, aflags, signal, binned, out);
     } else if (obs->d.nest) {
@@ -484,6 +875,25 @@ tb_obs *tb_obs_create(const tb_obs_desc *desc) {
         o->gamma = dd + 6 * nd;
         o->det_scale = dd + 7 * nd;
         o->n_amp_det = acc;
+        // tiles: each interval cut into chunks of kTmaTile samples
+        std::vector<int64_t> tt;
+        for (int64_t v = 0; v < nv; ++v) {
+            int64_t a = d.intervals[v].first, b = d.intervals[v].last;
+            for (int64_t off = 0; a + off < b; off += kTmaTile) {
+                int64_t cnt = b - (a + off);
+                if (cnt > kTmaTile) cnt = kTmaTile;
+                tt.push_back(a + off);
+                tt.push_back(off);
+                tt.push_back(cnt);
+                tt.push_back(v);
+            }
+        }
+        o->n_tiles = (int64_t)tt.size() / 4;
+        if (o->n_tiles > 0) {
+            TB_CUDA(cudaMalloc(&o->tiles, tt.size() * sizeof(int64_t)));
+            TB_CUDA(cudaMemcpy(o->tiles, tt.data(), tt.size() * sizeof(int64_t),
+                               cudaMemcpyHostToDevice));
+        }
         // the host arrays of the descriptor are not retained
         o->d.intervals = nullptr;
         o->d.epsilon = o->d.gamma = o->d.cal = o->d.det_scale = nullptr;
@@ -498,7 +908,59 @@ tb_obs *tb_obs_create(const tb_obs_desc *desc) {
 void tb_obs_destroy(tb_obs *obs) {
     if (obs == nullptr) return;
     if (obs->blob) cudaFree(obs->blob);
+    if (obs->tiles) cudaFree(obs->tiles);
+    if (obs->lpix) cudaFree(obs->lpix);
+    if (obs->wqu) cudaFree(obs->wqu);
     delete obs;
+}
+
+int tb_obs_pack_pointing(tb_obs *obs, void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs != nullptr, "NULL observation");
+    TB_REQUIRE(obs->d.pixels && obs->d.weights, "packing needs stored pixels and weights");
+    int64_t total = obs->d.n_det * obs->d.n_samp;
+    TB_REQUIRE((int64_t)obs->d.n_pix_submap * obs->d.n_submap < 2147483647LL,
+               "map too large for 32-bit local pixel indices");
+    if (obs->lpix == nullptr) {
+        TB_CUDA(cudaMalloc(&obs->lpix, sizeof(int32_t) * total));
+        TB_CUDA(cudaMalloc(&obs->wqu, sizeof(double2) * total));
+    }
+    ObsDev o = make_dev(obs, 0);
+    unsigned zero = 0;
+    TB_CUDA(cudaMemcpyToSymbolAsync(g_pack_mismatch, &zero, sizeof(zero), 0,
+                                    cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    int grid = tbr::sm_count() * 8;
+    k_pack_pointing<<<grid, kThreads, 0, (cudaStream_t)stream>>>(o, obs->lpix, obs->wqu);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+    unsigned bad = 0;
+    TB_CUDA(cudaMemcpyFromSymbolAsync(&bad, g_pack_mismatch, sizeof(bad), 0,
+                                      cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (bad) {
+        // the I weight is not the per-detector constant: keep the general kernels
+        cudaFree(obs->lpix);
+        cudaFree(obs->wqu);
+        obs->lpix = nullptr;
+        obs->wqu = nullptr;
+    }
+    TB_API_END
+}
+
+int tb_obs_has_compact_pointing(const tb_obs *obs) { return (obs && obs->lpix) ? 1 : 0; }
+
+int tb_set_option(const char *name, int value) {
+    TB_API_BEGIN
+    TB_REQUIRE(name != nullptr, "NULL option name");
+    if (std::string(name) == "tma") {
+        g_use_tma = value;
+    } else if (std::string(name) == "compact") {
+        g_use_compact = value;
+    } else {
+        throw tbr::Error{TB_ERR_ARG, std::string("unknown option: ") + name};
+    }
+    TB_API_END
 }
 
 int tb_lhs_pass1(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,

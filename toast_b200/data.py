@@ -130,7 +130,9 @@ class DetDataManager(dict):
             raise RuntimeError(f"detdata '{name}' exists with a different detector set")
         self[name] = DetectorData(detectors, shape, dtype)
         if accel:
+            # observation_data.py `ensure(..., accel=True)`: create on the device, zero-filled
             self[name].accel_create(name)
+            self[name].accel_reset(name)
         return False
 
 

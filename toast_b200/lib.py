@@ -104,6 +104,9 @@ PROTOTYPES = {
     "tb_amp_dot": (INT, [P, P, P, I64, P, P]),
     "tb_pcg_update": (INT, [P, P, P, P, P, P, P, P, P, I64, P, P]),
     "tb_pcg_direction": (INT, [P, P, P, P, I64, P]),
+    "tb_obs_pack_pointing": (INT, [P, P]),
+    "tb_obs_has_compact_pointing": (INT, [P]),
+    "tb_set_option": (INT, [STR, INT]),
     "tb_set_pixel_guard_scale": (None, [F64]),
     "tb_pixel_exact_count": (I64, [INT]),
 }

@@ -49,7 +49,7 @@ class DeviceObservation:
                  n_pix_submap, n_submap, global2local, amp_offset=0, epsilon=None, gamma=None,
                  cal=None, IAU=False, shared_flags=None, shared_flag_mask=0, solver_flags=None,
                  solver_flag_mask=255, pixels=None, weights=None, hwp=None, amp_offsets=None,
-                 device="cuda"):
+                 compact=True, device="cuda"):
         self.device = torch.device(device)
         self.lib = L.load()
         self.n_det = int(focalplane.shape[0])
@@ -66,6 +66,8 @@ class DeviceObservation:
         self.global2local = np.ascontiguousarray(global2local, dtype=np.int64)
         self.shared_flag_mask = int(shared_flag_mask)
         self.solver_flag_mask = int(solver_flag_mask)
+        # keep a compact (20 B/sample) copy of the stored pointing for the LHS passes
+        self.compact = bool(compact)
 
         # Offset amplitude layout
         nav = []
@@ -160,7 +162,12 @@ class DeviceObservation:
         if not h:
             raise RuntimeError(L.last_error())
         self._handle = _ObsHandle(self.lib, h)
+        if self.compact and self.pixels is not None and self.weights is not None:
+            L.check(self.lib.tb_obs_pack_pointing(h, None))
         return self._handle
+
+    def has_compact_pointing(self):
+        return bool(self.lib.tb_obs_has_compact_pointing(self.handle().h))
 
     def bytes_per_sample_stored(self):
         return 8 + 24 + (1 if self.solver_flags is not None else 0)
