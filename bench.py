@@ -395,9 +395,7 @@ def main_gpu(args):
                                  L.ptr(ds.zmap), ds.regen, None))
         if timers is not None:
             e[1].record()
-        ds._allreduce(ds.zmap)
-        L.check(lib.tb_cov_apply_diag(ds.n_local_submap, ds.n_pix_submap, 3, L.ptr(ds.cov),
-                                      L.ptr(ds.zmap), L.TB_MEM_DEVICE, None))
+        ds.reduce_and_apply_cov()
         st.q.zero_()
         if timers is not None:
             e[2].record()
@@ -434,6 +432,7 @@ def main_gpu(args):
     ms_step = ms_total / max(args.steps, 1)
     p1 = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))
     p2 = float(np.mean([e[2].elapsed_time(e[3]) for e in timers]))
+    pr = float(np.mean([e[1].elapsed_time(e[2]) for e in timers]))
 
     # ---- end to end: the LHS through the host-facing call, amplitudes in pinned host memory ----
     d_host = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -462,9 +461,9 @@ def main_gpu(args):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_step, ms_e2e, p1, p2], dtype=torch.float64, device=device)
+        t = torch.tensor([ms_step, ms_e2e, p1, p2, pr], dtype=torch.float64, device=device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms_step, ms_e2e, p1, p2 = [float(x) for x in t.tolist()]
+        ms_step, ms_e2e, p1, p2, pr = [float(x) for x in t.tolist()]
         cnt = torch.tensor([info["det_samples"]], dtype=torch.float64, device=device)
         torch.distributed.all_reduce(cnt)
         total_samples = float(cnt.item())
@@ -496,7 +495,13 @@ def main_gpu(args):
                 "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "pass1_ms": p1, "pass2_ms": p2,
+                "pass1_ms": p1, "pass2_ms": p2, "reduce_cov_ms": pr,
+                "map_reduction": "fused P2P reduce-scatter + cov + all-gather kernel"
+                                 if ds.peer is not None else
+                                 ("NCCL all-reduce + cov_apply" if world > 1 else "cov_apply"),
+                "zmap_bytes": int(ds.zmap.numel() * 8),
+                "streamed_bytes_per_sample_per_pass": 20 if dobs.has_compact_pointing()
+                and not args.regen else (1 if args.regen else 33),
                 "iteration_effective_gbs_per_gpu": iter_gbs,
                 "iteration_frac_of_peak": iter_gbs / peak,
             },

@@ -287,6 +287,22 @@ int tb_rhs_project(const tb_obs *obs, const double *signal, const uint8_t *amp_f
 int tb_bin_signal(const tb_obs *obs, const double *signal, double *zmap, int regen,
                   void *stream);
 
+/* ---- a6 fused with its collective: map reduction + covariance over NVLink peer memory ------
+ * Replaces  accel_update_host -> PixelData.sync_allreduce (MPI) -> accel_update_device ->
+ * covariance_apply  (ops/mapmaker_utils/mapmaker_utils.py:885-925, pixels.py:710-779,
+ * covariance.py:262-306) by ONE kernel per GPU: P2P reduce-scatter of the map slice this rank
+ * owns, 3x3 covariance product on that slice, P2P all-gather into every rank's map, bracketed by
+ * device-side flag barriers.  The map buffer is allocated by the library (peer-visible through
+ * CUDA IPC); handles are 128 bytes per rank and are exchanged by the caller (any transport).   */
+typedef struct tb_peer tb_peer;
+tb_peer *tb_peer_create(int rank, int world, size_t map_bytes);
+int tb_peer_get_handles(tb_peer *peer, void *out128);
+int tb_peer_open(tb_peer *peer, const void *all_handles /* world x 128 bytes, by rank */);
+void *tb_peer_map_ptr(tb_peer *peer);
+/* n_pix = n_local_submap * n_pix_submap (multiple of 1024); cov [n_pix,6] device pointer. */
+int tb_map_reduce_cov(tb_peer *peer, int64_t n_pix, const double *cov, void *stream);
+void tb_peer_destroy(tb_peer *peer);
+
 /* ---- a12/a13  amplitude-vector arithmetic for the PCG loop (templates/amplitudes.py:201-274,
  * :523-571; ops/mapmaker_solve.py:665-746).  All DEVICE pointers; scalars live on the device
  * so an iteration needs no host round trip.                                                 */

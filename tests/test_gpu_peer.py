@@ -1,0 +1,107 @@
+"""GPU tests of the fused map-reduction + covariance kernel (tb_map_reduce_cov).
+
+world = 1 runs on any GPU box (the kernel degenerates to cov_apply over its own buffer); the
+2-rank test spawns two processes when the box has two GPUs and compares the NVLink peer-memory
+path with NCCL all-reduce + cov_apply."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H  # noqa: F401
+from helpers import O, S
+from toast_b200 import kernels as KC
+from toast_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def test_single_rank_reduce_cov_equals_cov_apply():
+    lib = L.load()
+    n_loc, nps = 5, 3072
+    n_pix = n_loc * nps
+    rng = np.random.default_rng(2)
+    cov = rng.standard_normal((n_pix, 6))
+    z = rng.standard_normal((n_pix, 3))
+    h = lib.tb_peer_create(0, 1, n_pix * 24)
+    assert h
+    try:
+        from toast_b200.solver import _CudaView
+
+        t = torch.as_tensor(_CudaView(lib.tb_peer_map_ptr(h), n_pix * 3), device="cuda")
+        t.copy_(torch.from_numpy(z.reshape(-1)))
+        cov_d = torch.from_numpy(cov).cuda()
+        L.check(lib.tb_map_reduce_cov(h, n_pix, L.ptr(cov_d), None))
+        L.check(lib.tb_map_reduce_cov(h, n_pix, L.ptr(cov_d), None))  # twice: epochs advance
+        got = t.cpu().numpy().reshape(n_pix, 3)
+    finally:
+        lib.tb_peer_destroy(h)
+    ref = z.reshape(-1).copy()
+    O.cov_apply_diag(n_loc, nps, 3, cov.reshape(-1), ref)
+    O.cov_apply_diag(n_loc, nps, 3, cov.reshape(-1), ref)
+    np.testing.assert_array_equal(got, ref.reshape(n_pix, 3))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from toast_b200.solver import PeerMap
+
+        n_loc, nps = 7, 3072
+        n_pix = n_loc * nps
+        g = torch.Generator(device="cuda")
+        g.manual_seed(100 + rank)
+        z = torch.randn(n_pix * 3, generator=g, device="cuda", dtype=torch.float64)
+        g.manual_seed(5)
+        cov = torch.randn(n_pix * 6, generator=g, device="cuda", dtype=torch.float64)
+        # NCCL path
+        ref = z.clone()
+        dist.all_reduce(ref)
+        KC.cov_apply_diag(n_loc, nps, 3, cov, ref)
+        # fused peer path, three rounds to exercise the epoch barriers
+        pm = PeerMap(n_pix, torch.device("cuda", rank))
+        err = 0.0
+        for _ in range(3):
+            pm.tensor.copy_(z)
+            pm.reduce_cov(cov)
+            torch.cuda.synchronize()
+            err = max(err, float((pm.tensor - ref).abs().max() / ref.abs().max()))
+        dist.barrier()
+        if rank == 0:
+            out.put(err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_peer_reduction_matches_nccl():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-14

@@ -1,0 +1,250 @@
+// tb_peer.cu -- the map reduction of the destriper fused with the pixel-covariance product,
+// over NVLink peer memory.
+//
+// Reference flow per PCG iteration (ops/mapmaker_utils/mapmaker_utils.py:885-925,
+// pixels.py:710-779, covariance.py:262-306): copy zmap to the host, MPI all-reduce it, copy it
+// back, then run cov_apply over EVERY pixel on EVERY process.  Here one kernel per GPU does
+//     reduce-scatter  (sum my slice of the map over all peers with P2P loads)
+//  -> covariance apply on that slice only (1/N of the pixels)
+//  -> all-gather      (P2P stores of the finished slice into every peer's map)
+// with device-side flag barriers before and after, so nothing else is launched and the
+// reduction never leaves the NVLink domain.  Map buffers live in cudaMalloc memory shared
+// between the ranks' processes through CUDA IPC handles.
+#include "tb_device.cuh"
+#include "tb_runtime.cuh"
+
+constexpr int kMaxPeers = 16;
+constexpr int kPeerTile = 1024;            // pixels per tile (3072 doubles = 24 KB of smem)
+constexpr int kPeerThreads = 256;
+
+struct tb_peer {
+    int rank = 0, world = 1;
+    size_t map_bytes = 0;
+    double *map = nullptr;                 // my map buffer (peer-visible)
+    unsigned long long *flags = nullptr;   // [2][kMaxPeers] arrival / done flags (peer-visible)
+    double *peer_map[kMaxPeers] = {};
+    unsigned long long *peer_flags[kMaxPeers] = {};
+    unsigned int *counter = nullptr;       // local block counter
+    unsigned long long epoch = 0;
+    bool opened = false;
+};
+
+namespace {
+
+struct PeerArgs {
+    double *map[kMaxPeers];
+    unsigned long long *flags[kMaxPeers];
+    int rank, world;
+    unsigned long long epoch;
+    unsigned int *counter;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One CTA per tile of 1024 pixels of MY slice.
+__global__ void __launch_bounds__(kPeerThreads)
+k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *__restrict__ cov) {
+    __shared__ double2 sh[kPeerTile * 3 / 2]; // 1536 x 16 B = 24 KB
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+
+    // ---- start barrier: every rank has finished writing its local map (pass 1) ------------
+    if (blockIdx.x == 0 && tid < a.world) {
+        __threadfence_system();
+        st_release_sys(a.flags[tid] + a.rank, a.epoch); // row 0: "my map is ready"
+    }
+    if (tid < a.world) {
+        const unsigned long long *f = a.flags[a.rank] + tid;
+        while (ld_acquire_sys(f) < a.epoch) {
+        }
+    }
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t e0 = (tile_first + tile) * (int64_t)(kPeerTile * 3 / 2); // double2 index
+        // reduce: flat, fully coalesced 16-byte peer loads, all issued before the adds
+        double2 acc[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] = make_double2(0.0, 0.0);
+        for (int q = 0; q < a.world; ++q) {
+            const double2 *src = reinterpret_cast<const double2 *>(a.map[q]) + e0;
+            double2 v[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[k] = __ldcv(src + k * kPeerThreads + tid);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                acc[k].x += v[k].x;
+                acc[k].y += v[k].y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sh[k * kPeerThreads + tid] = acc[k];
+        __syncthreads();
+        // covariance apply: thread t owns pixels 4t .. 4t+3 of the tile
+        {
+            double *z = reinterpret_cast<double *>(sh) + 12 * tid;
+            const double *c = cov + ((tile_first + tile) * (int64_t)kPeerTile + 4 * tid) * 6;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const double *m = c + 6 * p;
+                double v0 = z[3 * p], v1 = z[3 * p + 1], v2 = z[3 * p + 2];
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0; // order of toast_map_cov.cpp:509-517
+                t0 += __ldg(m) * v0;
+                t0 += __ldg(m + 1) * v1;
+                t1 += __ldg(m + 1) * v0;
+                t0 += __ldg(m + 2) * v2;
+                t2 += __ldg(m + 2) * v0;
+                t1 += __ldg(m + 3) * v1;
+                t1 += __ldg(m + 4) * v2;
+                t2 += __ldg(m + 4) * v1;
+                t2 += __ldg(m + 5) * v2;
+                z[3 * p] = t0;
+                z[3 * p + 1] = t1;
+                z[3 * p + 2] = t2;
+            }
+        }
+        __syncthreads();
+        // all-gather: coalesced 16-byte stores of the finished tile into every peer's map
+        double2 r[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[k] = sh[k * kPeerThreads + tid];
+        for (int q = 0; q < a.world; ++q) {
+            double2 *dst = reinterpret_cast<double2 *>(a.map[q]) + e0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dst[k * kPeerThreads + tid] = r[k];
+        }
+        __syncthreads();
+    }
+
+    // ---- end barrier: every rank's slice has landed in my map ------------------------------
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int done = atomicAdd(a.counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        if (tid < a.world) {
+            __threadfence_system();
+            st_release_sys(a.flags[tid] + kMaxPeers + a.rank, a.epoch); // row 1: "I am done"
+            const unsigned long long *f = a.flags[a.rank] + kMaxPeers + tid;
+            while (ld_acquire_sys(f) < a.epoch) {
+            }
+        }
+        if (tid == 0) *a.counter = 0u;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+tb_peer *tb_peer_create(int rank, int world, size_t map_bytes) {
+    try {
+        tbr::require_device();
+        TB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+                   "bad rank / world size");
+        tb_peer *p = new tb_peer();
+        p->rank = rank;
+        p->world = world;
+        p->map_bytes = map_bytes;
+        TB_CUDA(cudaMalloc(&p->map, map_bytes ? map_bytes : 16));
+        TB_CUDA(cudaMemset(p->map, 0, map_bytes ? map_bytes : 16));
+        TB_CUDA(cudaMalloc(&p->flags, sizeof(unsigned long long) * 2 * kMaxPeers));
+        TB_CUDA(cudaMemset(p->flags, 0, sizeof(unsigned long long) * 2 * kMaxPeers));
+        TB_CUDA(cudaMalloc(&p->counter, sizeof(unsigned int)));
+        TB_CUDA(cudaMemset(p->counter, 0, sizeof(unsigned int)));
+        p->peer_map[rank] = p->map;
+        p->peer_flags[rank] = p->flags;
+        if (world == 1) p->opened = true;
+        return p;
+    } catch (const tbr::Error &e) {
+        tbr::set_error(e.code, e.msg);
+        return nullptr;
+    }
+}
+
+// out: 2 x 64 bytes (IPC handles of the map and flag buffers)
+int tb_peer_get_handles(tb_peer *p, void *out) {
+    TB_API_BEGIN
+    TB_REQUIRE(p && out, "NULL argument");
+    cudaIpcMemHandle_t h[2];
+    TB_CUDA(cudaIpcGetMemHandle(&h[0], p->map));
+    TB_CUDA(cudaIpcGetMemHandle(&h[1], p->flags));
+    memcpy(out, h, sizeof(h));
+    TB_API_END
+}
+
+// all: world x 128 bytes, rank-ordered
+int tb_peer_open(tb_peer *p, const void *all) {
+    TB_API_BEGIN
+    TB_REQUIRE(p && all, "NULL argument");
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all);
+    for (int q = 0; q < p->world; ++q) {
+        if (q == p->rank) continue;
+        void *m = nullptr, *f = nullptr;
+        TB_CUDA(cudaIpcOpenMemHandle(&m, h[2 * q], cudaIpcMemLazyEnablePeerAccess));
+        TB_CUDA(cudaIpcOpenMemHandle(&f, h[2 * q + 1], cudaIpcMemLazyEnablePeerAccess));
+        p->peer_map[q] = (double *)m;
+        p->peer_flags[q] = (unsigned long long *)f;
+    }
+    p->opened = true;
+    TB_API_END
+}
+
+void *tb_peer_map_ptr(tb_peer *p) { return p ? p->map : nullptr; }
+
+// binned = cov . sum_over_ranks(zmap), result in every rank's map buffer.  nnz = 3.
+int tb_map_reduce_cov(tb_peer *p, int64_t n_pix, const double *cov, void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(p && p->opened, "peer buffers are not opened");
+    TB_REQUIRE(n_pix % kPeerTile == 0, "n_pix must be a multiple of 1024");
+    TB_REQUIRE((size_t)n_pix * 24 <= p->map_bytes, "map buffer too small");
+    int64_t tiles = n_pix / kPeerTile;
+    int64_t per = (tiles + p->world - 1) / p->world;
+    int64_t first = per * p->rank;
+    int64_t mine = tiles - first;
+    if (mine > per) mine = per;
+    if (mine < 0) mine = 0;
+    PeerArgs a;
+    for (int q = 0; q < kMaxPeers; ++q) {
+        a.map[q] = p->peer_map[q];
+        a.flags[q] = p->peer_flags[q];
+    }
+    a.rank = p->rank;
+    a.world = p->world;
+    a.epoch = ++p->epoch;
+    a.counter = p->counter;
+    int64_t grid = mine < 1 ? 1 : mine;
+    int64_t cap = (int64_t)tbr::sm_count() * 4;
+    if (grid > cap) grid = cap;
+    k_map_reduce_cov<<<(unsigned)grid, kPeerThreads, 0, (cudaStream_t)stream>>>(a, first, mine,
+                                                                                cov);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+    TB_API_END
+}
+
+void tb_peer_destroy(tb_peer *p) {
+    if (!p) return;
+    for (int q = 0; q < p->world; ++q) {
+        if (q == p->rank) continue;
+        if (p->peer_map[q]) cudaIpcCloseMemHandle(p->peer_map[q]);
+        if (p->peer_flags[q]) cudaIpcCloseMemHandle(p->peer_flags[q]);
+    }
+    if (p->map) cudaFree(p->map);
+    if (p->flags) cudaFree(p->flags);
+    if (p->counter) cudaFree(p->counter);
+    delete p;
+}
+
+} // extern "C"

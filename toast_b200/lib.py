@@ -101,6 +101,12 @@ PROTOTYPES = {
     "tb_lhs_pass2": (INT, [P, P, P, P, P, INT, P]),
     "tb_rhs_project": (INT, [P, P, P, P, P, INT, P]),
     "tb_bin_signal": (INT, [P, P, P, INT, P]),
+    "tb_peer_create": (P, [INT, INT, SZ]),
+    "tb_peer_get_handles": (INT, [P, P]),
+    "tb_peer_open": (INT, [P, P]),
+    "tb_peer_map_ptr": (P, [P]),
+    "tb_map_reduce_cov": (INT, [P, I64, P, P]),
+    "tb_peer_destroy": (None, [P]),
     "tb_amp_dot": (INT, [P, P, P, I64, P, P]),
     "tb_pcg_update": (INT, [P, P, P, P, P, P, P, P, P, I64, P, P]),
     "tb_pcg_direction": (INT, [P, P, P, P, I64, P]),

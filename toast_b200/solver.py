@@ -184,6 +184,49 @@ class _ObsHandle:
             pass
 
 
+class _CudaView:
+    """Expose a raw device allocation to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class PeerMap:
+    """A map buffer visible to every rank of the node over NVLink (CUDA IPC) and the fused
+    reduce-scatter -> covariance -> all-gather kernel on it (``tb_map_reduce_cov``).  Replaces
+    ``PixelData.sync_allreduce`` + ``covariance_apply`` of the reference."""
+
+    def __init__(self, n_pix, device, group=None):
+        import torch.distributed as dist
+
+        self.lib = L.load()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n_pix = int(n_pix)
+        nbytes = self.n_pix * 3 * 8
+        self.h = self.lib.tb_peer_create(self.rank, self.world, nbytes)
+        if not self.h:
+            raise RuntimeError(L.last_error())
+        buf = ct.create_string_buffer(128)
+        L.check(self.lib.tb_peer_get_handles(self.h, buf))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, buf.raw, group=group)
+        L.check(self.lib.tb_peer_open(self.h, b"".join(handles)))
+        ptr = self.lib.tb_peer_map_ptr(self.h)
+        self.tensor = torch.as_tensor(_CudaView(ptr, self.n_pix * 3), device=device)
+        dist.barrier(group=group)
+
+    def reduce_cov(self, cov):
+        L.check(self.lib.tb_map_reduce_cov(self.h, self.n_pix, L.ptr(cov), None))
+
+    def __del__(self):
+        try:
+            self.lib.tb_peer_destroy(self.h)
+        except Exception:
+            pass
+
+
 class Destriper:
     """Fused SolverRHS / SolverLHS / solve() for one or more device observations.
 
@@ -192,7 +235,7 @@ class Destriper:
     recomputes pointing inside every pass instead of reading stored pixels/weights."""
 
     def __init__(self, observations, n_local_submap, n_pix_submap, cov, offset_var, amp_flags,
-                 regen=False, group=None, device="cuda"):
+                 regen=False, group=None, device="cuda", fused_reduce=True):
         self.obs = list(observations)
         self.device = torch.device(device)
         self.lib = L.load()
@@ -204,12 +247,28 @@ class Destriper:
         self.amp_flags = _dev_tensor(amp_flags, self.device, torch.uint8)
         self.n_amp = int(self.offset_var.numel())
         assert sum(o.n_amp for o in self.obs) == self.n_amp
-        self.zmap = torch.zeros((self.n_local_submap, self.n_pix_submap, 3), dtype=torch.float64,
-                                device=self.device)
         self._scal = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(group)
+        # Multi-GPU: keep the map in NVLink-peer-visible memory and reduce it with the fused
+        # kernel; fall back to NCCL all-reduce + cov_apply if peer memory cannot be set up.
+        self.peer = None
+        n_pix = self.n_local_submap * self.n_pix_submap
+        import os as _os
+        if self.world > 1 and fused_reduce and _os.environ.get("TB_FUSED_REDUCE", "1") != "0":
+            try:
+                self.peer = PeerMap(n_pix, self.device, group)
+            except Exception as exc:  # noqa: BLE001
+                import warnings
+
+                warnings.warn(f"peer-memory map reduction unavailable ({exc}); using NCCL")
+                self.peer = None
+        if self.peer is not None:
+            self.zmap = self.peer.tensor.view(self.n_local_submap, self.n_pix_submap, 3)
+        else:
+            self.zmap = torch.zeros((self.n_local_submap, self.n_pix_submap, 3),
+                                    dtype=torch.float64, device=self.device)
 
     # -- collectives ----------------------------------------------------------------------------
     def _allreduce(self, t):
@@ -217,16 +276,25 @@ class Destriper:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     # -- building blocks ------------------------------------------------------------------------
+    def reduce_and_apply_cov(self):
+        """zmap <- cov . sum_over_ranks(zmap): the collective of the path and the step after it
+        (mapmaker_utils.py:885-925 + covariance.py:262-306), fused over NVLink peer memory when
+        there is more than one rank."""
+        if self.peer is not None:
+            self.peer.reduce_cov(self.cov)
+            return
+        self._allreduce(self.zmap)
+        L.check(self.lib.tb_cov_apply_diag(self.n_local_submap, self.n_pix_submap, 3,
+                                           L.ptr(self.cov), L.ptr(self.zmap), L.TB_MEM_DEVICE,
+                                           None))
+
     def bin_amplitudes(self, amps):
         """binned = cov * allreduce(P^T N^-1 F a)   (BinMap with pre_process=TemplateMatrix)."""
         self.zmap.zero_()
         for o in self.obs:
             L.check(self.lib.tb_lhs_pass1(o.handle().h, L.ptr(amps), L.ptr(self.amp_flags),
                                           L.ptr(self.zmap), self.regen, None))
-        self._allreduce(self.zmap)
-        L.check(self.lib.tb_cov_apply_diag(self.n_local_submap, self.n_pix_submap, 3,
-                                           L.ptr(self.cov), L.ptr(self.zmap), L.TB_MEM_DEVICE,
-                                           None))
+        self.reduce_and_apply_cov()
         return self.zmap
 
     def bin_signal(self, signals):
@@ -235,10 +303,7 @@ class Destriper:
         for o, sig in zip(self.obs, signals):
             L.check(self.lib.tb_bin_signal(o.handle().h, L.ptr(sig), L.ptr(self.zmap), self.regen,
                                            None))
-        self._allreduce(self.zmap)
-        L.check(self.lib.tb_cov_apply_diag(self.n_local_submap, self.n_pix_submap, 3,
-                                           L.ptr(self.cov), L.ptr(self.zmap), L.TB_MEM_DEVICE,
-                                           None))
+        self.reduce_and_apply_cov()
         return self.zmap
 
     def lhs(self, amps_in, amps_out):
