@@ -299,7 +299,7 @@ tb_peer *tb_peer_create(int rank, int world, size_t map_bytes);
 int tb_peer_get_handles(tb_peer *peer, void *out128);
 int tb_peer_open(tb_peer *peer, const void *all_handles /* world x 128 bytes, by rank */);
 void *tb_peer_map_ptr(tb_peer *peer);
-/* n_pix = n_local_submap * n_pix_submap (multiple of 1024); cov [n_pix,6] device pointer. */
+/* n_pix = n_local_submap * n_pix_submap (multiple of 256); cov [n_pix,6] device pointer. */
 int tb_map_reduce_cov(tb_peer *peer, int64_t n_pix, const double *cov, void *stream);
 void tb_peer_destroy(tb_peer *peer);
 

@@ -14,8 +14,9 @@
 #include "tb_runtime.cuh"
 
 constexpr int kMaxPeers = 16;
-constexpr int kPeerTile = 1024;            // pixels per tile (3072 doubles = 24 KB of smem)
-constexpr int kPeerThreads = 256;
+constexpr int kPeerTile = 256;             // pixels per tile (768 doubles = 6 KB of smem)
+constexpr int kPeerThreads = 128;
+constexpr int kPeerPer = 3;                // double2 per thread per tile (128 x 3 x 2 = 768)
 
 struct tb_peer {
     int rank = 0, world = 1;
@@ -48,19 +49,23 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// One CTA per tile of 1024 pixels of MY slice.
+// One CTA per tile of 256 pixels of MY slice; several CTAs per SM so that the load, compute and
+// store phases of different tiles overlap.  WORLD > 0 unrolls the peer loop so that the loads
+// from ALL peers are in flight together (peer-load latency is ~2-4 us).
+template <int WORLD>
 __global__ void __launch_bounds__(kPeerThreads)
 k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *__restrict__ cov) {
-    __shared__ double2 sh[kPeerTile * 3 / 2]; // 1536 x 16 B = 24 KB
+    __shared__ double2 sh[kPeerTile * 3 / 2];
     __shared__ bool is_last;
     const int tid = threadIdx.x;
+    const int world = WORLD > 0 ? WORLD : a.world;
 
     // ---- start barrier: every rank has finished writing its local map (pass 1) ------------
-    if (blockIdx.x == 0 && tid < a.world) {
+    if (blockIdx.x == 0 && tid < world) {
         __threadfence_system();
         st_release_sys(a.flags[tid] + a.rank, a.epoch); // row 0: "my map is ready"
     }
-    if (tid < a.world) {
+    if (tid < world) {
         const unsigned long long *f = a.flags[a.rank] + tid;
         while (ld_acquire_sys(f) < a.epoch) {
         }
@@ -69,30 +74,45 @@ k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t e0 = (tile_first + tile) * (int64_t)(kPeerTile * 3 / 2); // double2 index
-        // reduce: flat, fully coalesced 16-byte peer loads, all issued before the adds
-        double2 acc[6];
+        double2 acc[kPeerPer];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) acc[k] = make_double2(0.0, 0.0);
-        for (int q = 0; q < a.world; ++q) {
-            const double2 *src = reinterpret_cast<const double2 *>(a.map[q]) + e0;
-            double2 v[6];
+        for (int k = 0; k < kPeerPer; ++k) acc[k] = make_double2(0.0, 0.0);
+        if (WORLD > 0) {
+            double2 v[WORLD > 0 ? WORLD : 1][kPeerPer];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) v[k] = __ldcv(src + k * kPeerThreads + tid);
+            for (int q = 0; q < WORLD; ++q) {
+                const double2 *src = reinterpret_cast<const double2 *>(a.map[q]) + e0;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                acc[k].x += v[k].x;
-                acc[k].y += v[k].y;
+                for (int k = 0; k < kPeerPer; ++k) v[q][k] = __ldcv(src + k * kPeerThreads + tid);
+            }
+#pragma unroll
+            for (int q = 0; q < WORLD; ++q) {
+#pragma unroll
+                for (int k = 0; k < kPeerPer; ++k) {
+                    acc[k].x += v[q][k].x;
+                    acc[k].y += v[q][k].y;
+                }
+            }
+        } else {
+            for (int q = 0; q < world; ++q) {
+                const double2 *src = reinterpret_cast<const double2 *>(a.map[q]) + e0;
+#pragma unroll
+                for (int k = 0; k < kPeerPer; ++k) {
+                    double2 u = __ldcv(src + k * kPeerThreads + tid);
+                    acc[k].x += u.x;
+                    acc[k].y += u.y;
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) sh[k * kPeerThreads + tid] = acc[k];
+        for (int k = 0; k < kPeerPer; ++k) sh[k * kPeerThreads + tid] = acc[k];
         __syncthreads();
-        // covariance apply: thread t owns pixels 4t .. 4t+3 of the tile
+        // covariance apply: thread t owns pixels 2t, 2t+1 of the tile
         {
-            double *z = reinterpret_cast<double *>(sh) + 12 * tid;
-            const double *c = cov + ((tile_first + tile) * (int64_t)kPeerTile + 4 * tid) * 6;
+            double *z = reinterpret_cast<double *>(sh) + 6 * tid;
+            const double *c = cov + ((tile_first + tile) * (int64_t)kPeerTile + 2 * tid) * 6;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < 2; ++p) {
                 const double *m = c + 6 * p;
                 double v0 = z[3 * p], v1 = z[3 * p + 1], v2 = z[3 * p + 2];
                 double t0 = 0.0, t1 = 0.0, t2 = 0.0; // order of toast_map_cov.cpp:509-517
@@ -112,13 +132,16 @@ k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *
         }
         __syncthreads();
         // all-gather: coalesced 16-byte stores of the finished tile into every peer's map
-        double2 r[6];
+        double2 r[kPeerPer];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) r[k] = sh[k * kPeerThreads + tid];
-        for (int q = 0; q < a.world; ++q) {
-            double2 *dst = reinterpret_cast<double2 *>(a.map[q]) + e0;
+        for (int k = 0; k < kPeerPer; ++k) r[k] = sh[k * kPeerThreads + tid];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) dst[k * kPeerThreads + tid] = r[k];
+        for (int q = 0; q < (WORLD > 0 ? WORLD : kMaxPeers); ++q) {
+            if (q < world) {
+                double2 *dst = reinterpret_cast<double2 *>(a.map[q]) + e0;
+#pragma unroll
+                for (int k = 0; k < kPeerPer; ++k) dst[k * kPeerThreads + tid] = r[k];
+            }
         }
         __syncthreads();
     }
@@ -132,7 +155,7 @@ k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *
     }
     __syncthreads();
     if (is_last) {
-        if (tid < a.world) {
+        if (tid < world) {
             __threadfence_system();
             st_release_sys(a.flags[tid] + kMaxPeers + a.rank, a.epoch); // row 1: "I am done"
             const unsigned long long *f = a.flags[a.rank] + kMaxPeers + tid;
@@ -207,7 +230,7 @@ int tb_map_reduce_cov(tb_peer *p, int64_t n_pix, const double *cov, void *stream
     TB_API_BEGIN
     tbr::require_device();
     TB_REQUIRE(p && p->opened, "peer buffers are not opened");
-    TB_REQUIRE(n_pix % kPeerTile == 0, "n_pix must be a multiple of 1024");
+    TB_REQUIRE(n_pix % kPeerTile == 0, "n_pix must be a multiple of 256");
     TB_REQUIRE((size_t)n_pix * 24 <= p->map_bytes, "map buffer too small");
     int64_t tiles = n_pix / kPeerTile;
     int64_t per = (tiles + p->world - 1) / p->world;
@@ -225,10 +248,15 @@ int tb_map_reduce_cov(tb_peer *p, int64_t n_pix, const double *cov, void *stream
     a.epoch = ++p->epoch;
     a.counter = p->counter;
     int64_t grid = mine < 1 ? 1 : mine;
-    int64_t cap = (int64_t)tbr::sm_count() * 4;
+    int64_t cap = (int64_t)tbr::sm_count() * 12;
     if (grid > cap) grid = cap;
-    k_map_reduce_cov<<<(unsigned)grid, kPeerThreads, 0, (cudaStream_t)stream>>>(a, first, mine,
-                                                                                cov);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p->world) {
+    case 2: k_map_reduce_cov<2><<<(unsigned)grid, kPeerThreads, 0, st>>>(a, first, mine, cov); break;
+    case 4: k_map_reduce_cov<4><<<(unsigned)grid, kPeerThreads, 0, st>>>(a, first, mine, cov); break;
+    case 8: k_map_reduce_cov<8><<<(unsigned)grid, kPeerThreads, 0, st>>>(a, first, mine, cov); break;
+    default: k_map_reduce_cov<0><<<(unsigned)grid, kPeerThreads, 0, st>>>(a, first, mine, cov);
+    }
     TB_CUDA(cudaGetLastError());
     tbr::count_launch();
     TB_API_END
