@@ -384,8 +384,11 @@ def main_gpu(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     history = []
 
-    def step(timers=None):
-        # one PCG iteration; `timers` collects (start, end) events of the two passes
+    host_sums = torch.zeros(2, dtype=torch.float64).pin_memory()
+    ev_sums = torch.cuda.Event()
+
+    def lhs_and_dot(timers=None):
+        # q = A d (pass 1, map reduction + covariance, pass 2) and d.q
         if timers is not None:
             e = [ev() for _ in range(4)]
         ds.zmap.zero_()
@@ -405,13 +408,20 @@ def main_gpu(args):
             e[3].record()
             timers.append(e)
         ds.dot(st.d, st.q, st.dq)
-        L.check(lib.tb_pcg_update(L.ptr(st.delta), L.ptr(st.dq), L.ptr(st.x), L.ptr(st.r),
-                                  L.ptr(st.d), L.ptr(st.q), L.ptr(st.s), L.ptr(ds.offset_var),
-                                  L.ptr(ds.amp_flags), n, L.ptr(st.sums), None))
-        ds._allreduce(st.sums)
-        history.append(float(st.sums[0].item()) / sqsum_init)  # host convergence test
-        ds.advance_direction(st)
 
+    def step(timers=None):
+        # One PCG iteration exactly as Destriper.solve runs it: x/r/s update + r.r, s.r of the
+        # current iteration, then -- while the host reads r.r back for the convergence test --
+        # the new direction and the NEXT iteration's LHS (both passes + reduction) and d.q.
+        ds.update(st)
+        host_sums.copy_(st.sums, non_blocking=True)
+        ev_sums.record()
+        ds.advance_direction(st)
+        lhs_and_dot(timers)
+        ev_sums.synchronize()
+        history.append(float(host_sums[0]) / sqsum_init)  # host convergence test
+
+    lhs_and_dot()  # the LHS of the first iteration (prologue of the pipelined loop)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # sampled under load: warm-up + timed region + e2e region
@@ -478,7 +488,20 @@ def main_gpu(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else \
             "fallback 6650 GB/s (B200_PROFILING.md)"
-        dom, dom_ms = ("k_bin (pass 1)", p1) if p1 >= p2 else ("k_project (pass 2)", p2)
+        compact = dobs.has_compact_pointing() and not args.regen
+        if compact:
+            names = ("k_lhs_compact<0> (pass 1: template -> noise-weighted map)",
+                     "k_lhs_compact<1> (pass 2: scan - weight - project)")
+        elif args.regen:
+            names = ("k_bin<REGEN> (pass 1)", "k_project<REGEN> (pass 2)")
+        else:
+            names = ("k_bin (pass 1)", "k_project (pass 2)")
+        dom, dom_ms = (names[0], p1) if p1 >= p2 else (names[1], p2)
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+        # `ncu --set full` capture of THIS workload (profiles/r1_ncu_passes.txt); null otherwise
+        traffic = None
+        if compact and args.workload == "c4" and args.scale == 1.0 and world == 1:
+            traffic = 8.226e9 if p1 >= p2 else 7.449e9
         alg_bytes = info["det_samples"] * BYTES_PER_SAMPLE_PASS
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         iter_gbs = info["det_samples"] * BYTES_PER_SAMPLE_ITER / (ms_step * 1e-3) / 1e9
@@ -493,7 +516,7 @@ def main_gpu(args):
                                    "flagged_fraction": round(info["flagged_fraction"], 4)}),
             "roofline": {
                 "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "pass1_ms": p1, "pass2_ms": p2, "reduce_cov_ms": pr,
                 "map_reduction": "fused P2P reduce-scatter + cov + all-gather kernel"

@@ -329,17 +329,25 @@ class Destriper:
                                     L.ptr(out), None))
         self._allreduce(out)
 
-    # -- one PCG iteration (everything after the convergence test of the previous one) ------------
-    def iteration(self, st):
-        """Advance the PCG state ``st`` by one iteration; returns nothing, leaves
-        r.r in st.sums[0] on the device."""
+    # -- PCG --------------------------------------------------------------------------------------
+    def lhs_and_dot(self, st):
+        """q = A d and d.q (device scalars): the expensive, state-preserving half of an
+        iteration (does not touch x or r)."""
         self.lhs(st.d, st.q)
         self.dot(st.d, st.q, st.dq)
+
+    def update(self, st):
+        """alpha = delta / d.q; x += alpha d; r -= alpha q; s = M^-1 r; sums = (r.r, s.r)."""
         L.check(self.lib.tb_pcg_update(L.ptr(st.delta), L.ptr(st.dq), L.ptr(st.x), L.ptr(st.r),
                                        L.ptr(st.d), L.ptr(st.q), L.ptr(st.s),
                                        L.ptr(self.offset_var), L.ptr(self.amp_flags), self.n_amp,
                                        L.ptr(st.sums), None))
         self._allreduce(st.sums)
+
+    def iteration(self, st):
+        """One full PCG iteration in the reference's order (mapmaker_solve.py:665-694)."""
+        self.lhs_and_dot(st)
+        self.update(st)
 
     def advance_direction(self, st):
         # delta_new = s.r = sums[1];  beta = delta_new / delta_old;  d = s + beta d
@@ -348,7 +356,12 @@ class Destriper:
         st.delta.copy_(st.sums[1:2])
 
     def solve(self, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, x0=None):
-        """The PCG of mapmaker_solve.py:524-755.  Returns (amplitudes, relative residuals)."""
+        """The PCG of mapmaker_solve.py:524-755.  Returns (amplitudes, relative residuals).
+
+        Same arithmetic and stopping rules as the reference.  The host needs one scalar per
+        iteration (r.r) for the convergence / stall tests; instead of idling the GPU while it
+        is read back, the next search direction and the next LHS -- which do not modify x or r
+        -- are enqueued first, so on exit x and r are exactly the reference's."""
         dev = self.device
         n = self.n_amp
         st = _PCGState(n, dev)
@@ -369,11 +382,21 @@ class Destriper:
         last_best = sqsum
         self.dot(st.d, st.r, st.delta)
         history = []
+        host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        ev = torch.cuda.Event()
+        if n_iter_max > 0:
+            self.lhs_and_dot(st)
         for it in range(n_iter_max):
             if not np.isfinite(sqsum):
                 raise RuntimeError("Residual is not finite")
-            self.iteration(st)
-            sqsum = float(st.sums[0].item())
+            self.update(st)
+            host.copy_(st.sums, non_blocking=True)
+            ev.record()
+            if it + 1 < n_iter_max:  # speculative: keeps the GPU busy during the read-back
+                self.advance_direction(st)
+                self.lhs_and_dot(st)
+            ev.synchronize()
+            sqsum = float(host[0])
             relative = sqsum / sqsum_init
             history.append(relative)
             if relative < convergence or sqsum < 1e-30:
@@ -383,7 +406,6 @@ class Destriper:
                 if last_best < sqsum_best * 2:
                     break
                 last_best = sqsum_best
-            self.advance_direction(st)
         return st.x, history
 
 
