@@ -328,6 +328,8 @@ int tb_obs_has_compact_pointing(const tb_obs *obs);
 
 /* Runtime options (A/B measurements, debugging):
  *   "compact" (default 1)  use the compact pointing in the LHS passes when it has been packed
+ *   "pair"    (default 1)  process detector rows two at a time so that co-pointed detectors
+ *                          (polarisation pairs) share one RED triple / map gather per sample
  *   "tma"     (default 0)  stage the stored-pointing LHS passes through shared memory with
  *                          cp.async.bulk + mbarrier (measured slower than direct loads)     */
 int tb_set_option(const char *name, int value);

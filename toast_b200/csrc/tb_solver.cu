@@ -564,6 +564,151 @@ k_lhs_compact(ObsDev o, const double *__restrict__ amps, const uint8_t *__restri
 
 int g_use_compact = 1; // tb_set_option("compact", 0/1)
 
+// =================================================================================================
+// Detector-pair LHS passes.
+//
+// Focalplanes hold polarisation pairs: detectors 2p and 2p+1 share a line of sight, so at every
+// sample they fall in the same pixel.  One thread therefore handles sample s of BOTH rows of a
+// pair: when the two local pixels coincide their noise-weighted contributions are added in
+// registers and ONE run / RED triple (pass 1) or ONE map gather (pass 2) serves both detectors,
+// which halves the scattered map traffic that limits these passes.  Nothing is assumed: rows
+// whose pixels differ (unpaired layouts, pixel-boundary rounding) take a second reduction stream
+// that costs nothing when no lane of the warp needs it.
+// =================================================================================================
+#ifndef TB_PAIR_CTAS
+#define TB_PAIR_CTAS 8
+#endif
+template <bool PASS2>
+__global__ void __launch_bounds__(kThreads, TB_PAIR_CTAS)
+k_lhs_pair(ObsDev o, int64_t n_pair, const double *__restrict__ amps,
+           const uint8_t *__restrict__ aflags, const double *__restrict__ binned,
+           double *__restrict__ out) {
+    TileId _tile = tile_of_block(blockIdx.x, n_pair);
+    const int d0 = 2 * _tile.det;
+    const bool has1 = (d0 + 1) < o.n_det;
+    const int d1 = has1 ? d0 + 1 : d0;
+    const int lane = threadIdx.x & 31;
+    const double scale0 = __ldg(o.det_scale + d0), scale1 = __ldg(o.det_scale + d1);
+    const double c0 = __ldg(o.cal + d0), c1 = __ldg(o.cal + d1);
+    const int64_t ao0 = __ldg(o.amp_offsets + d0), ao1 = __ldg(o.amp_offsets + d1);
+#pragma unroll 2
+    for (int k = 0; k < kPerThread; ++k) {
+        int64_t t = _tile.t0 + (int64_t)k * kThreads + threadIdx.x;
+        int64_t keyA = -1, keyB = -1;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+        if (t < o.V.total) {
+            int view = (o.V.n_view > 1) ? find_view(o.V, t) : 0;
+            int64_t off = t - __ldg(o.V.prefix + view);
+            int64_t i0 = (int64_t)d0 * o.n_samp + __ldg(o.V.first + view) + off;
+            int64_t i1 = i0 + o.n_samp;
+            int32_t lp0 = __ldcs(o.lpix + i0);
+            double2 wq0 = __ldcs(o.wqu + i0);
+            int32_t lp1 = -1;
+            double2 wq1 = make_double2(0.0, 0.0);
+            if (has1) {
+                lp1 = __ldcs(o.lpix + i1);
+                wq1 = __ldcs(o.wqu + i1);
+            }
+            int64_t rel = __ldg(o.amp_view_off + view) + fast_div(off, o.inv_step);
+            int64_t amp0 = ao0 + rel, amp1 = ao1 + rel;
+            bool ok0 = __ldg(aflags + amp0) == 0;
+            bool ok1 = has1 && (__ldg(aflags + amp1) == 0);
+            double tod0 = ok0 ? __ldg(amps + amp0) : 0.0;
+            double tod1 = ok1 ? __ldg(amps + amp1) : 0.0;
+            if (!PASS2) {
+                double sd0 = tod0 * scale0, sd1 = tod1 * scale1;
+                if (lp0 >= 0) {
+                    keyA = lp0;
+                    a0 = sd0 * c0;
+                    a1 = sd0 * wq0.x;
+                    a2 = sd0 * wq0.y;
+                }
+                if (lp1 >= 0) {
+                    if (lp1 == lp0) {
+                        a0 += sd1 * c1;
+                        a1 += sd1 * wq1.x;
+                        a2 += sd1 * wq1.y;
+                    } else {
+                        keyB = lp1;
+                        b0 = sd1 * c1;
+                        b1 = sd1 * wq1.x;
+                        b2 = sd1 * wq1.y;
+                    }
+                }
+            } else {
+                if (ok0) keyA = amp0;
+                if (ok1) keyB = amp1;
+                bool need0 = ok0 && lp0 != -1, need1 = ok1 && lp1 != -1;
+                double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+                bool have = false;
+                if (need0 && lp0 >= 0) {
+                    const double *m = binned + 3 * (int64_t)lp0;
+                    m0 = __ldg(m);
+                    m1 = __ldg(m + 1);
+                    m2 = __ldg(m + 2);
+                    have = true;
+                    double sc = 0.0; // ops_scan_map.cpp:59-64
+                    sc += c0 * m0;
+                    sc += wq0.x * m1;
+                    sc += wq0.y * m2;
+                    tod0 -= sc;
+                }
+                if (need1 && lp1 >= 0) {
+                    if (!(have && lp1 == lp0)) {
+                        const double *m = binned + 3 * (int64_t)lp1;
+                        m0 = __ldg(m);
+                        m1 = __ldg(m + 1);
+                        m2 = __ldg(m + 2);
+                    }
+                    double sc = 0.0;
+                    sc += c1 * m0;
+                    sc += wq1.x * m1;
+                    sc += wq1.y * m2;
+                    tod1 -= sc;
+                }
+                if (need0) a0 = tod0 * scale0;
+                if (need1) b0 = tod1 * scale1;
+            }
+        }
+        if (!PASS2) {
+            Runs r = find_runs<kBinRunCap>(keyA, lane);
+            a0 = seg_sum<kBinRunCap>(a0, r);
+            a1 = seg_sum<kBinRunCap>(a1, r);
+            a2 = seg_sum<kBinRunCap>(a2, r);
+            if (r.is_tail && keyA >= 0) {
+                double *z = out + keyA * 3;
+                atomicAdd(z, a0);
+                atomicAdd(z + 1, a1);
+                atomicAdd(z + 2, a2);
+            }
+            if (__any_sync(0xffffffffu, keyB >= 0)) {
+                Runs rb = find_runs<kBinRunCap>(keyB, lane);
+                b0 = seg_sum<kBinRunCap>(b0, rb);
+                b1 = seg_sum<kBinRunCap>(b1, rb);
+                b2 = seg_sum<kBinRunCap>(b2, rb);
+                if (rb.is_tail && keyB >= 0) {
+                    double *z = out + keyB * 3;
+                    atomicAdd(z, b0);
+                    atomicAdd(z + 1, b1);
+                    atomicAdd(z + 2, b2);
+                }
+            }
+        } else {
+            Runs r = find_runs(keyA, lane);
+            a0 = seg_sum(a0, r);
+            if (r.is_tail && keyA >= 0) atomicAdd(out + keyA, a0);
+            if (has1) {
+                Runs rb = find_runs(keyB, lane);
+                b0 = seg_sum(b0, rb);
+                if (rb.is_tail && keyB >= 0) atomicAdd(out + keyB, b0);
+            }
+        }
+    }
+}
+
+int g_use_pair = 1; // tb_set_option("pair", 0/1)
+
+
 
 ObsDev make_dev(const tb_obs *obs, int regen) {
     const tb_obs_desc &d = obs->d;
@@ -653,7 +798,12 @@ void launch_bin(const tb_obs *obs, const double *amps, const uint8_t *aflags, co
                 double *zmap, int regen, void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
+    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
+        int64_t n_pair = (o.n_det + 1) / 2;
+        int64_t nbp = ((o.V.total + kTile - 1) / kTile) * n_pair;
+        auto k = k_lhs_pair<false>;
+        TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, nullptr, zmap);
+    } else if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
         auto k = k_lhs_compact<false>;
         TBS_LAUNCH(k, nb, stream, o, amps, aflags, nullptr, zmap);
     } else if (!regen && !FROM_SIGNAL && tma_ok(o)) {
@@ -676,7 +826,12 @@ void launch_project(const tb_obs *obs, const double *amps, const uint8_t *aflags
                     void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
+    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
+        int64_t n_pair = (o.n_det + 1) / 2;
+        int64_t nbp = ((o.V.total + kTile - 1) / kTile) * n_pair;
+        auto k = k_lhs_pair<true>;
+        TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, binned, out);
+    } else if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
         auto k = k_lhs_compact<true>;
         TBS_LAUNCH(k, nb, stream, o, amps, aflags, binned, out);
     } else if (!regen && !FROM_SIGNAL && tma_ok(o)) {
@@ -963,6 +1118,8 @@ int tb_set_option(const char *name, int value) {
         g_use_tma = value;
     } else if (std::string(name) == "compact") {
         g_use_compact = value;
+    } else if (std::string(name) == "pair") {
+        g_use_pair = value;
     } else {
         throw tbr::Error{TB_ERR_ARG, std::string("unknown option: ") + name};
     }
