@@ -48,6 +48,10 @@ SHARDS = {
 }
 BYTES_PER_SAMPLE_PASS = 33      # pixel 8 + weights 24 + solver flag 1
 BYTES_PER_SAMPLE_ITER = 66
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_lhs_pair<0> / <1> on the default
+# workload, from profiles/r1_ncu_passes.txt (prof_r1_pair)
+NCU_TRAFFIC_PASS1 = 8.246e9
+NCU_TRAFFIC_PASS2 = 7.572e9
 
 
 def parse_args():
@@ -489,7 +493,11 @@ def main_gpu(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else \
             "fallback 6650 GB/s (B200_PROFILING.md)"
         compact = dobs.has_compact_pointing() and not args.regen
-        if compact:
+        pair = compact and lib.tb_get_option(b"pair") == 1 and lib.tb_get_option(b"compact") == 1
+        if pair:
+            names = ("k_lhs_pair<0> (pass 1: template -> noise-weighted map)",
+                     "k_lhs_pair<1> (pass 2: scan - weight - project)")
+        elif compact:
             names = ("k_lhs_compact<0> (pass 1: template -> noise-weighted map)",
                      "k_lhs_compact<1> (pass 2: scan - weight - project)")
         elif args.regen:
@@ -500,8 +508,8 @@ def main_gpu(args):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
         # `ncu --set full` capture of THIS workload (profiles/r1_ncu_passes.txt); null otherwise
         traffic = None
-        if compact and args.workload == "c4" and args.scale == 1.0 and world == 1:
-            traffic = 8.226e9 if p1 >= p2 else 7.449e9
+        if pair and args.workload == "c4" and args.scale == 1.0 and world == 1:
+            traffic = NCU_TRAFFIC_PASS1 if p1 >= p2 else NCU_TRAFFIC_PASS2
         alg_bytes = info["det_samples"] * BYTES_PER_SAMPLE_PASS
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         iter_gbs = info["det_samples"] * BYTES_PER_SAMPLE_ITER / (ms_step * 1e-3) / 1e9

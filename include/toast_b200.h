@@ -333,6 +333,7 @@ int tb_obs_has_compact_pointing(const tb_obs *obs);
  *   "tma"     (default 0)  stage the stored-pointing LHS passes through shared memory with
  *                          cp.async.bulk + mbarrier (measured slower than direct loads)     */
 int tb_set_option(const char *name, int value);
+int tb_get_option(const char *name); /* -1 if unknown */
 
 /* ---- test hooks ------------------------------------------------------------------------- */
 /* Scale the guard band that routes a sample to the exact (double-double atan2) pixel path;

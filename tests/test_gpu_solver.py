@@ -142,3 +142,45 @@ def test_destriping_recovers_baselines():
     O.template_add(pb, O, -amps.cpu().numpy(), clean)
     r2 = ds.rhs([torch.from_numpy(clean).cuda()])
     assert float(torch.abs(r2).max()) < 1e-6 * float(torch.abs(rhs).max())
+
+
+def _permuted(obs, perm):
+    out = dict(obs)
+    for k in ("focalplane", "epsilon", "gamma", "cal", "sigma", "detweight", "signal",
+              "det_flags"):
+        out[k] = np.ascontiguousarray(obs[k][perm])
+    out["n_det"] = len(perm)
+    return out
+
+
+@pytest.mark.parametrize("perm", [[0, 2, 1, 3, 4], [0, 1, 2, 3, 4], [3, 0, 4]])
+def test_lhs_kernel_variants_agree(perm):
+    """The shipped detector-pair kernels (co-pointed rows share a RED / gather) against the
+    oracle and against the single-row compact, TMA-staged and general kernels -- including an
+    odd detector count and rows whose neighbours do NOT point at the same pixel."""
+    ck = H.checker()
+    obs = _permuted(S.make_observation("c4", n_det=6, n_samp=30000, eps_max=0.03, nside=128),
+                    perm)
+    pb = O.build_problem(obs, ck)
+    rng = np.random.default_rng(4)
+    a = np.where(pb.amp_flags == 0, rng.standard_normal(pb.n_amp), 0.0)
+    ref = O.solver_lhs(pb, ck, a, covapply=ck.cov_apply_diag)
+    lib = L.load()
+    results = {}
+    try:
+        for name, opts in (("pair", dict(pair=1, compact=1, tma=0)),
+                           ("compact", dict(pair=0, compact=1, tma=0)),
+                           ("tma", dict(pair=0, compact=0, tma=1)),
+                           ("general", dict(pair=0, compact=0, tma=0))):
+            for k, v in opts.items():
+                L.check(lib.tb_set_option(k.encode(), v))
+            dobs, ds, _ = _device_problem(obs, pb)
+            q = torch.zeros(pb.n_amp, dtype=torch.float64, device="cuda")
+            ds.lhs(torch.from_numpy(a).cuda(), q)
+            results[name] = q.cpu().numpy()
+            assert_close_norm(results[name], ref, what=f"LHS ({name})")
+    finally:
+        for k, v in dict(pair=1, compact=1, tma=0).items():
+            lib.tb_set_option(k.encode(), v)
+    for name in ("compact", "tma", "general"):
+        assert_close_norm(results[name], results["pair"], rtol=1e-12, what=f"{name} vs pair")

@@ -1111,6 +1111,15 @@ int tb_obs_pack_pointing(tb_obs *obs, void *stream) {
 
 int tb_obs_has_compact_pointing(const tb_obs *obs) { return (obs && obs->lpix) ? 1 : 0; }
 
+int tb_get_option(const char *name) {
+    if (name == nullptr) return -1;
+    std::string n(name);
+    if (n == "tma") return g_use_tma;
+    if (n == "compact") return g_use_compact;
+    if (n == "pair") return g_use_pair;
+    return -1;
+}
+
 int tb_set_option(const char *name, int value) {
     TB_API_BEGIN
     TB_REQUIRE(name != nullptr, "NULL option name");

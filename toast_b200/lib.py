@@ -113,6 +113,7 @@ PROTOTYPES = {
     "tb_obs_pack_pointing": (INT, [P, P]),
     "tb_obs_has_compact_pointing": (INT, [P]),
     "tb_set_option": (INT, [STR, INT]),
+    "tb_get_option": (INT, [STR]),
     "tb_set_pixel_guard_scale": (None, [F64]),
     "tb_pixel_exact_count": (I64, [INT]),
 }
