@@ -184,3 +184,90 @@ def test_lhs_kernel_variants_agree(perm):
             lib.tb_set_option(k.encode(), v)
     for name in ("compact", "tma", "general"):
         assert_close_norm(results[name], results["pair"], rtol=1e-12, what=f"{name} vs pair")
+
+
+def test_full_size_properties_c4_shard():
+    """BASELINE full size (128 det x 2.16e6 samples, nside 2048: the bench workload), where the
+    oracle is too slow to be the checker: size-independent properties instead.
+      * hit map total == number of unflagged samples (integer, exact)
+      * pixels in range; fused pointing == 3-kernel chain on a detector subset (bit-exact)
+      * LHS is linear and symmetric (F^T N^-1 Z F), to 1e-10
+      * stored-pointing and regenerated-pointing LHS agree to 1e-10
+    """
+    from toast_b200 import kernels as K
+
+    n_det, n_samp = 128, 2160000
+    obs = S.make_observation("c4", n_det=n_det, n_samp=n_samp, with_signal=False)
+    nside, nest = obs["nside"], obs["nest"]
+    n_submap, nps = S.n_submap_for(nside, 16)
+    dev = torch.device("cuda")
+    sflags = torch.from_numpy(obs["shared_flags"]).to(dev)
+    solver_flags = torch.from_numpy(obs["det_flags"]).to(dev)
+    solver_flags |= sflags[None, :]
+    dobs = DeviceObservation(
+        focalplane=obs["focalplane"], boresight=obs["boresight"], intervals=obs["intervals"],
+        det_scale=obs["detweight"], step_length=obs["step_length"], nside=nside, nest=nest,
+        n_pix_submap=nps, n_submap=n_submap, global2local=np.zeros(n_submap, dtype=np.int64),
+        epsilon=obs["epsilon"], gamma=obs["gamma"], cal=obs["cal"], shared_flags=sflags,
+        shared_flag_mask=1, solver_flags=solver_flags, solver_flag_mask=1)
+    hits = np.zeros(n_submap, dtype=np.uint8)
+    dobs.expand_pointing(hits)
+    pix = dobs.pixels
+    assert int(pix.max()) < 12 * nside * nside and int(pix.min()) == -1
+    np.testing.assert_array_equal((pix < 0).any(dim=0).cpu().numpy(), obs["shared_flags"] != 0)
+
+    # fused == chain, bit-exact, on 4 detectors
+    sub = np.arange(4, dtype=np.int32)
+    q = torch.zeros((4, n_samp, 4), dtype=torch.float64, device=dev)
+    K.pointing_detector(obs["focalplane"][:4], dobs.boresight, sub, q, obs["intervals"], sflags, 1)
+    p2 = torch.zeros((4, n_samp), dtype=torch.int64, device=dev)
+    K.pixels_healpix(sub, q, sflags, 1, sub, p2, obs["intervals"],
+                     np.zeros(n_submap, dtype=np.uint8), nps, nside, nest)
+    assert torch.equal(p2, pix[:4])
+    w2 = torch.zeros((4, n_samp, 3), dtype=torch.float64, device=dev)
+    K.stokes_weights_IQU(sub, q, sub, w2, None, obs["intervals"], obs["epsilon"][:4],
+                         obs["gamma"][:4], obs["cal"][:4], False)
+    assert torch.equal(w2, dobs.weights[:4])
+    del q, p2, w2
+
+    local = np.flatnonzero(hits).astype(np.int64)
+    g2l = np.full(n_submap, -1, dtype=np.int64)
+    g2l[local] = np.arange(len(local))
+    dobs.set_global2local(g2l)
+    n_loc = len(local)
+    idx = np.arange(n_det, dtype=np.int32)
+    dobs.solver_flags |= (pix < 0).to(torch.uint8)
+    hmap = torch.zeros(n_loc * nps, dtype=torch.int64, device=dev)
+    inv = torch.zeros((n_loc, nps, 6), dtype=torch.float64, device=dev)
+    K.cov_accum(g2l, n_loc, nps, 3, hmap, inv, idx, pix, idx, dobs.weights, idx,
+                dobs.solver_flags, obs["detweight"], 1, obs["intervals"], None, 0)
+    assert int(hmap.sum()) == int((dobs.solver_flags == 0).sum())   # checksum of the hit map
+    rc = torch.zeros(n_loc * nps, dtype=torch.float64, device=dev)
+    # rcond >= 1e-3: pixels with condition numbers up to 1e8 (the 1e-8 production threshold)
+    # amplify the order-dependent fp64 rounding of the binning to ~1e-10 of the result
+    K.cov_invert(n_loc * nps, 3, inv, rc, 1e-3)
+
+    n_amp = dobs.n_amp
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    var = torch.rand(n_amp, generator=g, device=dev, dtype=torch.float64)
+    aflags = torch.zeros(n_amp, dtype=torch.uint8, device=dev)
+    ds = Destriper([dobs], n_loc, nps, inv, var, aflags)
+    a = torch.randn(n_amp, generator=g, device=dev, dtype=torch.float64)
+    b = torch.randn(n_amp, generator=g, device=dev, dtype=torch.float64)
+    Aa, Ab, Aab = (torch.zeros_like(a) for _ in range(3))
+    ds.lhs(a, Aa)
+    ds.lhs(b, Ab)
+    ds.lhs(2.5 * a - 0.75 * b, Aab)
+    lin = 2.5 * Aa - 0.75 * Ab
+    e_lin = float((Aab - lin).abs().max() / lin.abs().max())
+    assert e_lin < 1e-10, f"linearity {e_lin}"
+    ab, ba = float(torch.dot(a, Ab)), float(torch.dot(b, Aa))
+    scale = float(torch.sqrt(torch.dot(a, a) * torch.dot(Ab, Ab)))
+    assert abs(ab - ba) <= 1e-10 * scale, f"symmetry {ab} {ba} {scale}"
+    # regenerated pointing gives the same operator
+    ds_r = Destriper([dobs], n_loc, nps, inv, var, aflags, regen=True)
+    Ar = torch.zeros_like(a)
+    ds_r.lhs(a, Ar)
+    e_regen = float((Ar - Aa).abs().max() / Aa.abs().max())
+    assert e_regen < 1e-10, f"stored vs regenerated {e_regen}"

@@ -37,6 +37,31 @@ __device__ __forceinline__ int find_view(const Views &v, int64_t t) {
     return lo;
 }
 
+// A thread visits increasing flat indices, and a tile rarely straddles an interval: locate the
+// view once per tile (one binary search) and then only step forward, instead of a 7-deep chain
+// of dependent loads per sample (ground scans have ~100 intervals per observation).
+struct ViewCursor {
+    int view;
+    int64_t beg, end, first; // prefix[view], prefix[view + 1], first[view]
+};
+__device__ __forceinline__ ViewCursor view_cursor(const Views &v, int64_t t) {
+    ViewCursor c;
+    if (t >= v.total) t = v.total - 1;
+    c.view = (v.n_view > 1 && t > 0) ? find_view(v, t) : 0;
+    c.beg = __ldg(v.prefix + c.view);
+    c.end = __ldg(v.prefix + c.view + 1);
+    c.first = __ldg(v.first + c.view);
+    return c;
+}
+__device__ __forceinline__ void view_seek(const Views &v, ViewCursor &c, int64_t t) {
+    while (t >= c.end) { // t < total is the caller's responsibility
+        ++c.view;
+        c.beg = c.end;
+        c.end = __ldg(v.prefix + c.view + 1);
+        c.first = __ldg(v.first + c.view);
+    }
+}
+
 // Tile decomposition with TIME-MAJOR CTA order: consecutive CTAs work on the same time window
 // of consecutive detectors, so the pixels they scatter to / gather from are neighbours on the
 // sky and the zmap / map tiles stay resident in the 126 MB L2.

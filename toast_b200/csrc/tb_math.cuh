@@ -18,8 +18,10 @@
 
 #ifdef __CUDACC__
 #define TB_HD __host__ __device__ __forceinline__
+#define TB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define TB_HD inline
+#define TB_HD_NOINLINE __attribute__((noinline))
 #endif
 
 namespace tbm {
@@ -317,17 +319,25 @@ TB_HD int64_t zphi2pix(const PixCtx &c, double phi, double z, bool &ambiguous) {
     }
 }
 
+// The exact tier, kept out of line: it runs for ~1e-10 of the samples and inlining it (a
+// double-double atan2 plus a second copy of the pixel arithmetic, times the unroll factor) would
+// multiply the hot loop's code size by ~8 and thrash the instruction cache.
+template <bool NEST>
+TB_HD_NOINLINE int64_t vec2pix_exact(const PixCtx &c, double dx, double dy, double dz) {
+    bool dummy = false;
+    double phi = atan2_cr(dy, dx);
+    return zphi2pix<NEST>(c, phi, dz, dummy);
+}
+
 // Direction vector -> pixel, two-tier: library atan2 first, exact atan2 only if ambiguous.
-// `n_exact` (may be null) counts the samples that took the exact path.
+// `took_exact` (may be null) is set when the sample took the exact path.
 template <bool NEST>
 TB_HD int64_t vec2pix(const PixCtx &c, double dx, double dy, double dz, int *took_exact) {
     bool amb = false;
     double phi = atan2(dy, dx);
     int64_t p = zphi2pix<NEST>(c, phi, dz, amb);
     if (amb) {
-        bool dummy = false;
-        phi = atan2_cr(dy, dx);
-        p = zphi2pix<NEST>(c, phi, dz, dummy);
+        p = vec2pix_exact<NEST>(c, dx, dy, dz);
         if (took_exact) *took_exact = 1;
     }
     return p;
@@ -347,7 +357,11 @@ TB_HD void detector_cs2alpha(double dx, double dy, double dz, double ox, double 
     double r2 = dx * dx + dy * dy;
     double cx = 1.0, sx = 0.0; // atan2(0, 0) = 0 in the reference
     if (r2 > 0.0) {
+#ifdef __CUDA_ARCH__
+        double rinv = rsqrt(r2); // 1 ulp; no division
+#else
         double rinv = 1.0 / sqrt(r2);
+#endif
         cx = dx * rinv;
         sx = dy * rinv;
     }
@@ -357,11 +371,13 @@ TB_HD void detector_cs2alpha(double dx, double dy, double dz, double ox, double 
     double ay = (dx * (vm_y * oz - vm_z * oy) - dy * (vm_x * oz - vm_z * ox) +
                  dz * (vm_x * oy - vm_y * ox));
     double ax = (vm_x * ox + vm_y * oy + vm_z * oz);
+    // (ax, ay) = |vm x ...| (cos alpha, sin alpha) with vm, vo unit vectors orthogonal to vd, so
+    // n2 = ax^2 + ay^2 = 1 + O(1e-15): one Newton step 1/n2 ~= 2 - n2 is exact to O(1e-30).
     double n2 = ax * ax + ay * ay;
     c2a = 1.0;
     s2a = 0.0; // atan2(0, 0) = 0
     if (n2 > 0.0) {
-        double inv = 1.0 / n2;
+        double inv = (fabs(n2 - 1.0) < 1.0e-6) ? (2.0 - n2) : (1.0 / n2);
         c2a = (ax * ax - ay * ay) * inv;
         s2a = (2.0 * ax * ay) * inv;
     }

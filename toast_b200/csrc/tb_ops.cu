@@ -69,6 +69,7 @@ void check_index(const int32_t *idx, int64_t n_det, int64_t n_buf, const char *w
 #define TB_FOR_TILE_SAMPLES(V, n_det)                                                       \
     TileId _tile = tile_of_block(blockIdx.x, (n_det));                                      \
     const int det = _tile.det;                                                              \
+    ViewCursor _vc = view_cursor((V), _tile.t0 + threadIdx.x);                              \
     _Pragma("unroll") for (int _k = 0; _k < kPerThread; ++_k)
 
 #define TB_SAMPLE_COORDS(V)                                                                 \
@@ -77,9 +78,10 @@ void check_index(const int32_t *idx, int64_t n_det, int64_t n_buf, const char *w
     int view = 0;                                                                           \
     int64_t off = 0, s = 0;                                                                 \
     if (valid) {                                                                            \
-        view = ((V).n_view > 1) ? find_view((V), _t) : 0;                                   \
-        off = _t - __ldg((V).prefix + view);                                                \
-        s = __ldg((V).first + view) + off;                                                  \
+        view_seek((V), _vc, _t);                                                            \
+        view = _vc.view;                                                                    \
+        off = _t - _vc.beg;                                                                 \
+        s = _vc.first + off;                                                                \
     }
 
 // ================================================================================================

@@ -108,6 +108,7 @@ __device__ __forceinline__ void sample_pointing(const ObsDev &o, int det, int64_
     TileId _tile = tile_of_block(blockIdx.x, (o).n_det);                                   \
     const int det = _tile.det;                                                             \
     const int lane = threadIdx.x & 31;                                                     \
+    ViewCursor _vc = view_cursor((o).V, _tile.t0 + threadIdx.x);                           \
     _Pragma("unroll") for (int _k = 0; _k < kPerThread; ++_k)
 
 #define TBS_COORDS(o)                                                                      \
@@ -116,9 +117,10 @@ __device__ __forceinline__ void sample_pointing(const ObsDev &o, int det, int64_
     int view = 0;                                                                          \
     int64_t off = 0, s = 0;                                                                \
     if (valid) {                                                                           \
-        view = ((o).V.n_view > 1) ? find_view((o).V, _t) : 0;                              \
-        off = _t - __ldg((o).V.prefix + view);                                             \
-        s = __ldg((o).V.first + view) + off;                                               \
+        view_seek((o).V, _vc, _t);                                                         \
+        view = _vc.view;                                                                   \
+        off = _t - _vc.beg;                                                                \
+        s = _vc.first + off;                                                               \
     }
 
 // ---- pass 1: template -> timestream -> noise-weighted map -------------------------------------
@@ -502,15 +504,17 @@ k_lhs_compact(ObsDev o, const double *__restrict__ amps, const uint8_t *__restri
     const double scale = __ldg(o.det_scale + det);
     const double w0 = __ldg(o.cal + det);
     const int64_t amp_det = __ldg(o.amp_offsets + det);
+    ViewCursor vc = view_cursor(o.V, _tile.t0 + threadIdx.x);
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
         int64_t t = _tile.t0 + (int64_t)k * kThreads + threadIdx.x;
         int64_t key = -1;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0;
         if (t < o.V.total) {
-            int view = (o.V.n_view > 1) ? find_view(o.V, t) : 0;
-            int64_t off = t - __ldg(o.V.prefix + view);
-            int64_t i = (int64_t)det * o.n_samp + __ldg(o.V.first + view) + off;
+            view_seek(o.V, vc, t);
+            const int view = vc.view;
+            int64_t off = t - vc.beg;
+            int64_t i = (int64_t)det * o.n_samp + vc.first + off;
             int32_t lp = __ldcs(o.lpix + i);
             double2 wq = __ldcs(o.wqu + i);
             int64_t amp = amp_det + __ldg(o.amp_view_off + view) + fast_div(off, o.inv_step);
@@ -591,15 +595,17 @@ k_lhs_pair(ObsDev o, int64_t n_pair, const double *__restrict__ amps,
     const double scale0 = __ldg(o.det_scale + d0), scale1 = __ldg(o.det_scale + d1);
     const double c0 = __ldg(o.cal + d0), c1 = __ldg(o.cal + d1);
     const int64_t ao0 = __ldg(o.amp_offsets + d0), ao1 = __ldg(o.amp_offsets + d1);
+    ViewCursor vc = view_cursor(o.V, _tile.t0 + threadIdx.x);
 #pragma unroll 2
     for (int k = 0; k < kPerThread; ++k) {
         int64_t t = _tile.t0 + (int64_t)k * kThreads + threadIdx.x;
         int64_t keyA = -1, keyB = -1;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
         if (t < o.V.total) {
-            int view = (o.V.n_view > 1) ? find_view(o.V, t) : 0;
-            int64_t off = t - __ldg(o.V.prefix + view);
-            int64_t i0 = (int64_t)d0 * o.n_samp + __ldg(o.V.first + view) + off;
+            view_seek(o.V, vc, t);
+            const int view = vc.view;
+            int64_t off = t - vc.beg;
+            int64_t i0 = (int64_t)d0 * o.n_samp + vc.first + off;
             int64_t i1 = i0 + o.n_samp;
             int32_t lp0 = __ldcs(o.lpix + i0);
             double2 wq0 = __ldcs(o.wqu + i0);
