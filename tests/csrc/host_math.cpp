@@ -32,7 +32,8 @@ void tbm_zphi2pix(int64_t n, const double *z, const double *phi, int64_t nside, 
     tbm::PixCtx c = tbm::make_pix_ctx(nside, 1.0);
     for (int64_t i = 0; i < n; ++i) {
         bool a = false;
-        pix[i] = nest ? tbm::zphi2pix<true>(c, phi[i], z[i], a) : tbm::zphi2pix<false>(c, phi[i], z[i], a);
+        pix[i] = c.small ? (nest ? tbm::zphi2pix<true, int32_t>(c, phi[i], z[i], a) : tbm::zphi2pix<false, int32_t>(c, phi[i], z[i], a))
+                         : (nest ? tbm::zphi2pix<true, int64_t>(c, phi[i], z[i], a) : tbm::zphi2pix<false, int64_t>(c, phi[i], z[i], a));
         amb[i] = a ? 1 : 0;
     }
 }

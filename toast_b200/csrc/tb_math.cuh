@@ -189,6 +189,7 @@ struct PixCtx {
     double tqnside;    // 0.75 nside
     double guard;      // half-width of the "ambiguous" band around integers, units of jp/jm
     double guard_tt;   // same, in units of tt
+    bool small;        // nside <= 8192: 32-bit integer arithmetic is exact
 };
 
 TB_HD PixCtx make_pix_ctx(int64_t nside, double guard_scale) {
@@ -207,6 +208,7 @@ TB_HD PixCtx make_pix_ctx(int64_t nside, double guard_scale) {
     // |delta tt| <= 2 ulp(phi) * 2/pi + a few roundings < 2e-15; use 4x that.
     c.guard_tt = 8.0e-15 * guard_scale;
     c.guard = c.guard_tt * c.dnside;
+    c.small = nside <= 8192;
     return c;
 }
 
@@ -221,8 +223,19 @@ TB_HD uint64_t spread_bits(uint64_t v) {
     x = (x | (x << 1)) & 0x5555555555555555ull;
     return x;
 }
+TB_HD uint32_t spread_bits16(uint32_t v) { // 16 bits -> 32 bits
+    uint32_t x = v & 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
 TB_HD int64_t xy2pix(int64_t x, int64_t y) {
     return (int64_t)(spread_bits((uint64_t)x) | (spread_bits((uint64_t)y) << 1));
+}
+TB_HD int32_t xy2pix(int32_t x, int32_t y) {
+    return (int32_t)(spread_bits16((uint32_t)x) | (spread_bits16((uint32_t)y) << 1));
 }
 
 TB_HD bool near_integer(double v, double tol) { return fabs(v - rint(v)) <= tol; }
@@ -234,6 +247,7 @@ TB_HD double phi_to_tt(double phi, bool &ambiguous) {
     const double twopi = 2 * 3.14159265358979323846;
     const double two_over_pi = 0.63661977236758134308;
     double div = phi / twopi;
+    // |phi| <= pi so (int64)div == 0; the subtraction of 0.0 is kept for the sign of zero
     double phi_mod = twopi * (div - (double)((int64_t)div));
     double aphi = fabs(phi_mod);
     if (fabs(aphi - tol) <= tol * 1.0e-13) ambiguous = true;
@@ -242,9 +256,13 @@ TB_HD double phi_to_tt(double phi, bool &ambiguous) {
 }
 
 // (z, phi) -> pixel.  Sets `ambiguous` when a 2-ulp change of phi could alter the result.
-template <bool NEST>
+// I is the integer type of the intermediate ring / face arithmetic: int32_t is exact for
+// nside <= 8192 (12 nside^2 < 2^31) and costs a third of the emulated 64-bit integer ops;
+// both instantiations perform the same arithmetic as the reference's int64 code.
+template <bool NEST, typename I>
 TB_HD int64_t zphi2pix(const PixCtx &c, double phi, double z, bool &ambiguous) {
     const double twothirds = 0.66666666666666666667;
+    const I nside = (I)c.nside, nm1 = (I)c.nm1, fournside = (I)c.fournside;
     double za = fabs(z);
     double tt = phi_to_tt(phi, ambiguous);
     if (za <= twothirds) {
@@ -253,80 +271,95 @@ TB_HD int64_t zphi2pix(const PixCtx &c, double phi, double z, bool &ambiguous) {
         double vp = t1 - t2;
         double vm = t1 + t2;
         if (near_integer(vp, c.guard) || near_integer(vm, c.guard)) ambiguous = true;
-        int64_t jp = (int64_t)vp;
-        int64_t jm = (int64_t)vm;
+        I jp = (I)vp;
+        I jm = (I)vm;
         if (NEST) {
-            int64_t ifp = jp >> c.factor;
-            int64_t ifm = jm >> c.factor;
-            int64_t face;
+            I ifp = jp >> c.factor;
+            I ifm = jm >> c.factor;
+            I face;
             if (ifp == ifm) {
-                face = (ifp == 4) ? (int64_t)4 : ifp + 4;
+                face = (ifp == 4) ? (I)4 : ifp + 4;
             } else if (ifp < ifm) {
                 face = ifp;
             } else {
                 face = ifm + 8;
             }
-            int64_t x = jm & c.nm1;
-            int64_t y = c.nm1 - (jp & c.nm1);
-            return xy2pix(x, y) + (face << (2 * c.factor));
+            I x = jm & nm1;
+            I y = nm1 - (jp & nm1);
+            return (int64_t)(xy2pix(x, y) + (face << (2 * c.factor)));
         } else {
-            int64_t ir = (c.nside + 1) + jp - jm;
-            int64_t kshift = 1 - (ir & 1);
-            int64_t ip = (jp + jm - c.nside + kshift + 1) >> 1;
-            ip = ip % c.fournside;
-            return c.ncap + ((ir - 1) * c.fournside + ip);
+            I ir = (nside + 1) + jp - jm;
+            I kshift = 1 - (ir & 1);
+            I ip = (jp + jm - nside + kshift + 1) >> 1;
+            ip = (ip >= 0) ? (ip & (fournside - 1)) : (ip % fournside); // fournside = 2^k
+            return (int64_t)((I)c.ncap + ((ir - 1) * fournside + ip));
         }
     } else {
         double rtz = sqrt(3.0 * (1.0 - za));
         if (near_integer(tt, c.guard_tt)) ambiguous = true;
         double t1 = c.dnside * rtz;
         if (NEST) {
-            int64_t ntt = (int64_t)tt;
+            I ntt = (I)tt;
             double tp = tt - (double)ntt;
             double vp = tp * t1;
             double vm = (1.0 - tp) * t1;
             if (near_integer(vp, c.guard) || near_integer(vm, c.guard)) ambiguous = true;
-            int64_t jp = (int64_t)vp;
-            int64_t jm = (int64_t)vm;
-            if (jp >= c.nside) jp = c.nm1;
-            if (jm >= c.nside) jm = c.nm1;
-            int64_t face, x, y;
+            I jp = (I)vp;
+            I jm = (I)vm;
+            if (jp >= nside) jp = nm1;
+            if (jm >= nside) jm = nm1;
+            I face, x, y;
             if (z >= 0) {
                 face = ntt;
-                x = c.nm1 - jm;
-                y = c.nm1 - jp;
+                x = nm1 - jm;
+                y = nm1 - jp;
             } else {
                 face = ntt + 8;
                 x = jp;
                 y = jm;
             }
-            return xy2pix(x, y) + (face << (2 * c.factor));
+            return (int64_t)(xy2pix(x, y) + (face << (2 * c.factor)));
         } else {
             double tp = tt - floor(tt);
             double vp = tp * t1;
             double vm = (1.0 - tp) * t1;
             if (near_integer(vp, c.guard) || near_integer(vm, c.guard)) ambiguous = true;
-            int64_t jp = (int64_t)vp;
-            int64_t jm = (int64_t)vm;
-            int64_t ir = jp + jm + 1;
+            I jp = (I)vp;
+            I jm = (I)vm;
+            I ir = jp + jm + 1;
             double vi = tt * (double)ir;
             if (near_integer(vi, c.guard)) ambiguous = true;
-            int64_t ip = (int64_t)vi;
-            int64_t longpart = (int64_t)(ip / (4 * ir));
+            I ip = (I)vi;
+            I longpart = (I)(ip / (4 * ir));
             ip -= longpart;
-            return (z > 0.0) ? (2 * ir * (ir - 1) + ip) : (c.npix - 2 * ir * (ir + 1) + ip);
+            return (z > 0.0) ? (int64_t)(2 * ir * (ir - 1) + ip)
+                             : (int64_t)((I)c.npix - 2 * ir * (ir + 1) + ip);
         }
     }
 }
 
-// The exact tier, kept out of line: it runs for ~1e-10 of the samples and inlining it (a
-// double-double atan2 plus a second copy of the pixel arithmetic, times the unroll factor) would
-// multiply the hot loop's code size by ~8 and thrash the instruction cache.
+// Out-of-line tiers: (i) the exact double-double atan2 path, taken by ~1e-10 of the samples,
+// and (ii) the 64-bit-integer path for nside > 8192.  Inlining either into the unrolled hot loop
+// multiplies its code size and thrashes the instruction cache.  They take scalars by value and
+// rebuild the context: a reference to the kernel-parameter struct would force a local-memory
+// copy of it (and a stack frame) into every caller.
 template <bool NEST>
-TB_HD_NOINLINE int64_t vec2pix_exact(const PixCtx &c, double dx, double dy, double dz) {
+TB_HD_NOINLINE int64_t vec2pix_exact(int64_t nside, double dx, double dy, double dz) {
+    PixCtx c = make_pix_ctx(nside, 1.0);
     bool dummy = false;
     double phi = atan2_cr(dy, dx);
-    return zphi2pix<NEST>(c, phi, dz, dummy);
+    return c.small ? zphi2pix<NEST, int32_t>(c, phi, dz, dummy)
+                   : zphi2pix<NEST, int64_t>(c, phi, dz, dummy);
+}
+// returns the pixel with the "ambiguous" flag in bit 62
+template <bool NEST>
+TB_HD_NOINLINE int64_t zphi2pix_wide(int64_t nside, double guard_tt, double phi, double z) {
+    PixCtx c = make_pix_ctx(nside, 1.0);
+    c.guard_tt = guard_tt;
+    c.guard = guard_tt * c.dnside;
+    bool amb = false;
+    int64_t p = zphi2pix<NEST, int64_t>(c, phi, z, amb);
+    return p | (amb ? ((int64_t)1 << 62) : 0);
 }
 
 // Direction vector -> pixel, two-tier: library atan2 first, exact atan2 only if ambiguous.
@@ -335,9 +368,16 @@ template <bool NEST>
 TB_HD int64_t vec2pix(const PixCtx &c, double dx, double dy, double dz, int *took_exact) {
     bool amb = false;
     double phi = atan2(dy, dx);
-    int64_t p = zphi2pix<NEST>(c, phi, dz, amb);
+    int64_t p;
+    if (c.small) {
+        p = zphi2pix<NEST, int32_t>(c, phi, dz, amb);
+    } else {
+        p = zphi2pix_wide<NEST>(c.nside, c.guard_tt, phi, dz);
+        amb = (p >> 62) & 1;
+        p &= ~((int64_t)1 << 62);
+    }
     if (amb) {
-        p = vec2pix_exact<NEST>(c, dx, dy, dz);
+        p = vec2pix_exact<NEST>(c.nside, dx, dy, dz);
         if (took_exact) *took_exact = 1;
     }
     return p;

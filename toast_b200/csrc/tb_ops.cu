@@ -104,8 +104,13 @@ k_pointing_detector(Views V, int64_t n_det, int64_t n_samp, const double *__rest
 // ================================================================================================
 // a2 pixels_healpix
 // ================================================================================================
+// occupancy targets measured on B200 (profiles/r1_kernels_c2.json): these kernels are fp64 /
+// integer ALU bound and a few spills cost less than fewer resident warps
+#ifndef TB_POINT_CTAS
+#define TB_POINT_CTAS 4
+#endif
 template <bool NEST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 k_pixels_healpix(Views V, int64_t n_det, int64_t n_samp, tbm::PixCtx ctx,
                  const int32_t *__restrict__ qidx, const double *__restrict__ quats,
                  const uint8_t *__restrict__ flags, uint8_t mask,
@@ -183,7 +188,7 @@ struct FusedOut {
 };
 
 template <bool NEST, bool HWP>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, TB_POINT_CTAS)
 k_pointing_fused(Views V, int64_t n_det, int64_t n_samp, tbm::PixCtx ctx,
                  const double *__restrict__ fp, const double *__restrict__ boresight,
                  const uint8_t *__restrict__ flags, uint8_t mask, FusedOut o,

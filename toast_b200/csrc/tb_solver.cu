@@ -125,8 +125,11 @@ __device__ __forceinline__ void sample_pointing(const ObsDev &o, int det, int64_
 
 // ---- pass 1: template -> timestream -> noise-weighted map -------------------------------------
 // FROM_SIGNAL: bin a stored timestream instead of the template amplitudes (RHS / final BinMap).
+#ifndef TB_REGEN_CTAS
+#define TB_REGEN_CTAS 4
+#endif
 template <bool REGEN, bool NEST, bool FROM_SIGNAL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, REGEN ? TB_REGEN_CTAS : 6)
 k_bin(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ aflags,
       const double *__restrict__ signal, double *__restrict__ zmap) {
     int n_exact = 0;
@@ -173,7 +176,7 @@ k_bin(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ afl
 
 // ---- pass 2: (template - scanned map) -> noise weight -> template projection ------------------
 template <bool REGEN, bool NEST, bool FROM_SIGNAL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, REGEN ? TB_REGEN_CTAS : 6)
 k_project(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ aflags,
           const double *__restrict__ signal, const double *__restrict__ binned,
           double *__restrict__ amps_out) {
