@@ -547,7 +547,7 @@ def main_gpu(args):
             "clocks": clocks,
             "pcg_relative_residuals": history[args.warmup:args.warmup + 5],
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N=1 only
             try:
                 res = run_cpu(args.workload, 2, 1)
                 line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind",

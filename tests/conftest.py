@@ -12,6 +12,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_sessionstart(session):
+    """Build whatever is missing (nvcc cross-compiles without a GPU): the CUDA library, the
+    pybind11 module and the oracle's C restatement.  `__graft_entry__.build()` does the same."""
+    from toast_b200 import build as tb_build
+
+    tb_build.build()
+    tb_build.build_pybind()
+    from oracle import toast_oracle
+
+    toast_oracle.build()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 

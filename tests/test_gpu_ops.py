@@ -193,3 +193,32 @@ def test_mapmaker_end_to_end(name, n_det, n_samp, nside, regen):
     assert dev < max(1e-10, 1e3 * H.pcg_envelope(pb, rhs_ref, 12)[-1] ** 0.5), dev
     # the cleaned timestream is left in det_data (mapmaker.py:531-574)
     assert_close_norm(data.obs[0].detdata["signal"].data, clean, what="cleaned TOD")
+
+
+def test_scan_mask():
+    """ops/scan_map/scan_map.py:216-357 (used by the map-maker for the rcond / pixel masks)."""
+    from toast_b200.pixels import PixelData
+
+    obs, data = _data("c2", 4, 12000)
+    ob = data.obs[0]
+    dp, pix, wts = _pointing_ops(obs)
+    pix.apply(data)
+    dist = data["pixel_dist"]
+    mask = PixelData(dist, np.uint8, n_value=1)
+    rng = np.random.default_rng(8)
+    mask.data[:] = rng.integers(0, 4, mask.data.shape).astype(np.uint8)
+    data["mask"] = mask
+    before = ob.detdata["flags"].data.copy()
+    ops.ScanMask(det_flags="flags", det_flags_value=4, pixels="pixels", mask_key="mask",
+                 mask_bits=2, view="scanning").apply(data)
+    expect = before.copy()
+    p = ob.detdata["pixels"].data
+    for iv in obs["intervals"]:
+        a, b = int(iv["first"]), int(iv["last"])
+        sm, lp = dist.global_pixel_to_submap(p[:, a:b])
+        ok = sm >= 0
+        hit = np.zeros(sm.shape, dtype=bool)
+        hit[ok] = (mask.data[sm[ok], lp[ok], 0] & 2) != 0
+        expect[:, a:b] |= np.where(hit, 4, 0).astype(np.uint8)
+    np.testing.assert_array_equal(ob.detdata["flags"].data, expect)
+    assert (expect != before).any()

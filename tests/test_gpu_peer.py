@@ -105,3 +105,77 @@ def test_two_rank_peer_reduction_matches_nccl():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-14
+
+
+def _solve_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "1"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from toast_b200.solver import DeviceObservation, Destriper
+
+        n_det, n_samp, nside = 6, 24000, 64
+        obs = S.make_observation("c4", n_det=n_det, n_samp=n_samp, nside=nside, eps_max=0.03)
+        # the full problem (setup stages from the oracle) ...
+        pb = O.build_problem(obs, O)
+        # ... and this rank's detector shard of it
+        per = n_det // world
+        sl = slice(rank * per, (rank + 1) * per)
+        asl = slice(rank * per * int(pb.n_amp_views.sum()), (rank + 1) * per * int(pb.n_amp_views.sum()))
+        dobs = DeviceObservation(
+            focalplane=obs["focalplane"][sl], boresight=obs["boresight"],
+            intervals=obs["intervals"], det_scale=pb.det_scale[sl], step_length=pb.step_length,
+            nside=pb.nside, nest=pb.nest, n_pix_submap=pb.n_pix_submap, n_submap=pb.n_submap,
+            global2local=pb.global2local, epsilon=obs["epsilon"][sl], gamma=obs["gamma"][sl],
+            cal=obs["cal"][sl], shared_flags=pb.shared_flags, shared_flag_mask=1,
+            solver_flags=np.ascontiguousarray(pb.solver_flags[sl]), solver_flag_mask=1,
+            device=torch.device("cuda", rank))
+        dobs.expand_pointing(np.zeros(pb.n_submap, dtype=np.uint8))
+        res = {}
+        for fused in (True, False):
+            ds = Destriper([dobs], pb.n_local_submap, pb.n_pix_submap, pb.cov,
+                           pb.offset_var[asl], pb.amp_flags[asl], fused_reduce=fused,
+                           device=torch.device("cuda", rank))
+            assert (ds.peer is not None) == fused
+            rhs = ds.rhs([torch.from_numpy(np.ascontiguousarray(obs["signal"][sl])).cuda()])
+            amps, hist = ds.solve(rhs, n_iter_max=8)
+            res[fused] = (rhs.cpu().numpy(), hist)
+        if rank == 0:
+            rhs_ref = O.solver_rhs(pb, O, obs["signal"])
+            _, hist_ref = O.solve(pb, O, rhs_ref, n_iter_max=8)
+            out.put((res[True][0], res[False][0], rhs_ref[asl], res[True][1], res[False][1],
+                     hist_ref))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_destriper_matches_single_rank_oracle():
+    """Detector-sharded solve on 2 GPUs (fused peer reduction and NCCL) against the oracle's
+    single-process solve of the whole problem: RHS to 1e-10, residual history per the
+    reproducibility envelope."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_solve_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rhs_f, rhs_n, rhs_ref, hist_f, hist_n, hist_ref = out.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    H.assert_close_norm(rhs_f, rhs_ref, what="RHS shard (fused)")
+    H.assert_close_norm(rhs_n, rhs_ref, what="RHS shard (NCCL)")
+    obs = S.make_observation("c4", n_det=6, n_samp=24000, nside=64, eps_max=0.03)
+    pb = O.build_problem(obs, O)
+    env = H.pcg_envelope(pb, O.solver_rhs(pb, O, obs["signal"]), 8)
+    H.assert_history_matches(hist_f, hist_ref, env, what="2-rank fused")
+    H.assert_history_matches(hist_n, hist_ref, env, what="2-rank NCCL")

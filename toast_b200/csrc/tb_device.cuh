@@ -150,11 +150,6 @@ __device__ __forceinline__ double seg_sum(double v, const Runs &r) {
 }
 
 // ---- on-the-fly pointing ---------------------------------------------------------------------
-struct DetPointing {
-    tbm::Quat fp;
-    double cal, eta, gamma;
-};
-
 // boresight (x) detector quaternion with flagged samples -> identity boresight
 // (ops_pointing_detector.cpp:33-68)
 __device__ __forceinline__ tbm::Quat detector_quat(const double *boresight, int64_t s, bool flagged,

@@ -11,5 +11,6 @@ from .mapmaker_utils import (  # noqa: F401
     CovarianceAndHits,
     NoiseWeight,
     ScanMap,
+    ScanMask,
 )
 from .mapmaker import MapMaker, TemplateMatrix  # noqa: F401

@@ -70,6 +70,46 @@ class ScanMap(Operator):
         return {"detdata": [self.det_data]}
 
 
+class ScanMask(Operator):
+    """ops/scan_map/scan_map.py:216-357: raise `det_flags_value` in the detector flags wherever
+    the sample's pixel has any of `mask_bits` set in the integer mask map.  The reference does
+    this on the host with numpy; here the mask is gathered with the scan_map kernel."""
+
+    _defaults = dict(det_mask=1, det_flags="flags", det_flags_value=1, det_flag_mask=1,
+                     view=None, pixels="pixels", mask_key=None, mask_bits=255)
+
+    def _exec(self, data, detectors=None, use_accel=False, **kwargs):
+        if self.mask_key not in data:
+            raise RuntimeError(f"The mask_key '{self.mask_key}' does not exist in the data")
+        mask = data[self.mask_key]
+        dist = mask.distribution
+        if mask.n_value != 1:
+            raise RuntimeError("The mask map must have one value per pixel")
+        hit = PixelData(dist, np.float64, n_value=1)
+        hit.data[:] = (mask.data.astype(np.int64) & int(self.mask_bits)) != 0
+        for ob in data.obs:
+            dets = _dets(ob, detectors, self.det_mask)
+            if len(dets) == 0:
+                continue
+            ob.detdata.ensure(self.det_flags, dtype=np.uint8, detectors=ob.local_detectors)
+            pix = ob.detdata[self.pixels]
+            tmp = np.zeros((len(dets), ob.n_local_samples))
+            ones = np.ones((len(dets), ob.n_local_samples))
+            didx = np.arange(len(dets), dtype=np.int32)
+            K.ops_scan_map_float64(dist.global_submap_to_local, dist.n_pix_submap, hit.data, tmp,
+                                   didx, pix.data, pix.indices(dets), ones, didx,
+                                   ob.intervals[self.view], 1.0, True, False, False, False)
+            fl = ob.detdata[self.det_flags]
+            rows = fl.indices(dets)
+            fl.data[rows] |= np.where(tmp != 0, np.uint8(self.det_flags_value), np.uint8(0))
+
+    def _requires(self):
+        return {"global": [self.mask_key], "detdata": [self.pixels]}
+
+    def _provides(self):
+        return {"detdata": [self.det_flags]}
+
+
 class BuildNoiseWeighted(Operator):
     _defaults = dict(pixel_dist=None, zmap=None, view=None, det_data="signal", det_mask=1,
                      det_flags="flags", det_flag_mask=1, shared_flags="flags",

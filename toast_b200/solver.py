@@ -111,23 +111,13 @@ class DeviceObservation:
                          self.nest, self.epsilon, self.gamma, self.cal, self.IAU)
         self._handle = None
 
-    def hit_submaps(self):
-        hits = np.zeros(self.n_submap, dtype=np.uint8)
-        idx = np.arange(self.n_det, dtype=np.int32)
-        K.pointing_fused(self.focalplane, self.boresight, self.shared_flags,
-                         self.shared_flag_mask, None, None, idx, self._scratch_pixels(), None,
-                         None, None, self.intervals, hits, self.n_pix_submap, self.nside,
-                         self.nest, self.epsilon, self.gamma, self.cal, self.IAU)
-        return hits
-
-    def _scratch_pixels(self):
-        if self.pixels is None:
-            self.pixels = torch.zeros((self.n_det, self.n_samp), dtype=torch.int64,
-                                      device=self.device)
-        return self.pixels
-
     def set_global2local(self, g2l):
         self.global2local = np.ascontiguousarray(g2l, dtype=np.int64)
+        self._handle = None
+
+    def invalidate(self):
+        """Call after changing flags / pointing in place: the native handle (and its compact
+        copy of the pointing) is rebuilt on next use."""
         self._handle = None
 
     # -- native handle ------------------------------------------------------------------------
@@ -247,7 +237,6 @@ class Destriper:
         self.amp_flags = _dev_tensor(amp_flags, self.device, torch.uint8)
         self.n_amp = int(self.offset_var.numel())
         assert sum(o.n_amp for o in self.obs) == self.n_amp
-        self._scal = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(group)
