@@ -10,7 +10,10 @@
 namespace tbd {
 
 constexpr int kThreads = 256;          // threads per CTA
-constexpr int kPerThread = 4;          // samples per thread per tile
+#ifndef TB_PER_THREAD
+#define TB_PER_THREAD 4
+#endif
+constexpr int kPerThread = TB_PER_THREAD; // samples per thread per tile
 constexpr int kTile = kThreads * kPerThread; // samples per tile (flattened interval space)
 
 // The reference loops `for view: for isamp in [first, last)`.  We flatten that iteration
