@@ -494,7 +494,12 @@ def main_gpu(args):
             "fallback 6650 GB/s (B200_PROFILING.md)"
         compact = dobs.has_compact_pointing() and not args.regen
         pair = compact and lib.tb_get_option(b"pair") == 1 and lib.tb_get_option(b"compact") == 1
-        if pair:
+        pairw = pair and lib.tb_get_option(b"pairw") == 1 and \
+            bool(lib.tb_obs_has_pair_weights(dobs.handle().h))
+        if pairw:
+            names = ("k_lhs_pairw<0> (pass 1: template -> noise-weighted map)",
+                     "k_lhs_pairw<1> (pass 2: scan - weight - project)")
+        elif pair:
             names = ("k_lhs_pair<0> (pass 1: template -> noise-weighted map)",
                      "k_lhs_pair<1> (pass 2: scan - weight - project)")
         elif compact:
@@ -508,7 +513,7 @@ def main_gpu(args):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
         # `ncu --set full` capture of THIS workload (profiles/r1_ncu_passes.txt); null otherwise
         traffic = None
-        if pair and args.workload == "c4" and args.scale == 1.0 and world == 1:
+        if pair and not pairw and args.workload == "c4" and args.scale == 1.0 and world == 1:
             traffic = NCU_TRAFFIC_PASS1 if p1 >= p2 else NCU_TRAFFIC_PASS2
         alg_bytes = info["det_samples"] * BYTES_PER_SAMPLE_PASS
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
@@ -527,12 +532,15 @@ def main_gpu(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "pass1_ms": p1, "pass2_ms": p2, "reduce_cov_ms": pr,
-                "map_reduction": "fused P2P reduce-scatter + cov + all-gather kernel"
+                "map_reduction_tuning_ms": getattr(ds.peer, "tune_ms", None),
+                "map_reduction": ("fused NVLS kernel: multimem.ld_reduce + cov + multimem.st"
+                                  if getattr(ds.peer, "use_multimem", False) else
+                                  "fused P2P reduce-scatter + cov + all-gather kernel")
                                  if ds.peer is not None else
                                  ("NCCL all-reduce + cov_apply" if world > 1 else "cov_apply"),
                 "zmap_bytes": int(ds.zmap.numel() * 8),
-                "streamed_bytes_per_sample_per_pass": 20 if dobs.has_compact_pointing()
-                and not args.regen else (1 if args.regen else 33),
+                "streamed_bytes_per_sample_per_pass": (12 if pairw else 20) if compact
+                else (1 if args.regen else 33),
                 "iteration_effective_gbs_per_gpu": iter_gbs,
                 "iteration_frac_of_peak": iter_gbs / peak,
             },

@@ -302,6 +302,16 @@ void *tb_peer_map_ptr(tb_peer *peer);
 /* n_pix = n_local_submap * n_pix_submap (multiple of 256); cov [n_pix,6] device pointer. */
 int tb_map_reduce_cov(tb_peer *peer, int64_t n_pix, const double *cov, void *stream);
 void tb_peer_destroy(tb_peer *peer);
+/* NVLS form: attach to buffers the caller already made peer-visible (symmetric memory).
+ * `maps` / `flags` are world-long, rank-ordered arrays of device addresses (flags: 2 x 16 uint64
+ * per rank, zeroed); mc_map is the NVSwitch MULTICAST address of the map buffer (0 = none).  With
+ * a multicast address tb_map_reduce_cov sums the map inside the switch (multimem.ld_reduce),
+ * applies the covariance to this rank's slice and broadcasts it with multimem.st: about
+ * (1 + 1/N) |map| of NVLink traffic per direction instead of 2 (N-1)/N |map|.                 */
+tb_peer *tb_peer_attach(int rank, int world, size_t map_bytes, const uint64_t *maps,
+                        const uint64_t *flags, uint64_t mc_map);
+int tb_peer_has_multicast(const tb_peer *peer);
+int tb_peer_set_multimem(int on); /* A/B switch: 0 = P2P kernel even when multicast exists */
 
 /* ---- a12/a13  amplitude-vector arithmetic for the PCG loop (templates/amplitudes.py:201-274,
  * :523-571; ops/mapmaker_solve.py:665-746).  All DEVICE pointers; scalars live on the device
@@ -325,11 +335,18 @@ int tb_pcg_direction(const double *delta_new, const double *delta_old, double *d
  * discarded and the general kernels keep running.                                           */
 int tb_obs_pack_pointing(tb_obs *obs, void *stream);
 int tb_obs_has_compact_pointing(const tb_obs *obs);
+/* 1 if packing also found (and verified on every in-interval sample, to 1e-13 relative) that the
+ * (Q,U) weights of every detector pair (2p, 2p+1) are related by a fixed per-pair rotation-scale
+ * (ops_stokes_weights.cpp:95-139: both are eta*cal*(cos,sin) of angles that differ by a
+ * constant).  The LHS passes then stream one weight record per PAIR: 12 B / det-sample.      */
+int tb_obs_has_pair_weights(const tb_obs *obs);
 
 /* Runtime options (A/B measurements, debugging):
  *   "compact" (default 1)  use the compact pointing in the LHS passes when it has been packed
  *   "pair"    (default 1)  process detector rows two at a time so that co-pointed detectors
  *                          (polarisation pairs) share one RED triple / map gather per sample
+ *   "pairw"   (default 1)  with "pair": stream one (Q,U) record per detector pair when the
+ *                          packed pointing verified the fixed weight rotation of every pair
  *   "tma"     (default 0)  stage the stored-pointing LHS passes through shared memory with
  *                          cp.async.bulk + mbarrier (measured slower than direct loads)     */
 int tb_set_option(const char *name, int value);

@@ -12,7 +12,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from toast_b200 import kernels as KC  # noqa: E402
-from toast_b200.solver import PeerMap  # noqa: E402
+from toast_b200.solver import PeerMap, SymmPeerMap  # noqa: E402
+from toast_b200 import lib as L  # noqa: E402
 
 
 def main():
@@ -47,6 +48,15 @@ def main():
         res[name] = float(t.item())
 
     timeit(lambda: pm.reduce_cov(cov), "fused_p2p_reduce_cov_ms")
+    try:
+        sm = SymmPeerMap(n_pix, dev)
+        sm.tensor.copy_(z)
+        timeit(lambda: sm.reduce_cov(cov), "fused_nvls_reduce_cov_ms")
+        L.load().tb_peer_set_multimem(0)
+        timeit(lambda: sm.reduce_cov(cov), "fused_p2p_on_symm_ms")
+        L.load().tb_peer_set_multimem(1)
+    except Exception as exc:  # noqa: BLE001
+        res["nvls_error"] = repr(exc)[:300]
     timeit(lambda: dist.all_reduce(z), "nccl_allreduce_ms")
     timeit(lambda: KC.cov_apply_diag(n_loc, nps, 3, cov, z), "cov_apply_ms")
     if rank == 0:
@@ -55,6 +65,9 @@ def main():
         res["world"] = world
         per_dir = nbytes * (world - 1) / world
         res["fused_gbs_per_direction_per_gpu"] = per_dir / (res["fused_p2p_reduce_cov_ms"] * 1e-3) / 1e9
+        if "fused_nvls_reduce_cov_ms" in res:
+            res["nvls_gbs_per_direction_per_gpu"] = nbytes * (1 + 1 / world) / (
+                res["fused_nvls_reduce_cov_ms"] * 1e-3) / 1e9
         res["nccl_busbw_gbs"] = 2 * per_dir / (res["nccl_allreduce_ms"] * 1e-3) / 1e9
         print(json.dumps(res))
     dist.destroy_process_group()

@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "toast_b200.h")
 
 _CT = {
     "int64_t": tbl.I64, "int32_t": tbl.I32, "uint8_t": tbl.U8, "double": tbl.F64,
-    "int": tbl.INT, "size_t": tbl.SZ,
+    "int": tbl.INT, "size_t": tbl.SZ, "uint64_t": ct.c_uint64,
 }
 
 

@@ -168,7 +168,8 @@ def test_lhs_kernel_variants_agree(perm):
     lib = L.load()
     results = {}
     try:
-        for name, opts in (("pair", dict(pair=1, compact=1, tma=0)),
+        for name, opts in (("pairw", dict(pair=1, pairw=1, compact=1, tma=0)),
+                           ("pair", dict(pair=1, pairw=0, compact=1, tma=0)),
                            ("compact", dict(pair=0, compact=1, tma=0)),
                            ("tma", dict(pair=0, compact=0, tma=1)),
                            ("general", dict(pair=0, compact=0, tma=0))):
@@ -179,10 +180,16 @@ def test_lhs_kernel_variants_agree(perm):
             ds.lhs(torch.from_numpy(a).cuda(), q)
             results[name] = q.cpu().numpy()
             assert_close_norm(results[name], ref, what=f"LHS ({name})")
+            if name == "pairw":
+                # the shared-weight form is only taken when every pair (2p, 2p+1) is a real
+                # polarisation pair (fixed weight rotation, verified sample by sample)
+                co_pointed = all(perm[i] // 2 == perm[i + 1] // 2
+                                 for i in range(0, len(perm) - 1, 2))
+                assert bool(lib.tb_obs_has_pair_weights(dobs.handle().h)) == co_pointed
     finally:
-        for k, v in dict(pair=1, compact=1, tma=0).items():
+        for k, v in dict(pair=1, pairw=1, compact=1, tma=0).items():
             lib.tb_set_option(k.encode(), v)
-    for name in ("compact", "tma", "general"):
+    for name in ("pairw", "compact", "tma", "general"):
         assert_close_norm(results[name], results["pair"], rtol=1e-12, what=f"{name} vs pair")
 
 

@@ -28,6 +28,10 @@ struct tb_peer {
     unsigned int *counter = nullptr;       // local block counter
     unsigned long long epoch = 0;
     bool opened = false;
+    // attached form (tb_peer_attach): buffers are owned by the caller (symmetric memory set up by
+    // the host plumbing); mc_map is the NVLS multicast address of the same map buffer, or NULL
+    bool owned = true;
+    double *mc_map = nullptr;
 };
 
 namespace {
@@ -166,9 +170,153 @@ k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *
     }
 }
 
+// ---- NVLS variant: the NVSwitch does the reduction and the broadcast ----------------------------
+// `mc` is the multicast address of the map (one virtual address bound to the same buffer on every
+// GPU of the node).  multimem.ld_reduce pulls one element from ALL GPUs and returns the sum formed
+// inside the switch; multimem.st pushes one copy that the switch replicates to ALL GPUs.  Per GPU
+// the NVLink traffic falls from 2 (N-1)/N |map| per direction (P2P reduce-scatter + all-gather) to
+// about (1 + 1/N) |map|, and the SM issues 1/N of the loads and stores.  fp64 multimem.ld_reduce
+// exists as a scalar only (ptxas: no .v2.f64), so loads are 8-byte, perfectly coalesced; the
+// stores go out as 16-byte .v4.f32 bit patterns.
+__device__ __forceinline__ double mc_ld_reduce_f64(const double *p) {
+    double v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_16(double2 *p, double2 v) {
+    unsigned a = (unsigned)__double2loint(v.x), b = (unsigned)__double2hiint(v.x);
+    unsigned c = (unsigned)__double2loint(v.y), d = (unsigned)__double2hiint(v.y);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p),
+                 "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)),
+                 "f"(__uint_as_float(d))
+                 : "memory");
+}
+
+constexpr int kMcPer = kPeerTile * 3 / kPeerThreads; // 6 doubles per thread per tile
+
+__global__ void __launch_bounds__(kPeerThreads)
+k_map_reduce_cov_mc(PeerArgs a, double *mc, int64_t tile_first, int64_t n_tiles,
+                    const double *__restrict__ cov) {
+    __shared__ double sh[kPeerTile * 3];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    const int world = a.world;
+
+    // ---- start barrier: every rank has finished writing its local map (pass 1) ------------
+    if (blockIdx.x == 0 && tid < world) {
+        __threadfence_system();
+        st_release_sys(a.flags[tid] + a.rank, a.epoch);
+    }
+    if (tid < world) {
+        const unsigned long long *f = a.flags[a.rank] + tid;
+        while (ld_acquire_sys(f) < a.epoch) {
+        }
+    }
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t e0 = (tile_first + tile) * (int64_t)(kPeerTile * 3); // double index
+        double v[kMcPer];
+#pragma unroll
+        for (int k = 0; k < kMcPer; ++k) v[k] = mc_ld_reduce_f64(mc + e0 + k * kPeerThreads + tid);
+#pragma unroll
+        for (int k = 0; k < kMcPer; ++k) sh[k * kPeerThreads + tid] = v[k];
+        __syncthreads();
+        {
+            double *z = sh + 6 * tid; // thread t owns pixels 2t, 2t+1 of the tile
+            const double *c = cov + ((tile_first + tile) * (int64_t)kPeerTile + 2 * tid) * 6;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const double *m = c + 6 * p;
+                double v0 = z[3 * p], v1 = z[3 * p + 1], v2 = z[3 * p + 2];
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0; // order of toast_map_cov.cpp:509-517
+                t0 += __ldg(m) * v0;
+                t0 += __ldg(m + 1) * v1;
+                t1 += __ldg(m + 1) * v0;
+                t0 += __ldg(m + 2) * v2;
+                t2 += __ldg(m + 2) * v0;
+                t1 += __ldg(m + 3) * v1;
+                t1 += __ldg(m + 4) * v2;
+                t2 += __ldg(m + 4) * v1;
+                t2 += __ldg(m + 5) * v2;
+                z[3 * p] = t0;
+                z[3 * p + 1] = t1;
+                z[3 * p + 2] = t2;
+            }
+        }
+        __syncthreads();
+        const double2 *sh2 = reinterpret_cast<const double2 *>(sh);
+        double2 *dst = reinterpret_cast<double2 *>(mc + e0);
+#pragma unroll
+        for (int k = 0; k < kPeerPer; ++k) mc_st_16(dst + k * kPeerThreads + tid, sh2[k * kPeerThreads + tid]);
+        __syncthreads();
+    }
+
+    // ---- end barrier: every rank's slice has landed in my map ------------------------------
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int done = atomicAdd(a.counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        if (tid < world) {
+            __threadfence_system();
+            st_release_sys(a.flags[tid] + kMaxPeers + a.rank, a.epoch);
+            const unsigned long long *f = a.flags[a.rank] + kMaxPeers + tid;
+            while (ld_acquire_sys(f) < a.epoch) {
+            }
+        }
+        if (tid == 0) *a.counter = 0u;
+    }
+}
+
+int g_use_multimem = 1; // tb_set_option("multimem", 0/1)
+
 } // namespace
 
 extern "C" {
+
+int tb_peer_set_multimem(int on) {
+    g_use_multimem = on ? 1 : 0;
+    return 0;
+}
+
+// Attach to buffers the caller has already made peer-visible (symmetric memory): `maps` and
+// `flags` are world-long arrays of device addresses, rank-ordered (flags: 2 x 16 u64 per rank,
+// zeroed); mc_map is the NVLS multicast address of the map buffer or NULL.
+tb_peer *tb_peer_attach(int rank, int world, size_t map_bytes, const uint64_t *maps,
+                        const uint64_t *flags, uint64_t mc_map) {
+    try {
+        tbr::require_device();
+        TB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+                   "bad rank / world size");
+        TB_REQUIRE(maps && flags, "NULL argument");
+        tb_peer *p = new tb_peer();
+        p->rank = rank;
+        p->world = world;
+        p->map_bytes = map_bytes;
+        p->owned = false;
+        for (int q = 0; q < world; ++q) {
+            TB_REQUIRE(maps[q] != 0 && flags[q] != 0, "NULL peer address");
+            p->peer_map[q] = reinterpret_cast<double *>(maps[q]);
+            p->peer_flags[q] = reinterpret_cast<unsigned long long *>(flags[q]);
+        }
+        p->map = p->peer_map[rank];
+        p->flags = p->peer_flags[rank];
+        p->mc_map = reinterpret_cast<double *>(mc_map);
+        TB_CUDA(cudaMalloc(&p->counter, sizeof(unsigned int)));
+        TB_CUDA(cudaMemset(p->counter, 0, sizeof(unsigned int)));
+        p->opened = true;
+        return p;
+    } catch (const tbr::Error &e) {
+        tbr::set_error(e.code, e.msg);
+        return nullptr;
+    }
+}
+
+int tb_peer_has_multicast(const tb_peer *p) { return (p && p->mc_map) ? 1 : 0; }
 
 tb_peer *tb_peer_create(int rank, int world, size_t map_bytes) {
     try {
@@ -251,6 +399,15 @@ int tb_map_reduce_cov(tb_peer *p, int64_t n_pix, const double *cov, void *stream
     int64_t cap = (int64_t)tbr::sm_count() * 12;
     if (grid > cap) grid = cap;
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->mc_map != nullptr && g_use_multimem && p->world > 1) {
+        int64_t gm = mine < 1 ? 1 : mine;
+        int64_t capm = (int64_t)tbr::sm_count() * 8;
+        if (gm > capm) gm = capm;
+        k_map_reduce_cov_mc<<<(unsigned)gm, kPeerThreads, 0, st>>>(a, p->mc_map, first, mine, cov);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        return TB_OK;
+    }
     switch (p->world) {
     case 2: k_map_reduce_cov<2><<<(unsigned)grid, kPeerThreads, 0, st>>>(a, first, mine, cov); break;
     case 4: k_map_reduce_cov<4><<<(unsigned)grid, kPeerThreads, 0, st>>>(a, first, mine, cov); break;
@@ -264,6 +421,11 @@ int tb_map_reduce_cov(tb_peer *p, int64_t n_pix, const double *cov, void *stream
 
 void tb_peer_destroy(tb_peer *p) {
     if (!p) return;
+    if (!p->owned) {
+        if (p->counter) cudaFree(p->counter);
+        delete p;
+        return;
+    }
     for (int q = 0; q < p->world; ++q) {
         if (q == p->rank) continue;
         if (p->peer_map[q]) cudaIpcCloseMemHandle(p->peer_map[q]);

@@ -36,6 +36,11 @@ struct tb_obs {
     // and the two sample-dependent weights (Q, U) as one 16-byte record
     int32_t *lpix = nullptr;
     double2 *wqu = nullptr;
+    // detector-pair form of the compact pointing (tb_obs_pack_pointing): both local pixels of a
+    // pair as one 8-byte record, and the fixed 2x2 rotation-scale that maps the (Q,U) weights of
+    // detector 2p onto those of detector 2p+1 -- verified sample by sample while packing
+    int2 *lpp = nullptr;        // [n_pair][n_samp]
+    double2 *pair_rot = nullptr; // [n_pair] (A, B): (q1, u1) = (A q0 - B u0, B q0 + A u0)
 };
 
 namespace {
@@ -61,6 +66,8 @@ struct ObsDev {
     int64_t n_tiles;
     const int32_t *lpix;
     const double2 *wqu;
+    const int2 *lpp;
+    const double2 *pair_rot;
 };
 
 __device__ unsigned long long g_exact_count_solver = 0ull;
@@ -717,6 +724,199 @@ k_lhs_pair(ObsDev o, int64_t n_pair, const double *__restrict__ amps,
 
 int g_use_pair = 1; // tb_set_option("pair", 0/1)
 
+// =================================================================================================
+// Detector pairs with SHARED weights (12 B per det-sample).
+//
+// The (Q,U) weights of the two detectors of a polarisation pair are not independent: both are
+// eta*cal*(cos, sin) of an angle that differs by a constant (2 x the polariser offset, +4 x the
+// gamma offset with a HWP), i.e. (q1,u1) = [[A,-B],[B,A]] (q0,u0) with a per-pair constant
+// (A, B) -- (-1, 0) for the usual orthogonal pair.  tb_obs_pack_pointing fits (A, B) from one
+// sample and VERIFIES the relation on every in-interval sample of the pair to 1e-13 relative
+// (three orders inside the 1e-10 parity bar); only then are these kernels used.  A pair-sample is
+// then one 8-byte record (both local pixels) + one 16-byte record (q0,u0): 24 B / 2 det-samples.
+// =================================================================================================
+__device__ unsigned int g_pair_mismatch = 0u;
+
+__global__ void k_pair_fit(ObsDev o, int64_t n_pair, int64_t s_fit, double2 *__restrict__ rot) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pair) return;
+    int64_t d0 = 2 * p, d1 = d0 + 1;
+    double A = 0.0, B = 0.0;
+    if (d1 < o.n_det) {
+        double2 a = o.wqu[d0 * o.n_samp + s_fit], b = o.wqu[d1 * o.n_samp + s_fit];
+        double n2 = a.x * a.x + a.y * a.y;
+        if (n2 > 0.0) {
+            A = (b.x * a.x + b.y * a.y) / n2;
+            B = (b.y * a.x - b.x * a.y) / n2;
+            // orthogonal / parallel pairs: snap to the exact rotation
+            if (fabs(A - rint(A)) < 1e-14 && fabs(B - rint(B)) < 1e-14) {
+                A = rint(A);
+                B = rint(B);
+            }
+        }
+    }
+    rot[p] = make_double2(A, B);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_pack_pairs(ObsDev o, int64_t n_pair, const double2 *__restrict__ rot, int2 *__restrict__ lpp) {
+    const int64_t total = n_pair * o.V.total;
+    unsigned bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t p = i / o.V.total;
+        int64_t t = i - p * o.V.total;
+        int view = o.V.n_view > 1 ? find_view(o.V, t) : 0;
+        int64_t s = __ldg(o.V.first + view) + (t - __ldg(o.V.prefix + view));
+        int64_t d0 = 2 * p, d1 = d0 + 1;
+        int64_t i0 = d0 * o.n_samp + s;
+        int2 lp = make_int2(__ldcs(o.lpix + i0), -1);
+        if (d1 < o.n_det) {
+            int64_t i1 = i0 + o.n_samp;
+            lp.y = __ldcs(o.lpix + i1);
+            double2 a = __ldcs(o.wqu + i0), b = __ldcs(o.wqu + i1), r = __ldg(rot + p);
+            double ex = b.x - (r.x * a.x - r.y * a.y);
+            double ey = b.y - (r.y * a.x + r.x * a.y);
+            double n2 = b.x * b.x + b.y * b.y;
+            if (!(ex * ex + ey * ey <= 1e-26 * n2)) bad = 1;
+        }
+        lpp[p * o.n_samp + s] = lp;
+    }
+    if (bad) atomicOr(&g_pair_mismatch, 1u);
+}
+
+#ifndef TB_PAIRW_CTAS
+#define TB_PAIRW_CTAS 8
+#endif
+template <bool PASS2>
+__global__ void __launch_bounds__(kThreads, TB_PAIRW_CTAS)
+k_lhs_pairw(ObsDev o, int64_t n_pair, const double *__restrict__ amps,
+            const uint8_t *__restrict__ aflags, const double *__restrict__ binned,
+            double *__restrict__ out) {
+    TileId _tile = tile_of_block(blockIdx.x, n_pair);
+    const int d0 = 2 * _tile.det;
+    const bool has1 = (d0 + 1) < o.n_det;
+    const int d1 = has1 ? d0 + 1 : d0;
+    const int lane = threadIdx.x & 31;
+    const double scale0 = __ldg(o.det_scale + d0), scale1 = __ldg(o.det_scale + d1);
+    const double c0 = __ldg(o.cal + d0), c1 = __ldg(o.cal + d1);
+    const double2 rot = __ldg(o.pair_rot + _tile.det);
+    const int64_t ao0 = __ldg(o.amp_offsets + d0), ao1 = __ldg(o.amp_offsets + d1);
+    ViewCursor vc = view_cursor(o.V, _tile.t0 + threadIdx.x);
+#pragma unroll 2
+    for (int k = 0; k < kPerThread; ++k) {
+        int64_t t = _tile.t0 + (int64_t)k * kThreads + threadIdx.x;
+        int64_t keyA = -1, keyB = -1;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+        if (t < o.V.total) {
+            view_seek(o.V, vc, t);
+            const int view = vc.view;
+            int64_t off = t - vc.beg;
+            int64_t ip = (int64_t)_tile.det * o.n_samp + vc.first + off;
+            int64_t i0 = ip + (int64_t)_tile.det * o.n_samp; // row 2p of the per-detector array
+            int2 lp = __ldcs(o.lpp + ip);
+            double2 wq0 = __ldcs(o.wqu + i0);
+            const int32_t lp0 = lp.x, lp1 = lp.y;
+            double2 wq1 = make_double2(rot.x * wq0.x - rot.y * wq0.y, rot.y * wq0.x + rot.x * wq0.y);
+            int64_t rel = __ldg(o.amp_view_off + view) + fast_div(off, o.inv_step);
+            int64_t amp0 = ao0 + rel, amp1 = ao1 + rel;
+            bool ok0 = __ldg(aflags + amp0) == 0;
+            bool ok1 = has1 && (__ldg(aflags + amp1) == 0);
+            double tod0 = ok0 ? __ldg(amps + amp0) : 0.0;
+            double tod1 = ok1 ? __ldg(amps + amp1) : 0.0;
+            if (!PASS2) {
+                double sd0 = tod0 * scale0, sd1 = tod1 * scale1;
+                if (lp0 >= 0) {
+                    keyA = lp0;
+                    a0 = sd0 * c0;
+                    a1 = sd0 * wq0.x;
+                    a2 = sd0 * wq0.y;
+                }
+                if (lp1 >= 0) {
+                    if (lp1 == lp0) {
+                        a0 += sd1 * c1;
+                        a1 += sd1 * wq1.x;
+                        a2 += sd1 * wq1.y;
+                    } else {
+                        keyB = lp1;
+                        b0 = sd1 * c1;
+                        b1 = sd1 * wq1.x;
+                        b2 = sd1 * wq1.y;
+                    }
+                }
+            } else {
+                if (ok0) keyA = amp0;
+                if (ok1) keyB = amp1;
+                bool need0 = ok0 && lp0 != -1, need1 = ok1 && lp1 != -1;
+                double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+                bool have = false;
+                if (need0 && lp0 >= 0) {
+                    const double *m = binned + 3 * (int64_t)lp0;
+                    m0 = __ldg(m);
+                    m1 = __ldg(m + 1);
+                    m2 = __ldg(m + 2);
+                    have = true;
+                    double sc = 0.0; // ops_scan_map.cpp:59-64
+                    sc += c0 * m0;
+                    sc += wq0.x * m1;
+                    sc += wq0.y * m2;
+                    tod0 -= sc;
+                }
+                if (need1 && lp1 >= 0) {
+                    if (!(have && lp1 == lp0)) {
+                        const double *m = binned + 3 * (int64_t)lp1;
+                        m0 = __ldg(m);
+                        m1 = __ldg(m + 1);
+                        m2 = __ldg(m + 2);
+                    }
+                    double sc = 0.0;
+                    sc += c1 * m0;
+                    sc += wq1.x * m1;
+                    sc += wq1.y * m2;
+                    tod1 -= sc;
+                }
+                if (need0) a0 = tod0 * scale0;
+                if (need1) b0 = tod1 * scale1;
+            }
+        }
+        if (!PASS2) {
+            Runs r = find_runs<kBinRunCap>(keyA, lane);
+            a0 = seg_sum<kBinRunCap>(a0, r);
+            a1 = seg_sum<kBinRunCap>(a1, r);
+            a2 = seg_sum<kBinRunCap>(a2, r);
+            if (r.is_tail && keyA >= 0) {
+                double *z = out + keyA * 3;
+                atomicAdd(z, a0);
+                atomicAdd(z + 1, a1);
+                atomicAdd(z + 2, a2);
+            }
+            if (__any_sync(0xffffffffu, keyB >= 0)) {
+                Runs rb = find_runs<kBinRunCap>(keyB, lane);
+                b0 = seg_sum<kBinRunCap>(b0, rb);
+                b1 = seg_sum<kBinRunCap>(b1, rb);
+                b2 = seg_sum<kBinRunCap>(b2, rb);
+                if (rb.is_tail && keyB >= 0) {
+                    double *z = out + keyB * 3;
+                    atomicAdd(z, b0);
+                    atomicAdd(z + 1, b1);
+                    atomicAdd(z + 2, b2);
+                }
+            }
+        } else {
+            Runs r = find_runs(keyA, lane);
+            a0 = seg_sum(a0, r);
+            if (r.is_tail && keyA >= 0) atomicAdd(out + keyA, a0);
+            if (has1) {
+                Runs rb = find_runs(keyB, lane);
+                b0 = seg_sum(b0, rb);
+                if (rb.is_tail && keyB >= 0) atomicAdd(out + keyB, b0);
+            }
+        }
+    }
+}
+
+int g_use_pairw = 1; // tb_set_option("pairw", 0/1)
+
 
 
 ObsDev make_dev(const tb_obs *obs, int regen) {
@@ -750,6 +950,8 @@ ObsDev make_dev(const tb_obs *obs, int regen) {
     o.n_tiles = obs->n_tiles;
     o.lpix = obs->lpix;
     o.wqu = obs->wqu;
+    o.lpp = obs->lpp;
+    o.pair_rot = obs->pair_rot;
     if (regen) {
         TB_REQUIRE(d.boresight != nullptr && d.focalplane != nullptr,
                    "regen needs boresight and focalplane");
@@ -810,8 +1012,13 @@ void launch_bin(const tb_obs *obs, const double *amps, const uint8_t *aflags, co
     if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
         int64_t n_pair = (o.n_det + 1) / 2;
         int64_t nbp = ((o.V.total + kTile - 1) / kTile) * n_pair;
-        auto k = k_lhs_pair<false>;
-        TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, nullptr, zmap);
+        if (g_use_pairw && o.lpp != nullptr) {
+            auto k = k_lhs_pairw<false>;
+            TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, nullptr, zmap);
+        } else {
+            auto k = k_lhs_pair<false>;
+            TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, nullptr, zmap);
+        }
     } else if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
         auto k = k_lhs_compact<false>;
         TBS_LAUNCH(k, nb, stream, o, amps, aflags, nullptr, zmap);
@@ -838,8 +1045,13 @@ void launch_project(const tb_obs *obs, const double *amps, const uint8_t *aflags
     if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
         int64_t n_pair = (o.n_det + 1) / 2;
         int64_t nbp = ((o.V.total + kTile - 1) / kTile) * n_pair;
-        auto k = k_lhs_pair<true>;
-        TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, binned, out);
+        if (g_use_pairw && o.lpp != nullptr) {
+            auto k = k_lhs_pairw<true>;
+            TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, binned, out);
+        } else {
+            auto k = k_lhs_pair<true>;
+            TBS_LAUNCH(k, nbp, stream, o, n_pair, amps, aflags, binned, out);
+        }
     } else if (!regen && !FROM_SIGNAL && g_use_compact && o.lpix != nullptr) {
         auto k = k_lhs_compact<true>;
         TBS_LAUNCH(k, nb, stream, o, amps, aflags, binned, out);
@@ -1081,6 +1293,8 @@ void tb_obs_destroy(tb_obs *obs) {
     if (obs->tiles) cudaFree(obs->tiles);
     if (obs->lpix) cudaFree(obs->lpix);
     if (obs->wqu) cudaFree(obs->wqu);
+    if (obs->lpp) cudaFree(obs->lpp);
+    if (obs->pair_rot) cudaFree(obs->pair_rot);
     delete obs;
 }
 
@@ -1108,17 +1322,61 @@ int tb_obs_pack_pointing(tb_obs *obs, void *stream) {
     TB_CUDA(cudaMemcpyFromSymbolAsync(&bad, g_pack_mismatch, sizeof(bad), 0,
                                       cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     TB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (obs->lpp) cudaFree(obs->lpp);
+    if (obs->pair_rot) cudaFree(obs->pair_rot);
+    obs->lpp = nullptr;
+    obs->pair_rot = nullptr;
     if (bad) {
         // the I weight is not the per-detector constant: keep the general kernels
         cudaFree(obs->lpix);
         cudaFree(obs->wqu);
         obs->lpix = nullptr;
         obs->wqu = nullptr;
+    } else if (obs->V.total > 0) {
+        // pair form: fit the per-pair weight rotation on the first in-interval sample, then
+        // verify it on every sample while writing the paired pixel records
+        int64_t n_pair = (obs->d.n_det + 1) / 2;
+        std::vector<int64_t> hv(obs->V.n_view * 2 + 1);
+        TB_CUDA(cudaMemcpy(hv.data(), obs->V.first, sizeof(int64_t) * hv.size(),
+                           cudaMemcpyDeviceToHost)); // first[nv], prefix[nv+1] are contiguous
+        int64_t s_fit = 0;
+        for (int v = 0; v < obs->V.n_view; ++v) {
+            if (hv[obs->V.n_view + v + 1] > hv[obs->V.n_view + v]) {
+                s_fit = hv[v];
+                break;
+            }
+        }
+        TB_CUDA(cudaMalloc(&obs->lpp, sizeof(int2) * n_pair * obs->d.n_samp));
+        TB_CUDA(cudaMalloc(&obs->pair_rot, sizeof(double2) * n_pair));
+        TB_CUDA(cudaMemsetAsync(obs->lpp, 0xFF, sizeof(int2) * n_pair * obs->d.n_samp,
+                                (cudaStream_t)stream));
+        TB_CUDA(cudaMemcpyToSymbolAsync(g_pair_mismatch, &zero, sizeof(zero), 0,
+                                        cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        o = make_dev(obs, 0);
+        k_pair_fit<<<(unsigned)((n_pair + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            o, n_pair, s_fit, obs->pair_rot);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        k_pack_pairs<<<grid, kThreads, 0, (cudaStream_t)stream>>>(o, n_pair, obs->pair_rot,
+                                                                  obs->lpp);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        unsigned pbad = 0;
+        TB_CUDA(cudaMemcpyFromSymbolAsync(&pbad, g_pair_mismatch, sizeof(pbad), 0,
+                                          cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        TB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        if (pbad) { // weights of the pair are not related by a fixed rotation: k_lhs_pair
+            cudaFree(obs->lpp);
+            cudaFree(obs->pair_rot);
+            obs->lpp = nullptr;
+            obs->pair_rot = nullptr;
+        }
     }
     TB_API_END
 }
 
 int tb_obs_has_compact_pointing(const tb_obs *obs) { return (obs && obs->lpix) ? 1 : 0; }
+int tb_obs_has_pair_weights(const tb_obs *obs) { return (obs && obs->lpp) ? 1 : 0; }
 
 int tb_get_option(const char *name) {
     if (name == nullptr) return -1;
@@ -1126,6 +1384,7 @@ int tb_get_option(const char *name) {
     if (n == "tma") return g_use_tma;
     if (n == "compact") return g_use_compact;
     if (n == "pair") return g_use_pair;
+    if (n == "pairw") return g_use_pairw;
     return -1;
 }
 
@@ -1138,6 +1397,8 @@ int tb_set_option(const char *name, int value) {
         g_use_compact = value;
     } else if (std::string(name) == "pair") {
         g_use_pair = value;
+    } else if (std::string(name) == "pairw") {
+        g_use_pairw = value;
     } else {
         throw tbr::Error{TB_ERR_ARG, std::string("unknown option: ") + name};
     }

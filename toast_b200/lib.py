@@ -107,11 +107,15 @@ PROTOTYPES = {
     "tb_peer_map_ptr": (P, [P]),
     "tb_map_reduce_cov": (INT, [P, I64, P, P]),
     "tb_peer_destroy": (None, [P]),
+    "tb_peer_attach": (P, [INT, INT, SZ, P, P, ct.c_uint64]),
+    "tb_peer_has_multicast": (INT, [P]),
+    "tb_peer_set_multimem": (INT, [INT]),
     "tb_amp_dot": (INT, [P, P, P, I64, P, P]),
     "tb_pcg_update": (INT, [P, P, P, P, P, P, P, P, P, I64, P, P]),
     "tb_pcg_direction": (INT, [P, P, P, P, I64, P]),
     "tb_obs_pack_pointing": (INT, [P, P]),
     "tb_obs_has_compact_pointing": (INT, [P]),
+    "tb_obs_has_pair_weights": (INT, [P]),
     "tb_set_option": (INT, [STR, INT]),
     "tb_get_option": (INT, [STR]),
     "tb_set_pixel_guard_scale": (None, [F64]),

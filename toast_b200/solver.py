@@ -217,6 +217,82 @@ class PeerMap:
             pass
 
 
+class SymmPeerMap:
+    """The same fused map reduction on SYMMETRIC memory with an NVLS multicast mapping
+    (``torch.distributed._symmetric_memory`` is the plumbing that allocates the buffer on every
+    rank, exchanges the handles and binds the multicast object): ``tb_map_reduce_cov`` then lets
+    the NVSwitch form the sums (``multimem.ld_reduce``) and replicate the result
+    (``multimem.st``), see tb_peer.cu."""
+
+    def __init__(self, n_pix, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.lib = L.load()
+        grp = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(grp)
+        self.world = dist.get_world_size(grp)
+        self.n_pix = int(n_pix)
+        n = self.n_pix * 3
+        self.buf = symm_mem.empty(n + 64, dtype=torch.float64, device=device)  # tail: flags
+        self.buf.zero_()
+        hdl = symm_mem.rendezvous(self.buf, grp)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("no NVLS multicast mapping for symmetric memory on this system")
+        maps = (ct.c_uint64 * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        flags = (ct.c_uint64 * self.world)(*[int(p) + n * 8 for p in hdl.buffer_ptrs])
+        self._hdl = hdl
+        self.h = self.lib.tb_peer_attach(self.rank, self.world, n * 8, maps, flags, mc)
+        if not self.h:
+            raise RuntimeError(L.last_error())
+        self.tensor = self.buf[:n]
+        self.group = group
+        self.use_multimem = True
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def reduce_cov(self, cov):
+        L.check(self.lib.tb_peer_set_multimem(1 if self.use_multimem else 0))
+        L.check(self.lib.tb_map_reduce_cov(self.h, self.n_pix, L.ptr(cov), None))
+
+    def tune(self, cov, reps=3):
+        """Measure the in-switch (multimem) and the P2P form of the kernel on this node and map
+        size and keep the faster one (max over ranks, so every rank takes the same decision):
+        in-switch reduction moves ~|map| per NVLink direction for any N, P2P 2(N-1)/N x |map|/2,
+        so which one wins depends on N."""
+        import torch.distributed as dist
+
+        saved = self.tensor.clone()
+        times = []
+        for mode in (True, False):
+            self.use_multimem = mode
+            self.reduce_cov(cov)  # warm-up
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                self.reduce_cov(cov)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / reps)
+        t = torch.tensor(times, dtype=torch.float64, device=self.tensor.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.tune_ms = {"multimem": float(t[0]), "p2p": float(t[1])}
+        self.use_multimem = bool(t[0] <= t[1])
+        self.tensor.copy_(saved)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        return self.tune_ms
+
+    def __del__(self):
+        try:
+            self.lib.tb_peer_destroy(self.h)
+        except Exception:
+            pass
+
+
 class Destriper:
     """Fused SolverRHS / SolverLHS / solve() for one or more device observations.
 
@@ -246,13 +322,22 @@ class Destriper:
         n_pix = self.n_local_submap * self.n_pix_submap
         import os as _os
         if self.world > 1 and fused_reduce and _os.environ.get("TB_FUSED_REDUCE", "1") != "0":
-            try:
-                self.peer = PeerMap(n_pix, self.device, group)
-            except Exception as exc:  # noqa: BLE001
-                import warnings
+            import warnings
 
-                warnings.warn(f"peer-memory map reduction unavailable ({exc}); using NCCL")
-                self.peer = None
+            if _os.environ.get("TB_MULTIMEM", "1") != "0":
+                try:
+                    self.peer = SymmPeerMap(n_pix, self.device, group)
+                    self.peer.tune(self.cov)
+                except Exception as exc:  # noqa: BLE001
+                    warnings.warn(f"NVLS multicast map reduction unavailable ({exc}); "
+                                  "using P2P peer memory")
+                    self.peer = None
+            if self.peer is None:
+                try:
+                    self.peer = PeerMap(n_pix, self.device, group)
+                except Exception as exc:  # noqa: BLE001
+                    warnings.warn(f"peer-memory map reduction unavailable ({exc}); using NCCL")
+                    self.peer = None
         if self.peer is not None:
             self.zmap = self.peer.tensor.view(self.n_local_submap, self.n_pix_submap, 3)
         else:
