@@ -496,7 +496,14 @@ def main_gpu(args):
         pair = compact and lib.tb_get_option(b"pair") == 1 and lib.tb_get_option(b"compact") == 1
         pairw = pair and lib.tb_get_option(b"pairw") == 1 and \
             bool(lib.tb_obs_has_pair_weights(dobs.handle().h))
-        if pairw:
+        import ctypes as ct
+        n_rec, n_rows, xp = ct.c_int64(0), ct.c_int64(0), ct.c_int(0)
+        lib.tb_obs_crossing_stats(dobs.handle().h, ct.byref(n_rec), ct.byref(n_rows), ct.byref(xp))
+        crossings = compact and lib.tb_get_option(b"crossings") == 1 and n_rec.value > 0
+        if crossings:
+            names = ("k_lhs_x<0> (pass 1: template -> noise-weighted map, crossing list)",
+                     "k_lhs_x<1> (pass 2: scan - weight - project, crossing list)")
+        elif pairw:
             names = ("k_lhs_pairw<0> (pass 1: template -> noise-weighted map)",
                      "k_lhs_pairw<1> (pass 2: scan - weight - project)")
         elif pair:
@@ -513,7 +520,7 @@ def main_gpu(args):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
         # `ncu --set full` capture of THIS workload (profiles/r1_ncu_passes.txt); null otherwise
         traffic = None
-        if pair and not pairw and args.workload == "c4" and args.scale == 1.0 and world == 1:
+        if pair and not pairw and not crossings and args.workload == "c4" and args.scale == 1.0 and world == 1:
             traffic = NCU_TRAFFIC_PASS1 if p1 >= p2 else NCU_TRAFFIC_PASS2
         alg_bytes = info["det_samples"] * BYTES_PER_SAMPLE_PASS
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
@@ -539,8 +546,10 @@ def main_gpu(args):
                                  if ds.peer is not None else
                                  ("NCCL all-reduce + cov_apply" if world > 1 else "cov_apply"),
                 "zmap_bytes": int(ds.zmap.numel() * 8),
-                "streamed_bytes_per_sample_per_pass": (12 if pairw else 20) if compact
-                else (1 if args.regen else 33),
+                "streamed_bytes_per_sample_per_pass":
+                    (round(32.0 * n_rec.value / (info["n_det"] * info["n_samp"]), 2) if crossings
+                     else (12 if pairw else 20)) if compact else (1 if args.regen else 33),
+                "crossing_records": n_rec.value if crossings else None,
                 "iteration_effective_gbs_per_gpu": iter_gbs,
                 "iteration_frac_of_peak": iter_gbs / peak,
             },

@@ -340,6 +340,11 @@ int tb_obs_has_compact_pointing(const tb_obs *obs);
  * (ops_stokes_weights.cpp:95-139: both are eta*cal*(cos,sin) of angles that differ by a
  * constant).  The LHS passes then stream one weight record per PAIR: 12 B / det-sample.      */
 int tb_obs_has_pair_weights(const tb_obs *obs);
+/* Crossing list built by tb_obs_pack_pointing: consecutive samples of a detector (pair) that share
+ * the pixel and the baseline are collapsed into one 32-byte record {lp0, lp1, n, amp | sum Q,
+ * sum U}; both LHS passes are linear in the weights, so they stream records instead of samples
+ * (tb_solver.cu: k_lhs_x).  Built only when it is the smaller stream.  n_records = 0: not built. */
+int tb_obs_crossing_stats(const tb_obs *obs, int64_t *n_records, int64_t *n_rows, int *paired);
 
 /* Runtime options (A/B measurements, debugging):
  *   "compact" (default 1)  use the compact pointing in the LHS passes when it has been packed
@@ -347,6 +352,7 @@ int tb_obs_has_pair_weights(const tb_obs *obs);
  *                          (polarisation pairs) share one RED triple / map gather per sample
  *   "pairw"   (default 1)  with "pair": stream one (Q,U) record per detector pair when the
  *                          packed pointing verified the fixed weight rotation of every pair
+ *   "crossings" (default 1) use the crossing list in the LHS passes when it has been built
  *   "tma"     (default 0)  stage the stored-pointing LHS passes through shared memory with
  *                          cp.async.bulk + mbarrier (measured slower than direct loads)     */
 int tb_set_option(const char *name, int value);

@@ -41,6 +41,12 @@ struct tb_obs {
     // detector 2p onto those of detector 2p+1 -- verified sample by sample while packing
     int2 *lpp = nullptr;        // [n_pair][n_samp]
     double2 *pair_rot = nullptr; // [n_pair] (A, B): (q1, u1) = (A q0 - B u0, B q0 + A u0)
+    // crossing list (see k_lhs_x): one record per run of samples that share pixel(s) and baseline
+    int4 *xrec = nullptr;       // [n_xrec] {lp0, lp1, n_samples, amp_rel}
+    double2 *xqu = nullptr;     // [n_xrec] sum over the run of the (Q,U) weights
+    int4 *xblocks = nullptr;    // [n_xblocks] {row, first record, end record, 0}
+    int64_t n_xrec = 0, n_xblocks = 0, n_xrows = 0;
+    int x_paired = 0;           // rows are detector pairs (weights shared through pair_rot)
 };
 
 namespace {
@@ -68,6 +74,10 @@ struct ObsDev {
     const double2 *wqu;
     const int2 *lpp;
     const double2 *pair_rot;
+    const int4 *xrec;
+    const double2 *xqu;
+    const int4 *xblocks;
+    int x_paired;
 };
 
 __device__ unsigned long long g_exact_count_solver = 0ull;
@@ -917,6 +927,208 @@ k_lhs_pairw(ObsDev o, int64_t n_pair, const double *__restrict__ amps,
 
 int g_use_pairw = 1; // tb_set_option("pairw", 0/1)
 
+// =================================================================================================
+// Crossing list.
+//
+// While a detector crosses one pixel its samples share the pixel AND (almost always) the baseline
+// amplitude, so their contributions differ only through the (Q,U) weights -- and those enter both
+// passes LINEARLY:
+//   pass 1  zmap[pix] += sum_s  a w_d (cal, q_s, u_s)        = a w_d (n cal, Q, U)
+//   pass 2  out[amp]  += sum_s  w_d (a - (cal, q_s, u_s).m)  = w_d (n a - (n cal, Q, U).m)
+// with n the number of samples of the run and (Q, U) = sum_s (q_s, u_s).  The pointing is static
+// across PCG iterations, so tb_obs_pack_pointing collapses every run of consecutive samples
+// with the same (pixel of detector 0, pixel of detector 1, baseline) into ONE 32-byte record
+// {lp0, lp1, n, amp_rel | Q, U}; runs are cut at 32-sample boundaries so that a warp builds its
+// records alone.  Both LHS passes then stream records instead of samples: 32 B per crossing of a
+// detector PAIR -- 6.7 B / det-sample at the 2.4 samples per crossing of the nside-2048
+// satellite scan, < 2 B / det-sample for ground scans -- with no segmented reduction left in
+// pass 1 (adjacent records hit different pixels) and one map gather per crossing in pass 2.
+// Flags are part of the run state (a flagged sample has lp = -1), runs with both detectors
+// flagged are dropped.  Sums are re-associated: 1e-16 relative, inside the 1e-10 parity bar.
+// =================================================================================================
+constexpr int kXPer = 4;
+constexpr int kXTile = kThreads * kXPer; // records per CTA
+
+struct XState {
+    int32_t lp0, lp1, amp_rel;
+    double2 wq;
+};
+
+// state of flat sample t of row `row` (a detector pair when paired, else one detector)
+__device__ __forceinline__ XState x_state(const ObsDev &o, int paired, int64_t row, int64_t t) {
+    XState st;
+    st.lp0 = st.lp1 = -1;
+    st.amp_rel = -1;
+    st.wq = make_double2(0.0, 0.0);
+    if (t >= o.V.total) return st;
+    int view = o.V.n_view > 1 ? find_view(o.V, t) : 0;
+    int64_t off = t - __ldg(o.V.prefix + view);
+    int64_t s = __ldg(o.V.first + view) + off;
+    int64_t d0 = paired ? 2 * row : row;
+    int64_t i0 = d0 * o.n_samp + s;
+    st.lp0 = __ldcs(o.lpix + i0);
+    st.wq = __ldcs(o.wqu + i0);
+    if (paired && d0 + 1 < o.n_det) st.lp1 = __ldcs(o.lpix + i0 + o.n_samp);
+    st.amp_rel = (int32_t)(__ldg(o.amp_view_off + view) + fast_div(off, o.inv_step));
+    return st;
+}
+
+// FILL = false: counts[chunk] = records of the chunk; FILL = true: write them at base[chunk]
+template <bool FILL>
+__global__ void __launch_bounds__(kThreads)
+k_xbuild(ObsDev o, int paired, int64_t n_rows, int64_t chunks_per_row, int32_t *__restrict__ counts,
+         const int64_t *__restrict__ base, int4 *__restrict__ xrec, double2 *__restrict__ xqu) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_chunks = n_rows * chunks_per_row;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * kThreads) >> 5;
+    for (int64_t c = warp0; c < n_chunks; c += n_warps) {
+        int64_t row = c / chunks_per_row;
+        int64_t t = (c - row * chunks_per_row) * 32 + lane;
+        XState st = x_state(o, paired, row, t);
+        int32_t p0 = __shfl_up_sync(0xffffffffu, st.lp0, 1);
+        int32_t p1 = __shfl_up_sync(0xffffffffu, st.lp1, 1);
+        int32_t pa = __shfl_up_sync(0xffffffffu, st.amp_rel, 1);
+        bool head = (lane == 0) || p0 != st.lp0 || p1 != st.lp1 || pa != st.amp_rel;
+        bool keep = !(st.lp0 == -1 && st.lp1 == -1);
+        unsigned heads = __ballot_sync(0xffffffffu, head);
+        unsigned kept_heads = __ballot_sync(0xffffffffu, head && keep);
+        if (!FILL) {
+            if (lane == 0) counts[c] = __popc(kept_heads);
+            continue;
+        }
+        unsigned upto = heads & (0xffffffffu >> (31 - lane));
+        int head_lane = 31 - __clz(upto);
+        Runs r;
+        r.dist = lane - head_lane;
+        r.is_tail = (((heads >> 1) | 0x80000000u) >> lane) & 1u;
+        double Q = seg_sum(st.wq.x, r), U = seg_sum(st.wq.y, r);
+        if (r.is_tail && keep) {
+            int64_t idx = base[c] + __popc(kept_heads & ((1u << head_lane) - 1u));
+            xrec[idx] = make_int4(st.lp0, st.lp1, r.dist + 1, st.amp_rel);
+            xqu[idx] = make_double2(Q, U);
+        }
+    }
+}
+
+int g_use_x = 1; // tb_set_option("crossings", 0/1)
+
+#ifndef TB_X_CTAS
+#define TB_X_CTAS 8
+#endif
+template <bool PASS2>
+__global__ void __launch_bounds__(kThreads, TB_X_CTAS)
+k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ aflags,
+        const double *__restrict__ binned, double *__restrict__ out) {
+    const int4 blk = __ldg(o.xblocks + blockIdx.x);
+    const int row = blk.x;
+    const int d0 = o.x_paired ? 2 * row : row;
+    const bool has1 = o.x_paired && (d0 + 1) < o.n_det;
+    const int d1 = has1 ? d0 + 1 : d0;
+    const int lane = threadIdx.x & 31;
+    const double scale0 = __ldg(o.det_scale + d0), scale1 = __ldg(o.det_scale + d1);
+    const double c0 = __ldg(o.cal + d0), c1 = __ldg(o.cal + d1);
+    double2 rot = make_double2(0.0, 0.0);
+    if (has1) rot = __ldg(o.pair_rot + row);
+    const int64_t ao0 = __ldg(o.amp_offsets + d0), ao1 = __ldg(o.amp_offsets + d1);
+#pragma unroll 2
+    for (int k = 0; k < kXPer; ++k) {
+        const int i = blk.y + k * kThreads + threadIdx.x;
+        int32_t lp0 = -1, lp1 = -1, arel = -1;
+        bool ok0 = false, ok1 = false;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+        if (i < blk.z) {
+            const int4 r = __ldcs(o.xrec + i);
+            const double2 qu = __ldcs(o.xqu + i);
+            lp0 = r.x;
+            lp1 = r.y;
+            arel = r.w;
+            const double n = (double)r.z;
+            const int64_t amp0 = ao0 + arel, amp1 = ao1 + arel;
+            ok0 = __ldg(aflags + amp0) == 0;
+            ok1 = has1 && (__ldg(aflags + amp1) == 0);
+            const double tod0 = ok0 ? __ldg(amps + amp0) : 0.0;
+            const double tod1 = ok1 ? __ldg(amps + amp1) : 0.0;
+            const double2 qu1 = make_double2(rot.x * qu.x - rot.y * qu.y, rot.y * qu.x + rot.x * qu.y);
+            if (!PASS2) {
+                const double sd0 = tod0 * scale0, sd1 = tod1 * scale1;
+                if (lp0 >= 0) {
+                    a0 = sd0 * (c0 * n);
+                    a1 = sd0 * qu.x;
+                    a2 = sd0 * qu.y;
+                }
+                if (lp1 >= 0) {
+                    if (lp1 == lp0) {
+                        a0 += sd1 * (c1 * n);
+                        a1 += sd1 * qu1.x;
+                        a2 += sd1 * qu1.y;
+                        lp1 = -1;
+                    } else {
+                        b0 = sd1 * (c1 * n);
+                        b1 = sd1 * qu1.x;
+                        b2 = sd1 * qu1.y;
+                    }
+                }
+            } else {
+                const bool need0 = ok0 && lp0 != -1, need1 = ok1 && lp1 != -1;
+                double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+                bool have = false;
+                double v0 = n * tod0, v1 = n * tod1;
+                if (need0 && lp0 >= 0) {
+                    const double *m = binned + 3 * (int64_t)lp0;
+                    m0 = __ldg(m);
+                    m1 = __ldg(m + 1);
+                    m2 = __ldg(m + 2);
+                    have = true;
+                    double sc = 0.0;
+                    sc += (c0 * n) * m0;
+                    sc += qu.x * m1;
+                    sc += qu.y * m2;
+                    v0 -= sc;
+                }
+                if (need1 && lp1 >= 0) {
+                    if (!(have && lp1 == lp0)) {
+                        const double *m = binned + 3 * (int64_t)lp1;
+                        m0 = __ldg(m);
+                        m1 = __ldg(m + 1);
+                        m2 = __ldg(m + 2);
+                    }
+                    double sc = 0.0;
+                    sc += (c1 * n) * m0;
+                    sc += qu1.x * m1;
+                    sc += qu1.y * m2;
+                    v1 -= sc;
+                }
+                if (need0) a0 = v0 * scale0;
+                if (need1) b0 = v1 * scale1;
+            }
+        }
+        if (!PASS2) {
+            if (lp0 >= 0) {
+                double *z = out + (int64_t)lp0 * 3;
+                atomicAdd(z, a0);
+                atomicAdd(z + 1, a1);
+                atomicAdd(z + 2, a2);
+            }
+            if (lp1 >= 0) { // only when the two detectors of the pair fall in different pixels
+                double *z = out + (int64_t)lp1 * 3;
+                atomicAdd(z, b0);
+                atomicAdd(z + 1, b1);
+                atomicAdd(z + 2, b2);
+            }
+        } else {
+            // adjacent records share the baseline: one segmented sum per detector, one RED per run
+            Runs r = find_runs((int64_t)arel, lane);
+            a0 = seg_sum(a0, r);
+            if (has1) b0 = seg_sum(b0, r);
+            if (r.is_tail && arel >= 0) {
+                if (ok0) atomicAdd(out + ao0 + arel, a0);
+                if (ok1) atomicAdd(out + ao1 + arel, b0);
+            }
+        }
+    }
+}
+
 
 
 ObsDev make_dev(const tb_obs *obs, int regen) {
@@ -952,6 +1164,10 @@ ObsDev make_dev(const tb_obs *obs, int regen) {
     o.wqu = obs->wqu;
     o.lpp = obs->lpp;
     o.pair_rot = obs->pair_rot;
+    o.xrec = obs->xrec;
+    o.xqu = obs->xqu;
+    o.xblocks = obs->xblocks;
+    o.x_paired = obs->x_paired;
     if (regen) {
         TB_REQUIRE(d.boresight != nullptr && d.focalplane != nullptr,
                    "regen needs boresight and focalplane");
@@ -1009,7 +1225,10 @@ void launch_bin(const tb_obs *obs, const double *amps, const uint8_t *aflags, co
                 double *zmap, int regen, void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
+    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && o.xrec != nullptr) {
+        auto k = k_lhs_x<false>;
+        TBS_LAUNCH(k, obs->n_xblocks, stream, o, amps, aflags, nullptr, zmap);
+    } else if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
         int64_t n_pair = (o.n_det + 1) / 2;
         int64_t nbp = ((o.V.total + kTile - 1) / kTile) * n_pair;
         if (g_use_pairw && o.lpp != nullptr) {
@@ -1042,7 +1261,10 @@ void launch_project(const tb_obs *obs, const double *amps, const uint8_t *aflags
                     void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
+    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && o.xrec != nullptr) {
+        auto k = k_lhs_x<true>;
+        TBS_LAUNCH(k, obs->n_xblocks, stream, o, amps, aflags, binned, out);
+    } else if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
         int64_t n_pair = (o.n_det + 1) / 2;
         int64_t nbp = ((o.V.total + kTile - 1) / kTile) * n_pair;
         if (g_use_pairw && o.lpp != nullptr) {
@@ -1295,8 +1517,94 @@ void tb_obs_destroy(tb_obs *obs) {
     if (obs->wqu) cudaFree(obs->wqu);
     if (obs->lpp) cudaFree(obs->lpp);
     if (obs->pair_rot) cudaFree(obs->pair_rot);
+    if (obs->xrec) cudaFree(obs->xrec);
+    if (obs->xqu) cudaFree(obs->xqu);
+    if (obs->xblocks) cudaFree(obs->xblocks);
     delete obs;
 }
+
+} // extern "C"
+
+// Collapse the packed pointing into the crossing list (k_lhs_x) when that is the smaller stream.
+static void build_crossings(tb_obs *obs, cudaStream_t st) {
+    if (obs->xrec) cudaFree(obs->xrec);
+    if (obs->xqu) cudaFree(obs->xqu);
+    if (obs->xblocks) cudaFree(obs->xblocks);
+    obs->xrec = nullptr;
+    obs->xqu = nullptr;
+    obs->xblocks = nullptr;
+    obs->n_xrec = obs->n_xblocks = obs->n_xrows = 0;
+    if (obs->lpix == nullptr || obs->V.total <= 0) return;
+    const int paired = obs->lpp != nullptr ? 1 : 0;
+    const int64_t n_det = obs->d.n_det;
+    const int64_t n_rows = paired ? (n_det + 1) / 2 : n_det;
+    const int64_t cpr = (obs->V.total + 31) / 32;
+    const int64_t n_chunks = n_rows * cpr;
+    ObsDev o = make_dev(obs, 0);
+    int32_t *counts = nullptr;
+    TB_CUDA(cudaMalloc(&counts, sizeof(int32_t) * n_chunks));
+    int grid = tbr::sm_count() * 8;
+    k_xbuild<false><<<grid, kThreads, 0, st>>>(o, paired, n_rows, cpr, counts, nullptr, nullptr,
+                                               nullptr);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+    std::vector<int32_t> hc(n_chunks);
+    TB_CUDA(cudaMemcpyAsync(hc.data(), counts, sizeof(int32_t) * n_chunks, cudaMemcpyDeviceToHost,
+                            st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(counts);
+    std::vector<int64_t> hb(n_chunks);
+    std::vector<int64_t> row_ptr(n_rows + 1);
+    int64_t total = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        row_ptr[r] = total;
+        for (int64_t c = r * cpr; c < (r + 1) * cpr; ++c) {
+            hb[c] = total;
+            total += hc[c];
+        }
+    }
+    row_ptr[n_rows] = total;
+    // worth it only when the records are a smaller stream than the per-sample form
+    const double per_sample = (paired ? 12.0 : 20.0) * (double)obs->V.total * (double)n_det;
+    if (total == 0 || total >= 2147483647LL || 32.0 * (double)total > 0.8 * per_sample) return;
+    int64_t *base = nullptr;
+    TB_CUDA(cudaMalloc(&base, sizeof(int64_t) * n_chunks));
+    TB_CUDA(cudaMemcpyAsync(base, hb.data(), sizeof(int64_t) * n_chunks, cudaMemcpyHostToDevice,
+                            st));
+    TB_CUDA(cudaMalloc(&obs->xrec, sizeof(int4) * total));
+    TB_CUDA(cudaMalloc(&obs->xqu, sizeof(double2) * total));
+    k_xbuild<true><<<grid, kThreads, 0, st>>>(o, paired, n_rows, cpr, nullptr, base, obs->xrec,
+                                              obs->xqu);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+    // CTA table, TIME-major like tile_of_block: tile k of every row, then tile k + 1, ... so that
+    // resident CTAs work on the same time window (= the same sky region) of all rows
+    std::vector<int4> blocks;
+    int64_t max_tiles = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t nt = (row_ptr[r + 1] - row_ptr[r] + kXTile - 1) / kXTile;
+        if (nt > max_tiles) max_tiles = nt;
+    }
+    for (int64_t k = 0; k < max_tiles; ++k) {
+        for (int64_t r = 0; r < n_rows; ++r) {
+            int64_t b = row_ptr[r] + k * kXTile;
+            if (b >= row_ptr[r + 1]) continue;
+            int64_t e = b + kXTile < row_ptr[r + 1] ? b + kXTile : row_ptr[r + 1];
+            blocks.push_back(make_int4((int)r, (int)b, (int)e, 0));
+        }
+    }
+    TB_CUDA(cudaMalloc(&obs->xblocks, sizeof(int4) * blocks.size()));
+    TB_CUDA(cudaMemcpyAsync(obs->xblocks, blocks.data(), sizeof(int4) * blocks.size(),
+                            cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(base);
+    obs->n_xrec = total;
+    obs->n_xblocks = (int64_t)blocks.size();
+    obs->n_xrows = n_rows;
+    obs->x_paired = paired;
+}
+
+extern "C" {
 
 int tb_obs_pack_pointing(tb_obs *obs, void *stream) {
     TB_API_BEGIN
@@ -1371,7 +1679,17 @@ int tb_obs_pack_pointing(tb_obs *obs, void *stream) {
             obs->lpp = nullptr;
             obs->pair_rot = nullptr;
         }
+        build_crossings(obs, (cudaStream_t)stream);
     }
+    TB_API_END
+}
+
+int tb_obs_crossing_stats(const tb_obs *obs, int64_t *n_records, int64_t *n_rows, int *paired) {
+    TB_API_BEGIN
+    TB_REQUIRE(obs != nullptr, "NULL observation");
+    if (n_records) *n_records = obs->xrec ? obs->n_xrec : 0;
+    if (n_rows) *n_rows = obs->xrec ? obs->n_xrows : 0;
+    if (paired) *paired = obs->xrec ? obs->x_paired : 0;
     TB_API_END
 }
 
@@ -1385,6 +1703,7 @@ int tb_get_option(const char *name) {
     if (n == "compact") return g_use_compact;
     if (n == "pair") return g_use_pair;
     if (n == "pairw") return g_use_pairw;
+    if (n == "crossings") return g_use_x;
     return -1;
 }
 
@@ -1399,6 +1718,8 @@ int tb_set_option(const char *name, int value) {
         g_use_pair = value;
     } else if (std::string(name) == "pairw") {
         g_use_pairw = value;
+    } else if (std::string(name) == "crossings") {
+        g_use_x = value;
     } else {
         throw tbr::Error{TB_ERR_ARG, std::string("unknown option: ") + name};
     }

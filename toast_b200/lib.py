@@ -116,6 +116,7 @@ PROTOTYPES = {
     "tb_obs_pack_pointing": (INT, [P, P]),
     "tb_obs_has_compact_pointing": (INT, [P]),
     "tb_obs_has_pair_weights": (INT, [P]),
+    "tb_obs_crossing_stats": (INT, [P, P, P, P]),
     "tb_set_option": (INT, [STR, INT]),
     "tb_get_option": (INT, [STR]),
     "tb_set_pixel_guard_scale": (None, [F64]),
