@@ -501,7 +501,9 @@ def main_gpu(args):
         lib.tb_obs_crossing_stats(dobs.handle().h, ct.byref(n_rec), ct.byref(n_rows), ct.byref(xp))
         crossings = compact and lib.tb_get_option(b"crossings") == 1 and n_rec.value > 0
         if crossings:
-            names = ("k_lhs_x<0> (pass 1: template -> noise-weighted map, crossing list)",
+            names = ("k_bin_xs (pass 1: template -> noise-weighted map, pixel-sorted crossing list)"
+                     if lib.tb_get_option(b"sorted") == 1 else
+                     "k_lhs_x<0> (pass 1: template -> noise-weighted map, crossing list)",
                      "k_lhs_x<1> (pass 2: scan - weight - project, crossing list)")
         elif pairw:
             names = ("k_lhs_pairw<0> (pass 1: template -> noise-weighted map)",

@@ -353,6 +353,8 @@ int tb_obs_crossing_stats(const tb_obs *obs, int64_t *n_records, int64_t *n_rows
  *   "pairw"   (default 1)  with "pair": stream one (Q,U) record per detector pair when the
  *                          packed pointing verified the fixed weight rotation of every pair
  *   "crossings" (default 1) use the crossing list in the LHS passes when it has been built
+ *   "sorted"  (default 1)  with "crossings": pass 1 runs on a PIXEL-sorted copy of the crossing
+ *                          list (amplitudes gathered from the L2, map written sequentially)
  *   "tma"     (default 0)  stage the stored-pointing LHS passes through shared memory with
  *                          cp.async.bulk + mbarrier (measured slower than direct loads)     */
 int tb_set_option(const char *name, int value);

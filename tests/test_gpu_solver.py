@@ -158,13 +158,17 @@ def _permuted(obs, perm):
     return out
 
 
-@pytest.mark.parametrize("perm", [[0, 2, 1, 3, 4], [0, 1, 2, 3, 4], [3, 0, 4]])
-def test_lhs_kernel_variants_agree(perm):
+@pytest.mark.parametrize("perm,eps_max", [([0, 2, 1, 3, 4], 0.03), ([0, 1, 2, 3, 4], 0.03),
+                                          ([3, 0, 4], 0.03), ([0, 1, 2, 3, 4], 0.0),
+                                          ([0, 2, 1, 3, 4], 0.0)])
+def test_lhs_kernel_variants_agree(perm, eps_max):
     """The shipped detector-pair kernels (co-pointed rows share a RED / gather) against the
     oracle and against the single-row compact, TMA-staged and general kernels -- including an
     odd detector count and rows whose neighbours do NOT point at the same pixel."""
     ck = H.checker()
-    obs = _permuted(S.make_observation("c4", n_det=6, n_samp=30000, eps_max=0.03, nside=128),
+    # eps_max = 0: every pair has the same weight rotation (-1, 0) -> the constants of the
+    # pixel-sorted pass 1 are kernel arguments; eps_max > 0: per-pair table
+    obs = _permuted(S.make_observation("c4", n_det=6, n_samp=30000, eps_max=eps_max, nside=128),
                     perm)
     pb = O.build_problem(obs, ck, rcond_threshold=1e-5)  # 30-83 % of the samples unflagged
     assert np.mean((pb.solver_flags & pb.det_flag_mask) == 0) > 0.25
@@ -174,7 +178,10 @@ def test_lhs_kernel_variants_agree(perm):
     lib = L.load()
     results = {}
     try:
-        for name, opts in (("crossings", dict(crossings=1, pair=1, pairw=1, compact=1, tma=0)),
+        for name, opts in (("sorted", dict(sorted=1, crossings=1, pair=1, pairw=1, compact=1,
+                                           tma=0)),
+                           ("crossings", dict(sorted=0, crossings=1, pair=1, pairw=1, compact=1,
+                                              tma=0)),
                            ("pairw", dict(crossings=0, pair=1, pairw=1, compact=1, tma=0)),
                            ("pair", dict(crossings=0, pair=1, pairw=0, compact=1, tma=0)),
                            ("compact", dict(crossings=0, pair=0, compact=1, tma=0)),
@@ -203,9 +210,9 @@ def test_lhs_kernel_variants_agree(perm):
                                  for i in range(0, len(perm) - 1, 2))
                 assert bool(lib.tb_obs_has_pair_weights(dobs.handle().h)) == co_pointed
     finally:
-        for k, v in dict(crossings=1, pair=1, pairw=1, compact=1, tma=0).items():
+        for k, v in dict(sorted=1, crossings=1, pair=1, pairw=1, compact=1, tma=0).items():
             lib.tb_set_option(k.encode(), v)
-    for name in ("crossings", "pairw", "compact", "tma", "general"):
+    for name in ("sorted", "crossings", "pairw", "compact", "tma", "general"):
         # (pixels with rcond down to 1e-5 amplify the summation-order differences of the variants)
         assert_close_norm(results[name], results["pair"], rtol=1e-11, what=f"{name} vs pair")
 

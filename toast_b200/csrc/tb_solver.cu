@@ -47,6 +47,14 @@ struct tb_obs {
     int4 *xblocks = nullptr;    // [n_xblocks] {row, first record, end record, 0}
     int64_t n_xrec = 0, n_xblocks = 0, n_xrows = 0;
     int x_paired = 0;           // rows are detector pairs (weights shared through pair_rot)
+    // pixel-sorted copy of the crossing list for pass 1 (see k_bin_xs)
+    int4 *srec = nullptr;       // [n_srec] {local pixel, scaled-amplitude index, n0|n1<<8|row<<16, 0}
+    double2 *squ = nullptr;     // [n_srec]
+    double4 *stable = nullptr;  // [n_xrows] {cal0, cal1, A, B}
+    double *dscaled = nullptr;  // [n_det * n_amp_det] scratch: flag ? 0 : amplitude * det_scale
+    int64_t n_srec = 0;
+    int s_uniform = 0;          // every row has the same {cal0, cal1, A, B}: kernel constants
+    double s_const[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -1005,13 +1013,133 @@ k_xbuild(ObsDev o, int paired, int64_t n_rows, int64_t chunks_per_row, int32_t *
         double Q = seg_sum(st.wq.x, r), U = seg_sum(st.wq.y, r);
         if (r.is_tail && keep) {
             int64_t idx = base[c] + __popc(kept_heads & ((1u << head_lane) - 1u));
-            xrec[idx] = make_int4(st.lp0, st.lp1, r.dist + 1, st.amp_rel);
+            xrec[idx] = make_int4(st.lp0, st.lp1, (r.dist + 1) | ((int)row << 8), st.amp_rel);
             xqu[idx] = make_double2(Q, U);
         }
     }
 }
 
 int g_use_x = 1; // tb_set_option("crossings", 0/1)
+
+// =================================================================================================
+// Pass 1 on a PIXEL-SORTED copy of the crossing list.
+//
+// In time order every crossing scatters a RED triple to a different pixel of a map that does not
+// fit the L2 (0.33 GB at nside 2048): each record costs a DRAM read-modify-write of 1-2 sectors,
+// more traffic than the record itself.  The amplitude vector is the small side (44 MB: L2-
+// resident), so pass 1 is turned around: records sorted by pixel, amplitudes GATHERED from the
+// L2, the map written sequentially (segmented warp sums, one coalesced RED triple per pixel run).
+// The gather reads a per-pass scratch copy of the amplitudes with the baseline flag and the
+// detector noise weight folded in (k_amp_prescale, O(n_amp)), laid out [detector][baseline] so
+// that the partner detector of a pair is a constant offset away.  Pass 2 keeps the time order
+// (its scattered side is a read-only gather, its output the sequential amplitude runs).
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads)
+k_amp_prescale(ObsDev o, int64_t n_amp_det, const double *__restrict__ amps,
+               const uint8_t *__restrict__ aflags, double *__restrict__ dscaled) {
+    const int64_t total = o.n_det * n_amp_det;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t det = i / n_amp_det;
+        int64_t a = __ldg(o.amp_offsets + det) + (i - det * n_amp_det);
+        dscaled[i] = (__ldg(aflags + a) == 0) ? __ldg(amps + a) * __ldg(o.det_scale + det) : 0.0;
+    }
+}
+
+// keys / values for the sort.  value = record index | mode << 30 (0: as recorded, 1: detector 0
+// only, 2: detector 1 only -- the rare crossing whose two detectors fall in different pixels is
+// entered twice).  Records with no on-map pixel get key n_pix (sorted past the end).
+__global__ void __launch_bounds__(kThreads)
+k_xs_keys(const int4 *__restrict__ xrec, int64_t n_rec, int32_t n_pix, int32_t *__restrict__ keys,
+          int32_t *__restrict__ vals, unsigned int *__restrict__ counters /* {extra, excluded} */,
+          int64_t capacity) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_rec;
+         i += (int64_t)gridDim.x * kThreads) {
+        int4 r = xrec[i];
+        int32_t key = n_pix, val = (int32_t)i;
+        if (r.x >= 0) {
+            key = r.x;
+            if (r.y >= 0 && r.y != r.x) {
+                val |= (1 << 30);
+                int64_t j = n_rec + atomicAdd(counters, 1u);
+                if (j < capacity) {
+                    keys[j] = r.y;
+                    vals[j] = (int32_t)i | (2 << 30);
+                }
+            }
+        } else if (r.y >= 0) {
+            key = r.y;
+        } else {
+            atomicAdd(counters + 1, 1u);
+        }
+        keys[i] = key;
+        vals[i] = val;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_xs_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
+            const int32_t *__restrict__ keys, const int32_t *__restrict__ vals, int64_t n_sorted,
+            int paired, int64_t n_amp_det, int4 *__restrict__ srec, double2 *__restrict__ squ) {
+    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < n_sorted;
+         j += (int64_t)gridDim.x * kThreads) {
+        int32_t v = vals[j];
+        int32_t i = v & 0x3FFFFFFF, mode = (v >> 30) & 3;
+        int4 r = xrec[i];
+        int n = r.z & 0xFF, row = (int)((unsigned)r.z >> 8);
+        int n0 = (r.x >= 0 && mode != 2) ? n : 0;
+        int n1 = (r.y >= 0 && mode != 1 && (mode == 2 || r.x < 0 || r.y == r.x)) ? n : 0;
+        int64_t d0 = paired ? 2 * (int64_t)row : row;
+        srec[j] = make_int4(keys[j], (int32_t)(d0 * n_amp_det + r.w), n0 | (n1 << 8) | (row << 16), 0);
+        squ[j] = xqu[i];
+    }
+}
+
+#ifndef TB_XS_CTAS
+#define TB_XS_CTAS 8
+#endif
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kThreads, TB_XS_CTAS)
+k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t n_srec,
+         const double *__restrict__ dscaled, int32_t delta, double4 cst,
+         const double4 *__restrict__ table, double *__restrict__ zmap) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 2
+    for (int k = 0; k < kXPer; ++k) {
+        const int64_t i = (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
+        int64_t key = -1;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (i < n_srec) {
+            const int4 r = __ldcs(srec + i);
+            const double2 qu = __ldcs(squ + i);
+            key = r.x;
+            const int n0 = r.z & 0xFF, n1 = (r.z >> 8) & 0xFF;
+            double4 c = cst;
+            if (!UNIFORM) {
+                const double2 *tp = reinterpret_cast<const double2 *>(table + ((unsigned)r.z >> 16));
+                double2 ca = __ldg(tp), cb = __ldg(tp + 1);
+                c = make_double4(ca.x, ca.y, cb.x, cb.y);
+            }
+            const double t0 = n0 ? __ldg(dscaled + r.y) : 0.0;
+            const double t1 = n1 ? __ldg(dscaled + r.y + delta) : 0.0;
+            v0 = t0 * (c.x * (double)n0) + t1 * (c.y * (double)n1);
+            v1 = t0 * qu.x + t1 * (c.z * qu.x - c.w * qu.y);
+            v2 = t0 * qu.y + t1 * (c.w * qu.x + c.z * qu.y);
+        }
+        Runs r = find_runs<kBinRunCap>(key, lane);
+        v0 = seg_sum<kBinRunCap>(v0, r);
+        v1 = seg_sum<kBinRunCap>(v1, r);
+        v2 = seg_sum<kBinRunCap>(v2, r);
+        if (r.is_tail && key >= 0) {
+            double *z = zmap + key * 3;
+            atomicAdd(z, v0);
+            atomicAdd(z + 1, v1);
+            atomicAdd(z + 2, v2);
+        }
+    }
+}
+
+int g_use_xs = 1; // tb_set_option("sorted", 0/1)
 
 #ifndef TB_X_CTAS
 #define TB_X_CTAS 8
@@ -1043,7 +1171,7 @@ k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ a
             lp0 = r.x;
             lp1 = r.y;
             arel = r.w;
-            const double n = (double)r.z;
+            const double n = (double)(r.z & 0xFF); // (row index in the upper bits)
             const int64_t amp0 = ao0 + arel, amp1 = ao1 + arel;
             ok0 = __ldg(aflags + amp0) == 0;
             ok1 = has1 && (__ldg(aflags + amp1) == 0);
@@ -1225,7 +1353,26 @@ void launch_bin(const tb_obs *obs, const double *amps, const uint8_t *aflags, co
                 double *zmap, int regen, void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && o.xrec != nullptr) {
+    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && g_use_xs && o.xrec != nullptr &&
+        obs->srec != nullptr) {
+        const int64_t nad = obs->n_amp_det;
+        k_amp_prescale<<<tbr::sm_count() * 4, kThreads, 0, (cudaStream_t)stream>>>(
+            o, nad, amps, aflags, obs->dscaled);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        int64_t nbs = (obs->n_srec + kXTile - 1) / kXTile;
+        double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2],
+                                   obs->s_const[3]);
+        if (obs->s_uniform) {
+            auto k = k_bin_xs<true>;
+            TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, obs->n_srec, obs->dscaled,
+                       (int32_t)nad, cst, obs->stable, zmap);
+        } else {
+            auto k = k_bin_xs<false>;
+            TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, obs->n_srec, obs->dscaled,
+                       (int32_t)nad, cst, obs->stable, zmap);
+        }
+    } else if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && o.xrec != nullptr) {
         auto k = k_lhs_x<false>;
         TBS_LAUNCH(k, obs->n_xblocks, stream, o, amps, aflags, nullptr, zmap);
     } else if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
@@ -1520,10 +1667,102 @@ void tb_obs_destroy(tb_obs *obs) {
     if (obs->xrec) cudaFree(obs->xrec);
     if (obs->xqu) cudaFree(obs->xqu);
     if (obs->xblocks) cudaFree(obs->xblocks);
+    if (obs->srec) cudaFree(obs->srec);
+    if (obs->squ) cudaFree(obs->squ);
+    if (obs->stable) cudaFree(obs->stable);
+    if (obs->dscaled) cudaFree(obs->dscaled);
     delete obs;
 }
 
 } // extern "C"
+
+namespace tbr {
+void sort_pairs_i32(const int32_t *keys_in, int32_t *keys_out, const int32_t *vals_in,
+                    int32_t *vals_out, int64_t n, int end_bit, cudaStream_t st); // tb_sort.cu
+}
+
+// Pixel-sorted copy of the crossing list for pass 1 (k_bin_xs).  Skipped (pass 1 then runs on
+// the time-ordered list) when the packed fields would overflow.
+static void build_sorted(tb_obs *obs, cudaStream_t st) {
+    const int64_t n_rec = obs->n_xrec, n_rows = obs->n_xrows, n_det = obs->d.n_det;
+    const int64_t nad = obs->n_amp_det;
+    const int64_t n_pix = (int64_t)obs->d.n_pix_submap * obs->d.n_submap; // bound on local pixels
+    if (n_rec <= 0 || n_rec >= (1LL << 30) || n_rows >= 65536 || n_det * nad >= 2147483647LL ||
+        n_pix >= 2147483647LL)
+        return;
+    int grid = tbr::sm_count() * 8;
+    // entries: one per record + one more for each crossing whose detectors differ in pixel
+    unsigned int *counters = nullptr;
+    TB_CUDA(cudaMalloc(&counters, 2 * sizeof(unsigned int)));
+    int64_t capacity = n_rec + n_rec / 8 + 1024;
+    int32_t *kin = nullptr, *kout = nullptr, *vin = nullptr, *vout = nullptr;
+    TB_CUDA(cudaMalloc(&kin, sizeof(int32_t) * capacity));
+    TB_CUDA(cudaMalloc(&vin, sizeof(int32_t) * capacity));
+    TB_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st));
+    k_xs_keys<<<grid, kThreads, 0, st>>>(obs->xrec, n_rec, (int32_t)n_pix, kin, vin, counters,
+                                         capacity);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+    unsigned int hc[2] = {0, 0};
+    TB_CUDA(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(counters);
+    const int64_t n_entries = n_rec + hc[0];
+    const int64_t n_sorted = n_entries - hc[1];
+    if (n_entries > capacity || n_sorted <= 0) {
+        cudaFree(kin);
+        cudaFree(vin);
+        return;
+    }
+    TB_CUDA(cudaMalloc(&kout, sizeof(int32_t) * n_entries));
+    TB_CUDA(cudaMalloc(&vout, sizeof(int32_t) * n_entries));
+    int end_bit = 1;
+    while ((1LL << end_bit) <= n_pix) ++end_bit;
+    tbr::sort_pairs_i32(kin, kout, vin, vout, n_entries, end_bit, st);
+    cudaFree(kin);
+    cudaFree(vin);
+    TB_CUDA(cudaMalloc(&obs->srec, sizeof(int4) * n_sorted));
+    TB_CUDA(cudaMalloc(&obs->squ, sizeof(double2) * n_sorted));
+    k_xs_gather<<<grid, kThreads, 0, st>>>(obs->xrec, obs->xqu, kout, vout, n_sorted, obs->x_paired,
+                                           nad, obs->srec, obs->squ);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+    TB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(kout);
+    cudaFree(vout);
+    // per-row constants {cal0, cal1, A, B}
+    std::vector<double> cal(n_det);
+    TB_CUDA(cudaMemcpy(cal.data(), obs->cal, sizeof(double) * n_det, cudaMemcpyDeviceToHost));
+    std::vector<double2> rot;
+    if (obs->x_paired) {
+        rot.resize(n_rows);
+        TB_CUDA(cudaMemcpy(rot.data(), obs->pair_rot, sizeof(double2) * n_rows,
+                           cudaMemcpyDeviceToHost));
+    }
+    std::vector<double4> tab(n_rows);
+    bool uniform = true;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t d0 = obs->x_paired ? 2 * r : r, d1 = d0 + 1;
+        bool has1 = obs->x_paired && d1 < n_det;
+        // a missing partner never contributes (n1 = 0): give it the constants of row 0 so that
+        // an odd detector count does not break uniformity
+        tab[r] = make_double4(cal[d0], has1 ? cal[d1] : (r > 0 ? tab[0].y : cal[d0]),
+                              has1 ? rot[r].x : (r > 0 ? tab[0].z : 0.0),
+                              has1 ? rot[r].y : (r > 0 ? tab[0].w : 0.0));
+        if (tab[r].x != tab[0].x || tab[r].y != tab[0].y || tab[r].z != tab[0].z ||
+            tab[r].w != tab[0].w)
+            uniform = false;
+    }
+    TB_CUDA(cudaMalloc(&obs->stable, sizeof(double4) * n_rows));
+    TB_CUDA(cudaMemcpy(obs->stable, tab.data(), sizeof(double4) * n_rows, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMalloc(&obs->dscaled, sizeof(double) * n_det * nad));
+    obs->s_uniform = uniform ? 1 : 0;
+    obs->s_const[0] = tab[0].x;
+    obs->s_const[1] = tab[0].y;
+    obs->s_const[2] = tab[0].z;
+    obs->s_const[3] = tab[0].w;
+    obs->n_srec = n_sorted;
+}
 
 // Collapse the packed pointing into the crossing list (k_lhs_x) when that is the smaller stream.
 static void build_crossings(tb_obs *obs, cudaStream_t st) {
@@ -1534,6 +1773,15 @@ static void build_crossings(tb_obs *obs, cudaStream_t st) {
     obs->xqu = nullptr;
     obs->xblocks = nullptr;
     obs->n_xrec = obs->n_xblocks = obs->n_xrows = 0;
+    if (obs->srec) cudaFree(obs->srec);
+    if (obs->squ) cudaFree(obs->squ);
+    if (obs->stable) cudaFree(obs->stable);
+    if (obs->dscaled) cudaFree(obs->dscaled);
+    obs->srec = nullptr;
+    obs->squ = nullptr;
+    obs->stable = nullptr;
+    obs->dscaled = nullptr;
+    obs->n_srec = 0;
     if (obs->lpix == nullptr || obs->V.total <= 0) return;
     const int paired = obs->lpp != nullptr ? 1 : 0;
     const int64_t n_det = obs->d.n_det;
@@ -1602,6 +1850,7 @@ static void build_crossings(tb_obs *obs, cudaStream_t st) {
     obs->n_xblocks = (int64_t)blocks.size();
     obs->n_xrows = n_rows;
     obs->x_paired = paired;
+    build_sorted(obs, st);
 }
 
 extern "C" {
@@ -1704,6 +1953,7 @@ int tb_get_option(const char *name) {
     if (n == "pair") return g_use_pair;
     if (n == "pairw") return g_use_pairw;
     if (n == "crossings") return g_use_x;
+    if (n == "sorted") return g_use_xs;
     return -1;
 }
 
@@ -1720,6 +1970,8 @@ int tb_set_option(const char *name, int value) {
         g_use_pairw = value;
     } else if (std::string(name) == "crossings") {
         g_use_x = value;
+    } else if (std::string(name) == "sorted") {
+        g_use_xs = value;
     } else {
         throw tbr::Error{TB_ERR_ARG, std::string("unknown option: ") + name};
     }
