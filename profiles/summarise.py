@@ -105,6 +105,11 @@ def launch_summary(csv_name, out_name, pass1_pattern, n_iter=3):
 
 
 if __name__ == "__main__":
-    ncu_summary(["prof_r1_passes", "prof_r1_tma", "prof_r1_compact", "prof_r1_pair"],
-                "r1_ncu_passes.txt")
-    launch_summary("launches_r1.csv", "r1_launches_step.csv", r"k_lhs_pair<\(?(bool\))?0>")
+    import sys
+    if "--r1" in sys.argv:  # first two sessions (per-sample kernels)
+        ncu_summary(["prof_r1_passes", "prof_r1_tma", "prof_r1_compact", "prof_r1_pair"],
+                    "r1_ncu_passes.txt")
+        launch_summary("launches_r1.csv", "r1_launches_step.csv", r"k_lhs_pair<\(?(bool\))?0>")
+    else:  # session 3: crossing-list kernels (the shipped path)
+        ncu_summary(["prof_s3_x"], "r1_ncu_crossings.txt")
+        launch_summary("launches_s3.csv", "r1_launches_step_crossings.csv", r"k_bin_xs")

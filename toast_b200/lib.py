@@ -142,6 +142,12 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # TB_OPTIONS="crossings=0,sorted=0": kernel-variant switches for A/B measurements
+    for item in os.environ.get("TB_OPTIONS", "").split(","):
+        if "=" in item:
+            k, v = item.split("=", 1)
+            if lib.tb_set_option(k.strip().encode(), int(v)) != 0:
+                raise RuntimeError(f"TB_OPTIONS: unknown option {k!r}")
     return lib
 
 
