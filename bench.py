@@ -48,10 +48,12 @@ SHARDS = {
 }
 BYTES_PER_SAMPLE_PASS = 33      # pixel 8 + weights 24 + solver flag 1
 BYTES_PER_SAMPLE_ITER = 66
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_lhs_pair<0> / <1> on the default
-# workload, from profiles/r1_ncu_passes.txt (prof_r1_pair)
-NCU_TRAFFIC_PASS1 = 8.246e9
-NCU_TRAFFIC_PASS2 = 7.572e9
+# dram__bytes_read.sum + dram__bytes_write.sum per launch on the default workload, from the
+# committed `ncu --set full` captures (profiles/r1_ncu_passes.txt, profiles/r1_ncu_crossings.txt)
+NCU_TRAFFIC = {
+    "k_lhs_pair<0>": 8.246e9, "k_lhs_pair<1>": 7.572e9,
+    "k_bin_xs": 1.480e9, "k_lhs_x<1>": 3.373e9,
+}
 
 
 def parse_args():
@@ -392,25 +394,9 @@ def main_gpu(args):
     ev_sums = torch.cuda.Event()
 
     def lhs_and_dot(timers=None):
-        # q = A d (pass 1, map reduction + covariance, pass 2) and d.q
-        if timers is not None:
-            e = [ev() for _ in range(4)]
-        ds.zmap.zero_()
-        if timers is not None:
-            e[0].record()
-        L.check(lib.tb_lhs_pass1(dobs.handle().h, L.ptr(st.d), L.ptr(ds.amp_flags),
-                                 L.ptr(ds.zmap), ds.regen, None))
-        if timers is not None:
-            e[1].record()
-        ds.reduce_and_apply_cov()
-        st.q.zero_()
-        if timers is not None:
-            e[2].record()
-        L.check(lib.tb_lhs_pass2(dobs.handle().h, L.ptr(st.d), L.ptr(ds.amp_flags),
-                                 L.ptr(ds.zmap), L.ptr(st.q), ds.regen, None))
-        if timers is not None:
-            e[3].record()
-            timers.append(e)
+        # q = A d (pass 1, map reduction + covariance, pass 2) and d.q -- Destriper.lhs, the
+        # call solve() makes; with N > 1 it pipelines the passes with the map reduction
+        ds.lhs(st.d, st.q, timers)
         ds.dot(st.d, st.q, st.dq)
 
     def step(timers=None):
@@ -438,12 +424,30 @@ def main_gpu(args):
     t_start, t_end = ev(), ev()
     t_start.record()
     for _ in range(args.steps):
-        step(timers)
+        step(None if ds.pipeline else timers)
     t_end.record()
     barrier()
     launches = lib.tb_launch_count() - launches0
     ms_total = t_start.elapsed_time(t_end)
     ms_step = ms_total / max(args.steps, 1)
+    if ds.pipeline and os.environ.get("TB_PIPE_TIMELINE", "0") == "1":
+        # diagnostics: when every launch of one pipelined LHS starts and ends (ms from the first)
+        for rep in range(3):
+            tl = []
+            barrier()
+            ds._enqueue_pipelined(st.d, st.q, tl)
+            barrier()
+        if rank == 0:
+            t0 = tl[0][1]
+            for label, e0, e1 in tl:
+                print(f"timeline {label:12s} {t0.elapsed_time(e0):8.3f} -> "
+                      f"{t0.elapsed_time(e1):8.3f} ms", file=sys.stderr)
+    if ds.pipeline:
+        # per-phase durations come from a few extra UN-pipelined applications of the same LHS
+        # (outside the timed region; they change neither x nor r)
+        for _ in range(5):
+            lhs_and_dot(timers)
+        barrier()
     p1 = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))
     p2 = float(np.mean([e[2].elapsed_time(e[3]) for e in timers]))
     pr = float(np.mean([e[1].elapsed_time(e[2]) for e in timers]))
@@ -501,9 +505,12 @@ def main_gpu(args):
         lib.tb_obs_crossing_stats(dobs.handle().h, ct.byref(n_rec), ct.byref(n_rows), ct.byref(xp))
         crossings = compact and lib.tb_get_option(b"crossings") == 1 and n_rec.value > 0
         if crossings:
+            sp = int(lib.tb_obs_sorted_passes(dobs.handle().h))
             names = ("k_bin_xs (pass 1: template -> noise-weighted map, pixel-sorted crossing list)"
-                     if lib.tb_get_option(b"sorted") == 1 else
+                     if sp >= 1 else
                      "k_lhs_x<0> (pass 1: template -> noise-weighted map, crossing list)",
+                     "k_proj_xs (pass 2: scan - weight - project, pixel-sorted crossing list)"
+                     if sp == 2 else
                      "k_lhs_x<1> (pass 2: scan - weight - project, crossing list)")
         elif pairw:
             names = ("k_lhs_pairw<0> (pass 1: template -> noise-weighted map)",
@@ -522,8 +529,8 @@ def main_gpu(args):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
         # `ncu --set full` capture of THIS workload (profiles/r1_ncu_passes.txt); null otherwise
         traffic = None
-        if pair and not pairw and not crossings and args.workload == "c4" and args.scale == 1.0 and world == 1:
-            traffic = NCU_TRAFFIC_PASS1 if p1 >= p2 else NCU_TRAFFIC_PASS2
+        if args.workload == "c4" and args.scale == 1.0 and world == 1:
+            traffic = NCU_TRAFFIC.get(dom.split(" ")[0])
         alg_bytes = info["det_samples"] * BYTES_PER_SAMPLE_PASS
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         iter_gbs = info["det_samples"] * BYTES_PER_SAMPLE_ITER / (ms_step * 1e-3) / 1e9
@@ -548,6 +555,10 @@ def main_gpu(args):
                                  if ds.peer is not None else
                                  ("NCCL all-reduce + cov_apply" if world > 1 else "cov_apply"),
                 "zmap_bytes": int(ds.zmap.numel() * 8),
+                "pipeline": (f"{ds.n_chunks} pixel chunks: pass 1 -> NVLink reduction -> pass 2 "
+                             "overlapped on two streams; pass1/pass2/reduce_cov_ms are from "
+                             "un-pipelined applications outside the timed region")
+                            if ds.pipeline else None,
                 "streamed_bytes_per_sample_per_pass":
                     (round(32.0 * n_rec.value / (info["n_det"] * info["n_samp"]), 2) if crossings
                      else (12 if pairw else 20)) if compact else (1 if args.regen else 33),

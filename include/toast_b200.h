@@ -278,8 +278,23 @@ void tb_obs_destroy(tb_obs *obs);
 
 int tb_lhs_pass1(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
                  double *zmap, int regen, void *stream);
+/* amplitudes == NULL means "the amplitudes given to the preceding tb_lhs_pass1 on this
+ * observation" (their prescaled copy is reused); only valid when tb_obs_sorted_passes() == 2. */
 int tb_lhs_pass2(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
                  const double *binned, double *amplitudes_out, int regen, void *stream);
+/* Which LHS passes run on the pixel-sorted crossing list: 0 none, 1 pass 1, 2 both. */
+int tb_obs_sorted_passes(const tb_obs *obs);
+/* Pixel chunks of the sorted crossing list, for pipelining the passes with the map reduction
+ * (pass 1 of chunk c -> reduction of that pixel range -> pass 2 of chunk c).  pixel_bounds is a
+ * host array of n_chunks + 1 non-decreasing LOCAL pixel indices; chunk c holds the crossings
+ * whose pixel lies in [pixel_bounds[c], pixel_bounds[c + 1]) (the outer chunks are open-ended).
+ * tb_lhs_pass1_chunk(chunk 0) also prepares the amplitudes for every later chunk of both passes;
+ * the sum over chunks equals tb_lhs_pass1 / tb_lhs_pass2. */
+int tb_obs_set_pixel_chunks(tb_obs *obs, int64_t n_chunks, const int64_t *pixel_bounds);
+int tb_lhs_pass1_chunk(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                       double *zmap, int64_t chunk, void *stream);
+int tb_lhs_pass2_chunk(const tb_obs *obs, const double *binned, double *amplitudes_out,
+                       int64_t chunk, void *stream);
 /* RHS projection (SolverRHS, mapmaker_solve.py:107-229): out += F^T N^-1 (signal - P m). */
 int tb_rhs_project(const tb_obs *obs, const double *signal, const uint8_t *amp_flags,
                    const double *binned, double *amplitudes_out, int regen, void *stream);
@@ -301,6 +316,11 @@ int tb_peer_open(tb_peer *peer, const void *all_handles /* world x 128 bytes, by
 void *tb_peer_map_ptr(tb_peer *peer);
 /* n_pix = n_local_submap * n_pix_submap (multiple of 256); cov [n_pix,6] device pointer. */
 int tb_map_reduce_cov(tb_peer *peer, int64_t n_pix, const double *cov, void *stream);
+/* The same for the local pixel range [pix_first, pix_first + n_pix) only (both multiples of 256):
+ * lets the caller pipeline the reduction of one part of the map with the passes over the next.
+ * Every rank must issue the same sequence of calls, stream-ordered per peer object. */
+int tb_map_reduce_cov_range(tb_peer *p, int64_t pix_first, int64_t n_pix, const double *cov,
+                            void *stream);
 void tb_peer_destroy(tb_peer *peer);
 /* NVLS form: attach to buffers the caller already made peer-visible (symmetric memory).
  * `maps` / `flags` are world-long, rank-ordered arrays of device addresses (flags: 2 x 16 uint64

@@ -26,7 +26,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
       --log-file $OUT/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline \
       > $OUT/launches_$TAG.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on \
-      -k regex:'k_bin_xs|k_lhs_x' --launch-skip 6 -c 2 -f -o $OUT/prof_${TAG}_x \
+      -k regex:'k_bin_xs|k_lhs_x|k_proj_xs' --launch-skip 6 -c 2 -f -o $OUT/prof_${TAG}_x \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/prof_${TAG}_x.log 2>&1
 fi
 ls -la $OUT

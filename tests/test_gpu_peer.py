@@ -145,6 +145,7 @@ def _solve_worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     try:
+        from toast_b200 import lib as L_
         from toast_b200.solver import DeviceObservation, Destriper
 
         n_det, n_samp, nside = 6, 24000, 64
@@ -173,11 +174,30 @@ def _solve_worker(rank, world, port, out):
             rhs = ds.rhs([torch.from_numpy(np.ascontiguousarray(obs["signal"][sl])).cuda()])
             amps, hist = ds.solve(rhs, n_iter_max=8)
             res[fused] = (rhs.cpu().numpy(), hist)
+            if fused:
+                # the (opt-in) chunk pipeline -- passes overlapped with the ranged peer
+                # reduction on a second stream, replayed from a CUDA graph -- against the same
+                # LHS run phase by phase
+                ds._setup_pipeline(4)
+                assert ds.pipeline and ds.n_chunks >= 2
+                g = torch.Generator(device="cuda")
+                g.manual_seed(11 + rank)
+                a = torch.randn(ds.n_amp, generator=g, device="cuda", dtype=torch.float64)
+                a[ds.amp_flags != 0] = 0.0
+                q_pipe, q_ser = torch.zeros_like(a), torch.zeros_like(a)
+                for _ in range(3):
+                    ds.lhs(a, q_pipe)
+                ds.pipeline = False
+                L_.check(L_.load().tb_set_option(b"peer_ctas", 12))
+                ds.lhs(a, q_ser)
+                torch.cuda.synchronize()
+                res["pipe_err"] = max(res.get("pipe_err", 0.0),
+                                      float((q_pipe - q_ser).abs().max() / q_ser.abs().max()))
         if rank == 0:
             rhs_ref = O.solver_rhs(pb, O, obs["signal"])
             _, hist_ref = O.solve(pb, O, rhs_ref, n_iter_max=8)
             out.put((res[True][0], res[False][0], rhs_ref[asl], res[True][1], res[False][1],
-                     hist_ref))
+                     hist_ref, res["pipe_err"]))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -196,10 +216,11 @@ def test_two_rank_destriper_matches_single_rank_oracle():
     procs = [ctx.Process(target=_solve_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    rhs_f, rhs_n, rhs_ref, hist_f, hist_n, hist_ref = out.get(timeout=600)
+    rhs_f, rhs_n, rhs_ref, hist_f, hist_n, hist_ref, pipe_err = out.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    assert pipe_err < 1e-12, f"pipelined vs phase-by-phase LHS: {pipe_err}"
     H.assert_close_norm(rhs_f, rhs_ref, what="RHS shard (fused)")
     H.assert_close_norm(rhs_n, rhs_ref, what="RHS shard (NCCL)")
     obs = S.make_observation("c4", n_det=6, n_samp=24000, nside=64, eps_max=0.03)

@@ -178,8 +178,10 @@ def test_lhs_kernel_variants_agree(perm, eps_max):
     lib = L.load()
     results = {}
     try:
-        for name, opts in (("sorted", dict(sorted=1, crossings=1, pair=1, pairw=1, compact=1,
-                                           tma=0)),
+        for name, opts in (("sorted2", dict(sorted=1, sorted2=1, crossings=1, pair=1, pairw=1,
+                                            compact=1, tma=0)),
+                           ("sorted", dict(sorted=1, sorted2=0, crossings=1, pair=1, pairw=1,
+                                           compact=1, tma=0)),
                            ("crossings", dict(sorted=0, crossings=1, pair=1, pairw=1, compact=1,
                                               tma=0)),
                            ("pairw", dict(crossings=0, pair=1, pairw=1, compact=1, tma=0)),
@@ -194,6 +196,8 @@ def test_lhs_kernel_variants_agree(perm, eps_max):
             ds.lhs(torch.from_numpy(a).cuda(), q)
             results[name] = q.cpu().numpy()
             assert_close_norm(results[name], ref, what=f"LHS ({name})")
+            if name in ("sorted2", "sorted"):
+                assert lib.tb_obs_sorted_passes(dobs.handle().h) == (2 if name == "sorted2" else 1)
             if name == "crossings":
                 import ctypes as ct
 
@@ -210,11 +214,85 @@ def test_lhs_kernel_variants_agree(perm, eps_max):
                                  for i in range(0, len(perm) - 1, 2))
                 assert bool(lib.tb_obs_has_pair_weights(dobs.handle().h)) == co_pointed
     finally:
-        for k, v in dict(sorted=1, crossings=1, pair=1, pairw=1, compact=1, tma=0).items():
+        for k, v in dict(sorted=1, sorted2=1, crossings=1, pair=1, pairw=1, compact=1,
+                         tma=0).items():
             lib.tb_set_option(k.encode(), v)
-    for name in ("sorted", "crossings", "pairw", "compact", "tma", "general"):
+    for name in ("sorted2", "sorted", "crossings", "pairw", "compact", "tma", "general"):
         # (pixels with rcond down to 1e-5 amplify the summation-order differences of the variants)
         assert_close_norm(results[name], results["pair"], rtol=1e-11, what=f"{name} vs pair")
+
+
+def test_pixel_chunked_passes_sum_to_the_whole():
+    """tb_lhs_pass1_chunk / tb_lhs_pass2_chunk (the units the multi-GPU pipeline overlaps with
+    the map reduction): any chunking of the local pixel range gives the un-chunked LHS, and
+    flagged amplitudes receive nothing."""
+    ck = H.checker()
+    obs = S.make_observation("c4", n_det=6, n_samp=30000, eps_max=0.03, nside=128)
+    pb = O.build_problem(obs, ck, rcond_threshold=1e-5)
+    pb.amp_flags[::7] = 1  # make sure flagged baselines are exercised
+    rng = np.random.default_rng(5)
+    a = np.where(pb.amp_flags == 0, rng.standard_normal(pb.n_amp), 0.0)
+    ref = O.solver_lhs(pb, ck, a, covapply=ck.cov_apply_diag)
+    dobs, ds, _ = _device_problem(obs, pb)
+    lib = L.load()
+    h = dobs.handle().h
+    assert lib.tb_obs_sorted_passes(h) == 2
+    n_pix = pb.n_local_submap * pb.n_pix_submap
+    a_d = torch.from_numpy(a).cuda()
+    for bounds in ([0, n_pix], [0, 256, 512, n_pix], list(range(0, n_pix + 1, 3072)),
+                   [0, n_pix // 2 // 256 * 256, n_pix // 2 // 256 * 256, n_pix]):
+        b = np.array(bounds, dtype=np.int64)
+        n_chunks = len(b) - 1
+        L.check(lib.tb_obs_set_pixel_chunks(h, n_chunks, L.ptr(b)))
+        ds.zmap.zero_()
+        for c in range(n_chunks):
+            L.check(lib.tb_lhs_pass1_chunk(h, L.ptr(a_d), L.ptr(ds.amp_flags), L.ptr(ds.zmap), c,
+                                           None))
+        ds.reduce_and_apply_cov()
+        q = torch.full((pb.n_amp,), 0.0, dtype=torch.float64, device="cuda")
+        for c in reversed(range(n_chunks)):
+            L.check(lib.tb_lhs_pass2_chunk(h, L.ptr(ds.zmap), L.ptr(q), c, None))
+        qh = q.cpu().numpy()
+        assert_close_norm(qh, ref, what=f"chunked LHS ({n_chunks} chunks)")
+        assert np.all(qh[pb.amp_flags != 0] == 0.0)
+    with pytest.raises(RuntimeError):
+        L.check(lib.tb_lhs_pass2_chunk(h, L.ptr(ds.zmap), L.ptr(q), n_chunks, None))
+
+
+def test_off_map_samples_keep_the_time_ordered_pass2():
+    """Unflagged samples whose submap is not local have no pixel to be sorted by: pass 2 must
+    stay on the time-ordered crossing list (the reference itself indexes out of bounds there,
+    ops_scan_map.cpp:44-52, so the checker is the general per-sample kernel)."""
+    obs = S.make_observation("c4", n_det=4, n_samp=30000, eps_max=0.0, nside=128)
+    pb = O.build_problem(obs, O, rcond_threshold=1e-5)
+    drop = int(np.flatnonzero(pb.global2local >= 0)[1])
+    g2l = pb.global2local.copy()
+    g2l[drop] = -1
+    keep = g2l >= 0
+    g2l[keep] = np.arange(int(keep.sum()))
+    cov = np.delete(pb.cov, pb.global2local[drop], axis=0)
+    rng = np.random.default_rng(6)
+    a = np.where(pb.amp_flags == 0, rng.standard_normal(pb.n_amp), 0.0)
+    lib = L.load()
+    out = {}
+    try:
+        for name, opts in (("sorted", dict(crossings=1, compact=1)),
+                           ("general", dict(crossings=0, pair=0, compact=0, tma=0))):
+            for k, v in opts.items():
+                L.check(lib.tb_set_option(k.encode(), v))
+            dobs, _, _ = _device_problem(obs, pb)
+            dobs.set_global2local(g2l)
+            ds = Destriper([dobs], int(keep.sum()), pb.n_pix_submap, cov, pb.offset_var,
+                           pb.amp_flags)
+            if name == "sorted":
+                assert lib.tb_obs_sorted_passes(dobs.handle().h) == 1
+            q = torch.zeros(pb.n_amp, dtype=torch.float64, device="cuda")
+            ds.lhs(torch.from_numpy(a).cuda(), q)
+            out[name] = q.cpu().numpy()
+    finally:
+        for k, v in dict(crossings=1, pair=1, compact=1, tma=0).items():
+            lib.tb_set_option(k.encode(), v)
+    assert_close_norm(out["sorted"], out["general"], what="off-map samples")
 
 
 def test_full_size_properties_c4_shard():

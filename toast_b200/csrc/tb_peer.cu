@@ -26,7 +26,9 @@ struct tb_peer {
     double *peer_map[kMaxPeers] = {};
     unsigned long long *peer_flags[kMaxPeers] = {};
     unsigned int *counter = nullptr;       // local block counter
-    unsigned long long epoch = 0;
+    // barrier epoch, kept on the DEVICE and advanced by the kernel itself so that a captured
+    // CUDA graph of the reduction can be replayed
+    unsigned long long *epoch_ctr = nullptr;
     bool opened = false;
     // attached form (tb_peer_attach): buffers are owned by the caller (symmetric memory set up by
     // the host plumbing); mc_map is the NVLS multicast address of the same map buffer, or NULL
@@ -40,7 +42,7 @@ struct PeerArgs {
     double *map[kMaxPeers];
     unsigned long long *flags[kMaxPeers];
     int rank, world;
-    unsigned long long epoch;
+    unsigned long long *epoch_ctr;
     unsigned int *counter;
 };
 
@@ -63,15 +65,18 @@ k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *
     __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int world = WORLD > 0 ? WORLD : a.world;
+    // launches on one peer object are stream-ordered and the counter only moves when the last
+    // CTA of a launch retires, so every thread of this launch reads the same value
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(a.epoch_ctr) + 1;
 
     // ---- start barrier: every rank has finished writing its local map (pass 1) ------------
     if (blockIdx.x == 0 && tid < world) {
         __threadfence_system();
-        st_release_sys(a.flags[tid] + a.rank, a.epoch); // row 0: "my map is ready"
+        st_release_sys(a.flags[tid] + a.rank, epoch); // row 0: "my map is ready"
     }
     if (tid < world) {
         const unsigned long long *f = a.flags[a.rank] + tid;
-        while (ld_acquire_sys(f) < a.epoch) {
+        while (ld_acquire_sys(f) < epoch) {
         }
     }
     __syncthreads();
@@ -161,12 +166,15 @@ k_map_reduce_cov(PeerArgs a, int64_t tile_first, int64_t n_tiles, const double *
     if (is_last) {
         if (tid < world) {
             __threadfence_system();
-            st_release_sys(a.flags[tid] + kMaxPeers + a.rank, a.epoch); // row 1: "I am done"
+            st_release_sys(a.flags[tid] + kMaxPeers + a.rank, epoch); // row 1: "I am done"
             const unsigned long long *f = a.flags[a.rank] + kMaxPeers + tid;
-            while (ld_acquire_sys(f) < a.epoch) {
+            while (ld_acquire_sys(f) < epoch) {
             }
         }
-        if (tid == 0) *a.counter = 0u;
+        if (tid == 0) {
+            *a.counter = 0u;
+            *a.epoch_ctr = epoch;
+        }
     }
 }
 
@@ -201,15 +209,16 @@ k_map_reduce_cov_mc(PeerArgs a, double *mc, int64_t tile_first, int64_t n_tiles,
     __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int world = a.world;
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(a.epoch_ctr) + 1;
 
     // ---- start barrier: every rank has finished writing its local map (pass 1) ------------
     if (blockIdx.x == 0 && tid < world) {
         __threadfence_system();
-        st_release_sys(a.flags[tid] + a.rank, a.epoch);
+        st_release_sys(a.flags[tid] + a.rank, epoch);
     }
     if (tid < world) {
         const unsigned long long *f = a.flags[a.rank] + tid;
-        while (ld_acquire_sys(f) < a.epoch) {
+        while (ld_acquire_sys(f) < epoch) {
         }
     }
     __syncthreads();
@@ -263,18 +272,26 @@ k_map_reduce_cov_mc(PeerArgs a, double *mc, int64_t tile_first, int64_t n_tiles,
     if (is_last) {
         if (tid < world) {
             __threadfence_system();
-            st_release_sys(a.flags[tid] + kMaxPeers + a.rank, a.epoch);
+            st_release_sys(a.flags[tid] + kMaxPeers + a.rank, epoch);
             const unsigned long long *f = a.flags[a.rank] + kMaxPeers + tid;
-            while (ld_acquire_sys(f) < a.epoch) {
+            while (ld_acquire_sys(f) < epoch) {
             }
         }
-        if (tid == 0) *a.counter = 0u;
+        if (tid == 0) {
+            *a.counter = 0u;
+            *a.epoch_ctr = epoch;
+        }
     }
 }
 
 int g_use_multimem = 1; // tb_set_option("multimem", 0/1)
 
 } // namespace
+
+// CTAs per SM of the reduction kernels (tb_set_option("peer_ctas", n)).  Stand-alone the kernel
+// wants many resident CTAs (peer-load latency); pipelined with the LHS passes it has to leave
+// most of every SM to them.
+int tb_peer_ctas_per_sm = 12;
 
 extern "C" {
 
@@ -308,6 +325,8 @@ tb_peer *tb_peer_attach(int rank, int world, size_t map_bytes, const uint64_t *m
         p->mc_map = reinterpret_cast<double *>(mc_map);
         TB_CUDA(cudaMalloc(&p->counter, sizeof(unsigned int)));
         TB_CUDA(cudaMemset(p->counter, 0, sizeof(unsigned int)));
+        TB_CUDA(cudaMalloc(&p->epoch_ctr, sizeof(unsigned long long)));
+        TB_CUDA(cudaMemset(p->epoch_ctr, 0, sizeof(unsigned long long)));
         p->opened = true;
         return p;
     } catch (const tbr::Error &e) {
@@ -333,6 +352,8 @@ tb_peer *tb_peer_create(int rank, int world, size_t map_bytes) {
         TB_CUDA(cudaMemset(p->flags, 0, sizeof(unsigned long long) * 2 * kMaxPeers));
         TB_CUDA(cudaMalloc(&p->counter, sizeof(unsigned int)));
         TB_CUDA(cudaMemset(p->counter, 0, sizeof(unsigned int)));
+        TB_CUDA(cudaMalloc(&p->epoch_ctr, sizeof(unsigned long long)));
+        TB_CUDA(cudaMemset(p->epoch_ctr, 0, sizeof(unsigned long long)));
         p->peer_map[rank] = p->map;
         p->peer_flags[rank] = p->flags;
         if (world == 1) p->opened = true;
@@ -375,17 +396,28 @@ void *tb_peer_map_ptr(tb_peer *p) { return p ? p->map : nullptr; }
 
 // binned = cov . sum_over_ranks(zmap), result in every rank's map buffer.  nnz = 3.
 int tb_map_reduce_cov(tb_peer *p, int64_t n_pix, const double *cov, void *stream) {
+    return tb_map_reduce_cov_range(p, 0, n_pix, cov, stream);
+}
+
+// The same for the pixel range [pix_first, pix_first + n_pix) only: lets the caller pipeline the
+// reduction of one part of the map with the binning of the next (every rank must issue the same
+// sequence of calls; calls on one peer object must be stream-ordered).
+int tb_map_reduce_cov_range(tb_peer *p, int64_t pix_first, int64_t n_pix, const double *cov,
+                            void *stream) {
     TB_API_BEGIN
     tbr::require_device();
     TB_REQUIRE(p && p->opened, "peer buffers are not opened");
-    TB_REQUIRE(n_pix % kPeerTile == 0, "n_pix must be a multiple of 256");
-    TB_REQUIRE((size_t)n_pix * 24 <= p->map_bytes, "map buffer too small");
+    TB_REQUIRE(pix_first >= 0 && n_pix >= 0 && pix_first % kPeerTile == 0 &&
+                   n_pix % kPeerTile == 0,
+               "pixel range must be aligned to 256 pixels");
+    TB_REQUIRE((size_t)(pix_first + n_pix) * 24 <= p->map_bytes, "map buffer too small");
     int64_t tiles = n_pix / kPeerTile;
     int64_t per = (tiles + p->world - 1) / p->world;
     int64_t first = per * p->rank;
     int64_t mine = tiles - first;
     if (mine > per) mine = per;
     if (mine < 0) mine = 0;
+    first += pix_first / kPeerTile;
     PeerArgs a;
     for (int q = 0; q < kMaxPeers; ++q) {
         a.map[q] = p->peer_map[q];
@@ -393,15 +425,15 @@ int tb_map_reduce_cov(tb_peer *p, int64_t n_pix, const double *cov, void *stream
     }
     a.rank = p->rank;
     a.world = p->world;
-    a.epoch = ++p->epoch;
+    a.epoch_ctr = p->epoch_ctr;
     a.counter = p->counter;
     int64_t grid = mine < 1 ? 1 : mine;
-    int64_t cap = (int64_t)tbr::sm_count() * 12;
+    int64_t cap = (int64_t)tbr::sm_count() * tb_peer_ctas_per_sm;
     if (grid > cap) grid = cap;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->mc_map != nullptr && g_use_multimem && p->world > 1) {
         int64_t gm = mine < 1 ? 1 : mine;
-        int64_t capm = (int64_t)tbr::sm_count() * 8;
+        int64_t capm = (int64_t)tbr::sm_count() * (tb_peer_ctas_per_sm < 8 ? tb_peer_ctas_per_sm : 8);
         if (gm > capm) gm = capm;
         k_map_reduce_cov_mc<<<(unsigned)gm, kPeerThreads, 0, st>>>(a, p->mc_map, first, mine, cov);
         TB_CUDA(cudaGetLastError());
@@ -423,6 +455,7 @@ void tb_peer_destroy(tb_peer *p) {
     if (!p) return;
     if (!p->owned) {
         if (p->counter) cudaFree(p->counter);
+        if (p->epoch_ctr) cudaFree(p->epoch_ctr);
         delete p;
         return;
     }
@@ -434,6 +467,7 @@ void tb_peer_destroy(tb_peer *p) {
     if (p->map) cudaFree(p->map);
     if (p->flags) cudaFree(p->flags);
     if (p->counter) cudaFree(p->counter);
+    if (p->epoch_ctr) cudaFree(p->epoch_ctr);
     delete p;
 }
 

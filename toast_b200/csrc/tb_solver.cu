@@ -51,8 +51,12 @@ struct tb_obs {
     int4 *srec = nullptr;       // [n_srec] {local pixel, scaled-amplitude index, n0|n1<<8|row<<16, 0}
     double2 *squ = nullptr;     // [n_srec]
     double4 *stable = nullptr;  // [n_xrows] {cal0, cal1, A, B}
-    double *dscaled = nullptr;  // [n_det * n_amp_det] scratch: flag ? 0 : amplitude * det_scale
+    double *dscaled = nullptr;  // [n_det * n_amp_det] scratch: amplitude * det_scale, NaN-tagged if flagged
     int64_t n_srec = 0;
+    int s_pass2_ok = 0;         // no unflagged off-map sample: pass 2 may run on the sorted list too
+    // pixel chunks of the sorted list (tb_obs_set_pixel_chunks): records of chunk c are
+    // [chunk_rec[c], chunk_rec[c + 1])
+    std::vector<int64_t> chunk_rec;
     int s_uniform = 0;          // every row has the same {cal0, cal1, A, B}: kernel constants
     double s_const[4] = {0, 0, 0, 0};
 };
@@ -1034,15 +1038,26 @@ int g_use_x = 1; // tb_set_option("crossings", 0/1)
 // that the partner detector of a pair is a constant offset away.  Pass 2 keeps the time order
 // (its scattered side is a read-only gather, its output the sequential amplitude runs).
 // =================================================================================================
+// Flagged baselines are marked in the prescaled copy with a NaN of this bit pattern (an arithmetic
+// NaN never carries this payload, so a diverged solve still propagates its own NaNs).
+constexpr unsigned long long kAmpFlagBits = 0x7FF8000000B200B2ULL;
+__device__ __forceinline__ bool amp_is_flagged(double v) {
+    return (unsigned long long)__double_as_longlong(v) == kAmpFlagBits;
+}
+
+// grid = (tiles of the baselines of one detector, n_det)
 __global__ void __launch_bounds__(kThreads)
 k_amp_prescale(ObsDev o, int64_t n_amp_det, const double *__restrict__ amps,
                const uint8_t *__restrict__ aflags, double *__restrict__ dscaled) {
-    const int64_t total = o.n_det * n_amp_det;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+    const int64_t det = blockIdx.y;
+    const int64_t a0 = __ldg(o.amp_offsets + det);
+    const double scale = __ldg(o.det_scale + det);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_amp_det;
          i += (int64_t)gridDim.x * kThreads) {
-        int64_t det = i / n_amp_det;
-        int64_t a = __ldg(o.amp_offsets + det) + (i - det * n_amp_det);
-        dscaled[i] = (__ldg(aflags + a) == 0) ? __ldg(amps + a) * __ldg(o.det_scale + det) : 0.0;
+        const int64_t a = a0 + i;
+        dscaled[det * n_amp_det + i] = (__ldg(aflags + a) == 0)
+                                           ? __ldg(amps + a) * scale
+                                           : __longlong_as_double((long long)kAmpFlagBits);
     }
 }
 
@@ -1051,12 +1066,13 @@ k_amp_prescale(ObsDev o, int64_t n_amp_det, const double *__restrict__ amps,
 // entered twice).  Records with no on-map pixel get key n_pix (sorted past the end).
 __global__ void __launch_bounds__(kThreads)
 k_xs_keys(const int4 *__restrict__ xrec, int64_t n_rec, int32_t n_pix, int32_t *__restrict__ keys,
-          int32_t *__restrict__ vals, unsigned int *__restrict__ counters /* {extra, excluded} */,
-          int64_t capacity) {
+          int32_t *__restrict__ vals,
+          unsigned int *__restrict__ counters /* {extra, excluded, off-map} */, int64_t capacity) {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_rec;
          i += (int64_t)gridDim.x * kThreads) {
         int4 r = xrec[i];
         int32_t key = n_pix, val = (int32_t)i;
+        if (r.x == -2 || r.y == -2) atomicAdd(counters + 2, 1u);
         if (r.x >= 0) {
             key = r.x;
             if (r.y >= 0 && r.y != r.x) {
@@ -1100,13 +1116,13 @@ k_xs_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
 #endif
 template <bool UNIFORM>
 __global__ void __launch_bounds__(kThreads, TB_XS_CTAS)
-k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t n_srec,
-         const double *__restrict__ dscaled, int32_t delta, double4 cst,
+k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
+         int64_t n_srec, const double *__restrict__ dscaled, int32_t delta, double4 cst,
          const double4 *__restrict__ table, double *__restrict__ zmap) {
     const int lane = threadIdx.x & 31;
 #pragma unroll 2
     for (int k = 0; k < kXPer; ++k) {
-        const int64_t i = (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
+        const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
         int64_t key = -1;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0;
         if (i < n_srec) {
@@ -1120,8 +1136,10 @@ k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t
                 double2 ca = __ldg(tp), cb = __ldg(tp + 1);
                 c = make_double4(ca.x, ca.y, cb.x, cb.y);
             }
-            const double t0 = n0 ? __ldg(dscaled + r.y) : 0.0;
-            const double t1 = n1 ? __ldg(dscaled + r.y + delta) : 0.0;
+            double t0 = n0 ? __ldg(dscaled + r.y) : 0.0;
+            double t1 = n1 ? __ldg(dscaled + r.y + delta) : 0.0;
+            if (amp_is_flagged(t0)) t0 = 0.0;
+            if (amp_is_flagged(t1)) t1 = 0.0;
             v0 = t0 * (c.x * (double)n0) + t1 * (c.y * (double)n1);
             v1 = t0 * qu.x + t1 * (c.z * qu.x - c.w * qu.y);
             v2 = t0 * qu.y + t1 * (c.w * qu.x + c.z * qu.y);
@@ -1140,6 +1158,68 @@ k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t
 }
 
 int g_use_xs = 1; // tb_set_option("sorted", 0/1)
+
+// Pass 2 on the same pixel-sorted list: the binned map is read SEQUENTIALLY (every pixel once,
+// adjacent records share the load) instead of one cold 24-byte gather per crossing, and the
+// projected values are scattered with fp64 REDs into the amplitude vector, which is the L2-
+// resident side (44 MB per GPU for C4).  Used when no sample of the observation is unflagged but
+// off the local map (such samples have no pixel to be sorted by; they keep k_lhs_x<1>).
+#ifndef TB_XS2_CTAS
+#define TB_XS2_CTAS 6
+#endif
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kThreads, TB_XS2_CTAS)
+k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
+          int64_t rec_end, const double *__restrict__ dscaled, int32_t delta, double4 cst,
+          const double4 *__restrict__ table, const double *__restrict__ det_scale,
+          const int64_t *__restrict__ amp_offsets, int paired, int n_det,
+          const double *__restrict__ binned, double *__restrict__ out) {
+#pragma unroll 2
+    for (int k = 0; k < kXPer; ++k) {
+        const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
+        if (i >= rec_end) continue;
+        const int4 r = __ldcs(srec + i);
+        const double2 qu = __ldcs(squ + i);
+        const int n0 = r.z & 0xFF, n1 = (r.z >> 8) & 0xFF;
+        const int row = (int)((unsigned)r.z >> 16);
+        double4 c = cst;
+        if (!UNIFORM) {
+            const double2 *tp = reinterpret_cast<const double2 *>(table + row);
+            double2 ca = __ldg(tp), cb = __ldg(tp + 1);
+            c = make_double4(ca.x, ca.y, cb.x, cb.y);
+        }
+        const int d0 = paired ? 2 * row : row;
+        const int d1 = (paired && d0 + 1 < n_det) ? d0 + 1 : d0;
+        const int64_t arel = (int64_t)r.y - (int64_t)d0 * delta;
+        const double *m = binned + 3 * (int64_t)r.x;
+        const double m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+        if (n0) {
+            const double a = __ldg(dscaled + r.y); // amplitude x detector weight, NaN-tagged if flagged
+            if (!amp_is_flagged(a)) {
+                double sc = 0.0;
+                sc += (c.x * (double)n0) * m0;
+                sc += qu.x * m1;
+                sc += qu.y * m2;
+                atomicAdd(out + __ldg(amp_offsets + d0) + arel,
+                          (double)n0 * a - sc * __ldg(det_scale + d0));
+            }
+        }
+        if (n1) {
+            const double a = __ldg(dscaled + r.y + delta);
+            if (!amp_is_flagged(a)) {
+                const double q1 = c.z * qu.x - c.w * qu.y, u1 = c.w * qu.x + c.z * qu.y;
+                double sc = 0.0;
+                sc += (c.y * (double)n1) * m0;
+                sc += q1 * m1;
+                sc += u1 * m2;
+                atomicAdd(out + __ldg(amp_offsets + d1) + arel,
+                          (double)n1 * a - sc * __ldg(det_scale + d1));
+            }
+        }
+    }
+}
+
+int g_use_xs2 = 1; // tb_set_option("sorted2", 0/1)
 
 #ifndef TB_X_CTAS
 #define TB_X_CTAS 8
@@ -1259,6 +1339,22 @@ k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ a
 
 
 
+// first record whose pixel is >= bound[c], for every chunk bound
+__global__ void k_xs_lower_bound(const int4 *__restrict__ srec, int64_t n_srec,
+                                 const int64_t *__restrict__ bounds, int n_bounds,
+                                 int64_t *__restrict__ rec) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_bounds) return;
+    const int64_t b = bounds[c];
+    int64_t lo = 0, hi = n_srec;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)srec[mid].x < b) lo = mid + 1;
+        else hi = mid;
+    }
+    rec[c] = lo;
+}
+
 ObsDev make_dev(const tb_obs *obs, int regen) {
     const tb_obs_desc &d = obs->d;
     ObsDev o;
@@ -1348,30 +1444,63 @@ void launch_tma(const ObsDev &o, const double *amps, const uint8_t *aflags, cons
     tbr::count_launch();
 }
 
+inline bool sorted_ok(const tb_obs *obs) {
+    return g_use_compact && g_use_x && g_use_xs && obs->xrec != nullptr && obs->srec != nullptr;
+}
+inline bool sorted2_ok(const tb_obs *obs) { return sorted_ok(obs) && g_use_xs2 && obs->s_pass2_ok; }
+
+void launch_prescale(const tb_obs *obs, const ObsDev &o, const double *amps, const uint8_t *aflags,
+                     void *stream) {
+    const int64_t nad = obs->n_amp_det;
+    int64_t gx = (nad + kThreads * 4 - 1) / (kThreads * 4);
+    if (gx < 1) gx = 1;
+    TB_REQUIRE(o.n_det < 65536, "too many detectors for the prescale grid");
+    dim3 grid((unsigned)gx, (unsigned)o.n_det);
+    k_amp_prescale<<<grid, kThreads, 0, (cudaStream_t)stream>>>(o, nad, amps, aflags, obs->dscaled);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+}
+
+void launch_bin_sorted(const tb_obs *obs, int64_t rec_first, int64_t rec_end, double *zmap,
+                       void *stream) {
+    int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
+    double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    if (obs->s_uniform) {
+        auto k = k_bin_xs<true>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
+                   (int32_t)obs->n_amp_det, cst, obs->stable, zmap);
+    } else {
+        auto k = k_bin_xs<false>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
+                   (int32_t)obs->n_amp_det, cst, obs->stable, zmap);
+    }
+}
+
+void launch_project_sorted(const tb_obs *obs, int64_t rec_first, int64_t rec_end,
+                           const double *binned, double *out, void *stream) {
+    int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
+    double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    if (obs->s_uniform) {
+        auto k = k_proj_xs<true>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
+                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
+                   obs->x_paired, (int)obs->d.n_det, binned, out);
+    } else {
+        auto k = k_proj_xs<false>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
+                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
+                   obs->x_paired, (int)obs->d.n_det, binned, out);
+    }
+}
+
 template <bool FROM_SIGNAL>
 void launch_bin(const tb_obs *obs, const double *amps, const uint8_t *aflags, const double *signal,
                 double *zmap, int regen, void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && g_use_xs && o.xrec != nullptr &&
-        obs->srec != nullptr) {
-        const int64_t nad = obs->n_amp_det;
-        k_amp_prescale<<<tbr::sm_count() * 4, kThreads, 0, (cudaStream_t)stream>>>(
-            o, nad, amps, aflags, obs->dscaled);
-        TB_CUDA(cudaGetLastError());
-        tbr::count_launch();
-        int64_t nbs = (obs->n_srec + kXTile - 1) / kXTile;
-        double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2],
-                                   obs->s_const[3]);
-        if (obs->s_uniform) {
-            auto k = k_bin_xs<true>;
-            TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, obs->n_srec, obs->dscaled,
-                       (int32_t)nad, cst, obs->stable, zmap);
-        } else {
-            auto k = k_bin_xs<false>;
-            TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, obs->n_srec, obs->dscaled,
-                       (int32_t)nad, cst, obs->stable, zmap);
-        }
+    if (!regen && !FROM_SIGNAL && sorted_ok(obs)) {
+        launch_prescale(obs, o, amps, aflags, stream);
+        launch_bin_sorted(obs, 0, obs->n_srec, zmap, stream);
     } else if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && o.xrec != nullptr) {
         auto k = k_lhs_x<false>;
         TBS_LAUNCH(k, obs->n_xblocks, stream, o, amps, aflags, nullptr, zmap);
@@ -1408,7 +1537,13 @@ void launch_project(const tb_obs *obs, const double *amps, const uint8_t *aflags
                     void *stream) {
     ObsDev o = make_dev(obs, regen);
     int64_t nb = obs_blocks(obs);
-    if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && o.xrec != nullptr) {
+    if (!FROM_SIGNAL && amps == nullptr)
+        TB_REQUIRE(!regen && sorted2_ok(obs),
+                   "pass 2 without amplitudes needs the prescaled copy of the sorted pass 1");
+    if (!regen && !FROM_SIGNAL && sorted2_ok(obs)) {
+        if (amps != nullptr) launch_prescale(obs, o, amps, aflags, stream);
+        launch_project_sorted(obs, 0, obs->n_srec, binned, out, stream);
+    } else if (!regen && !FROM_SIGNAL && g_use_compact && g_use_x && o.xrec != nullptr) {
         auto k = k_lhs_x<true>;
         TBS_LAUNCH(k, obs->n_xblocks, stream, o, amps, aflags, binned, out);
     } else if (!regen && !FROM_SIGNAL && g_use_compact && g_use_pair && o.lpix != nullptr) {
@@ -1693,17 +1828,17 @@ static void build_sorted(tb_obs *obs, cudaStream_t st) {
     int grid = tbr::sm_count() * 8;
     // entries: one per record + one more for each crossing whose detectors differ in pixel
     unsigned int *counters = nullptr;
-    TB_CUDA(cudaMalloc(&counters, 2 * sizeof(unsigned int)));
+    TB_CUDA(cudaMalloc(&counters, 3 * sizeof(unsigned int)));
     int64_t capacity = n_rec + n_rec / 8 + 1024;
     int32_t *kin = nullptr, *kout = nullptr, *vin = nullptr, *vout = nullptr;
     TB_CUDA(cudaMalloc(&kin, sizeof(int32_t) * capacity));
     TB_CUDA(cudaMalloc(&vin, sizeof(int32_t) * capacity));
-    TB_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st));
+    TB_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st));
     k_xs_keys<<<grid, kThreads, 0, st>>>(obs->xrec, n_rec, (int32_t)n_pix, kin, vin, counters,
                                          capacity);
     TB_CUDA(cudaGetLastError());
     tbr::count_launch();
-    unsigned int hc[2] = {0, 0};
+    unsigned int hc[3] = {0, 0, 0};
     TB_CUDA(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
     cudaFree(counters);
@@ -1762,6 +1897,8 @@ static void build_sorted(tb_obs *obs, cudaStream_t st) {
     obs->s_const[2] = tab[0].z;
     obs->s_const[3] = tab[0].w;
     obs->n_srec = n_sorted;
+    obs->s_pass2_ok = hc[2] == 0 ? 1 : 0;
+    obs->chunk_rec.assign({0, n_sorted});
 }
 
 // Collapse the packed pointing into the crossing list (k_lhs_x) when that is the smaller stream.
@@ -1782,6 +1919,8 @@ static void build_crossings(tb_obs *obs, cudaStream_t st) {
     obs->stable = nullptr;
     obs->dscaled = nullptr;
     obs->n_srec = 0;
+    obs->s_pass2_ok = 0;
+    obs->chunk_rec.clear();
     if (obs->lpix == nullptr || obs->V.total <= 0) return;
     const int paired = obs->lpp != nullptr ? 1 : 0;
     const int64_t n_det = obs->d.n_det;
@@ -1945,6 +2084,8 @@ int tb_obs_crossing_stats(const tb_obs *obs, int64_t *n_records, int64_t *n_rows
 int tb_obs_has_compact_pointing(const tb_obs *obs) { return (obs && obs->lpix) ? 1 : 0; }
 int tb_obs_has_pair_weights(const tb_obs *obs) { return (obs && obs->lpp) ? 1 : 0; }
 
+extern int tb_peer_ctas_per_sm; // tb_peer.cu
+
 int tb_get_option(const char *name) {
     if (name == nullptr) return -1;
     std::string n(name);
@@ -1954,6 +2095,8 @@ int tb_get_option(const char *name) {
     if (n == "pairw") return g_use_pairw;
     if (n == "crossings") return g_use_x;
     if (n == "sorted") return g_use_xs;
+    if (n == "sorted2") return g_use_xs2;
+    if (n == "peer_ctas") return tb_peer_ctas_per_sm;
     return -1;
 }
 
@@ -1972,6 +2115,11 @@ int tb_set_option(const char *name, int value) {
         g_use_x = value;
     } else if (std::string(name) == "sorted") {
         g_use_xs = value;
+    } else if (std::string(name) == "sorted2") {
+        g_use_xs2 = value;
+    } else if (std::string(name) == "peer_ctas") {
+        TB_REQUIRE(value >= 1 && value <= 16, "peer_ctas must be in [1, 16]");
+        tb_peer_ctas_per_sm = value;
     } else {
         throw tbr::Error{TB_ERR_ARG, std::string("unknown option: ") + name};
     }
@@ -1991,9 +2139,68 @@ int tb_lhs_pass2(const tb_obs *obs, const double *amplitudes, const uint8_t *amp
                  const double *binned, double *amplitudes_out, int regen, void *stream) {
     TB_API_BEGIN
     tbr::require_device();
-    TB_REQUIRE(obs && amplitudes && amp_flags && binned && amplitudes_out, "NULL argument");
+    // amplitudes == NULL: "the amplitudes of the preceding tb_lhs_pass1 on this observation"
+    TB_REQUIRE(obs && amp_flags && binned && amplitudes_out, "NULL argument");
     launch_project<false>(obs, amplitudes, amp_flags, nullptr, binned, amplitudes_out, regen,
                           stream);
+    TB_API_END
+}
+
+int tb_obs_sorted_passes(const tb_obs *obs) {
+    if (obs == nullptr) return 0;
+    return sorted2_ok(obs) ? 2 : (sorted_ok(obs) ? 1 : 0);
+}
+
+int tb_obs_set_pixel_chunks(tb_obs *obs, int64_t n_chunks, const int64_t *pixel_bounds) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs && pixel_bounds && n_chunks >= 1 && n_chunks <= 4096, "bad chunk arguments");
+    TB_REQUIRE(obs->srec != nullptr, "the observation has no pixel-sorted crossing list");
+    for (int64_t c = 0; c < n_chunks; ++c)
+        TB_REQUIRE(pixel_bounds[c] <= pixel_bounds[c + 1], "pixel bounds must be non-decreasing");
+    int64_t *db = nullptr, *dr = nullptr;
+    const int nb = (int)n_chunks + 1;
+    TB_CUDA(cudaMalloc(&db, sizeof(int64_t) * nb));
+    TB_CUDA(cudaMalloc(&dr, sizeof(int64_t) * nb));
+    TB_CUDA(cudaMemcpy(db, pixel_bounds, sizeof(int64_t) * nb, cudaMemcpyHostToDevice));
+    k_xs_lower_bound<<<(nb + 127) / 128, 128>>>(obs->srec, obs->n_srec, db, nb, dr);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+    std::vector<int64_t> rec(nb);
+    TB_CUDA(cudaMemcpy(rec.data(), dr, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost));
+    cudaFree(db);
+    cudaFree(dr);
+    // the first / last chunk take whatever lies outside the given bounds
+    rec[0] = 0;
+    rec[n_chunks] = obs->n_srec;
+    obs->chunk_rec = rec;
+    TB_API_END
+}
+
+int tb_lhs_pass1_chunk(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                       double *zmap, int64_t chunk, void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs && amplitudes && amp_flags && zmap, "NULL argument");
+    TB_REQUIRE(sorted_ok(obs), "chunked passes need the pixel-sorted crossing list");
+    TB_REQUIRE(chunk >= 0 && chunk + 1 < (int64_t)obs->chunk_rec.size(), "bad chunk index");
+    if (chunk == 0) {
+        ObsDev o = make_dev(obs, 0);
+        launch_prescale(obs, o, amplitudes, amp_flags, stream);
+    }
+    launch_bin_sorted(obs, obs->chunk_rec[chunk], obs->chunk_rec[chunk + 1], zmap, stream);
+    TB_API_END
+}
+
+int tb_lhs_pass2_chunk(const tb_obs *obs, const double *binned, double *amplitudes_out,
+                       int64_t chunk, void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs && binned && amplitudes_out, "NULL argument");
+    TB_REQUIRE(sorted2_ok(obs), "chunked pass 2 needs the pixel-sorted crossing list");
+    TB_REQUIRE(chunk >= 0 && chunk + 1 < (int64_t)obs->chunk_rec.size(), "bad chunk index");
+    launch_project_sorted(obs, obs->chunk_rec[chunk], obs->chunk_rec[chunk + 1], binned,
+                          amplitudes_out, stream);
     TB_API_END
 }
 

@@ -99,6 +99,10 @@ PROTOTYPES = {
     "tb_obs_destroy": (None, [P]),
     "tb_lhs_pass1": (INT, [P, P, P, P, INT, P]),
     "tb_lhs_pass2": (INT, [P, P, P, P, P, INT, P]),
+    "tb_obs_sorted_passes": (INT, [P]),
+    "tb_obs_set_pixel_chunks": (INT, [P, I64, P]),
+    "tb_lhs_pass1_chunk": (INT, [P, P, P, P, I64, P]),
+    "tb_lhs_pass2_chunk": (INT, [P, P, P, I64, P]),
     "tb_rhs_project": (INT, [P, P, P, P, P, INT, P]),
     "tb_bin_signal": (INT, [P, P, P, INT, P]),
     "tb_peer_create": (P, [INT, INT, SZ]),
@@ -106,6 +110,7 @@ PROTOTYPES = {
     "tb_peer_open": (INT, [P, P]),
     "tb_peer_map_ptr": (P, [P]),
     "tb_map_reduce_cov": (INT, [P, I64, P, P]),
+    "tb_map_reduce_cov_range": (INT, [P, I64, I64, P, P]),
     "tb_peer_destroy": (None, [P]),
     "tb_peer_attach": (P, [INT, INT, SZ, P, P, ct.c_uint64]),
     "tb_peer_has_multicast": (INT, [P]),

@@ -207,8 +207,9 @@ class PeerMap:
         self.tensor = torch.as_tensor(_CudaView(ptr, self.n_pix * 3), device=device)
         dist.barrier(group=group)
 
-    def reduce_cov(self, cov):
-        L.check(self.lib.tb_map_reduce_cov(self.h, self.n_pix, L.ptr(cov), None))
+    def reduce_cov(self, cov, pix_first=0, n_pix=None, stream=None):
+        n_pix = self.n_pix - pix_first if n_pix is None else n_pix
+        L.check(self.lib.tb_map_reduce_cov_range(self.h, pix_first, n_pix, L.ptr(cov), stream))
 
     def __del__(self):
         try:
@@ -252,9 +253,10 @@ class SymmPeerMap:
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
-    def reduce_cov(self, cov):
+    def reduce_cov(self, cov, pix_first=0, n_pix=None, stream=None):
+        n_pix = self.n_pix - pix_first if n_pix is None else n_pix
         L.check(self.lib.tb_peer_set_multimem(1 if self.use_multimem else 0))
-        L.check(self.lib.tb_map_reduce_cov(self.h, self.n_pix, L.ptr(cov), None))
+        L.check(self.lib.tb_map_reduce_cov_range(self.h, pix_first, n_pix, L.ptr(cov), stream))
 
     def tune(self, cov, reps=3):
         """Measure the in-switch (multimem) and the P2P form of the kernel on this node and map
@@ -343,6 +345,107 @@ class Destriper:
         else:
             self.zmap = torch.zeros((self.n_local_submap, self.n_pix_submap, 3),
                                     dtype=torch.float64, device=self.device)
+        # The chunk pipeline is OPT-IN (TB_PIPE_CHUNKS=4): measured on 2 GPUs it gains 9-14 %
+        # (1.46-1.54 ms against 1.69 ms per iteration) because the reduction kernel and the
+        # passes compete for the same L1/LSU and L2 bandwidth; not yet measured on 4 / 8 GPUs.
+        self.pipeline = False
+        self._setup_pipeline(int(_os.environ.get("TB_PIPE_CHUNKS", "0")))
+
+    # -- chunk pipeline -------------------------------------------------------------------------
+    def _sorted_passes(self):
+        """2 when BOTH passes of every observation run on the pixel-sorted crossing list."""
+        if self.regen:
+            return 0
+        return min(int(self.lib.tb_obs_sorted_passes(o.handle().h)) for o in self.obs)
+
+    def _setup_pipeline(self, n_chunks):
+        """Multi-GPU with both passes pixel-sorted: cut the local map into pixel chunks so that
+        pass 1 of chunk c+1 and pass 2 of chunk c-1 overlap the NVLink reduction of chunk c
+        (the reduction runs on its own high-priority stream)."""
+        import os as _os
+        if self.peer is None or n_chunks < 2 or self._sorted_passes() != 2:
+            return
+        n_pix = self.n_local_submap * self.n_pix_submap
+        unit = 256 * self.world          # every chunk splits evenly over the ranks
+        units = n_pix // unit
+        n_chunks = max(1, min(n_chunks, units))
+        if n_chunks < 2:
+            return
+        bounds = np.array([(c * units) // n_chunks * unit for c in range(n_chunks + 1)],
+                          dtype=np.int64)
+        bounds[-1] = n_pix               # (the remainder, < unit pixels, joins the last chunk)
+        for o in self.obs:
+            L.check(self.lib.tb_obs_set_pixel_chunks(o.handle().h, n_chunks, L.ptr(bounds)))
+        self.chunk_bounds = bounds
+        self.n_chunks = n_chunks
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        # leave most of every SM to the passes the reduction overlaps (measured best: 3)
+        L.check(self.lib.tb_set_option(b"peer_ctas", int(_os.environ.get("TB_PEER_CTAS", "3"))))
+        self.ev_binned = [torch.cuda.Event() for _ in range(n_chunks)]
+        self.ev_reduced = [torch.cuda.Event() for _ in range(n_chunks)]
+        self.pipeline = True
+        self.use_graph = _os.environ.get("TB_GRAPH", "1") != "0"
+        self._graphs = {}
+
+    def _lhs_pipelined(self, amps_in, amps_out):
+        """The pipelined LHS, replayed from a CUDA graph: 3 launches + 2 cross-stream edges per
+        chunk are launch-bound from Python (measured: ~30 us of host time per chunk)."""
+        if not self.use_graph:
+            return self._enqueue_pipelined(amps_in, amps_out)
+        key = (amps_in.data_ptr(), amps_out.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                self._enqueue_pipelined(amps_in, amps_out)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graphs[key] = g
+        g.replay()
+        return amps_out
+
+    def _enqueue_pipelined(self, amps_in, amps_out, timeline=None):
+        """``timeline``: optional list receiving (label, start event, end event) per launch
+        (diagnostics: profiles/pipe_timeline.py)."""
+        main = torch.cuda.current_stream(self.device)
+        ms, cs = main.cuda_stream, self.comm_stream.cuda_stream
+
+        def timed(label, stream, fn):
+            if timeline is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            timeline.append((label, e0, e1))
+
+        timed("zero", main, lambda: (self.zmap.zero_(), amps_out.zero_()))
+        for c in range(self.n_chunks):
+            def p1(c=c):
+                for o in self.obs:
+                    L.check(self.lib.tb_lhs_pass1_chunk(o.handle().h, L.ptr(amps_in),
+                                                        L.ptr(self.amp_flags), L.ptr(self.zmap),
+                                                        c, ms))
+            timed(f"pass1[{c}]", main, p1)
+            self.ev_binned[c].record(main)
+            self.comm_stream.wait_event(self.ev_binned[c])
+            first = int(self.chunk_bounds[c])
+            timed(f"reduce[{c}]", self.comm_stream,
+                  lambda: self.peer.reduce_cov(self.cov, first,
+                                               int(self.chunk_bounds[c + 1]) - first, cs))
+            self.ev_reduced[c].record(self.comm_stream)
+        for c in range(self.n_chunks):
+            main.wait_event(self.ev_reduced[c])
+
+            def p2(c=c):
+                for o in self.obs:
+                    L.check(self.lib.tb_lhs_pass2_chunk(o.handle().h, L.ptr(self.zmap),
+                                                        L.ptr(amps_out), c, ms))
+            timed(f"pass2[{c}]", main, p2)
+        return amps_out
 
     # -- collectives ----------------------------------------------------------------------------
     def _allreduce(self, t):
@@ -380,13 +483,34 @@ class Destriper:
         self.reduce_and_apply_cov()
         return self.zmap
 
-    def lhs(self, amps_in, amps_out):
-        """SolverLHS: amps_out = F^T N^-1 Z F amps_in."""
-        binned = self.bin_amplitudes(amps_in)
-        amps_out.zero_()
+    def lhs(self, amps_in, amps_out, timers=None):
+        """SolverLHS: amps_out = F^T N^-1 Z F amps_in.  ``timers``: optional list that receives
+        four CUDA events (pass 1 start/end, pass 2 start/end) of the un-pipelined form."""
+        if self.pipeline and timers is None:
+            return self._lhs_pipelined(amps_in, amps_out)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers is not None \
+            else None
+        self.zmap.zero_()
+        if ev:
+            ev[0].record()
         for o in self.obs:
-            L.check(self.lib.tb_lhs_pass2(o.handle().h, L.ptr(amps_in), L.ptr(self.amp_flags),
-                                          L.ptr(binned), L.ptr(amps_out), self.regen, None))
+            L.check(self.lib.tb_lhs_pass1(o.handle().h, L.ptr(amps_in), L.ptr(self.amp_flags),
+                                          L.ptr(self.zmap), self.regen, None))
+        if ev:
+            ev[1].record()
+        self.reduce_and_apply_cov()
+        amps_out.zero_()
+        if ev:
+            ev[2].record()
+        # both passes pixel-sorted: pass 2 reuses the prescaled amplitudes of pass 1
+        reuse = self._sorted_passes() == 2
+        for o in self.obs:
+            L.check(self.lib.tb_lhs_pass2(o.handle().h, None if reuse else L.ptr(amps_in),
+                                          L.ptr(self.amp_flags), L.ptr(self.zmap),
+                                          L.ptr(amps_out), self.regen, None))
+        if ev:
+            ev[3].record()
+            timers.append(ev)
         return amps_out
 
     def rhs(self, signals):
