@@ -111,5 +111,6 @@ if __name__ == "__main__":
                     "r1_ncu_passes.txt")
         launch_summary("launches_r1.csv", "r1_launches_step.csv", r"k_lhs_pair<\(?(bool\))?0>")
     else:  # session 3: crossing-list kernels (the shipped path)
-        ncu_summary(["prof_s3_x"], "r1_ncu_crossings.txt")
-        launch_summary("launches_s3.csv", "r1_launches_step_crossings.csv", r"k_bin_xs")
+        # prof_s3_x: k_bin_xs + time-ordered k_lhs_x<1>; prof_s4_x: k_bin_xs + k_proj_xs (shipped)
+        ncu_summary(["prof_s3_x", "prof_s4_x"], "r1_ncu_crossings.txt")
+        launch_summary("launches_s4.csv", "r1_launches_step_crossings.csv", r"k_bin_xs")
