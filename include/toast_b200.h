@@ -302,6 +302,46 @@ int tb_rhs_project(const tb_obs *obs, const double *signal, const uint8_t *amp_f
 int tb_bin_signal(const tb_obs *obs, const double *signal, double *zmap, int regen,
                   void *stream);
 
+/* ---- Offset template: noise prior and its preconditioner -------------------------------------
+ * Replaces Offset._add_prior (templates/offset/offset.py:884-960: scipy.signal.convolve
+ * mode="same" per (detector, observation, view) segment, then flagged amplitudes zeroed) and
+ * Offset._apply_precond with use_noise_prior=True (:962-1010: scipy.linalg.cho_solve_banded on
+ * the lower banded Cholesky factor, or a "same" convolution with the Toeplitz kernel when
+ * precond_width <= 1).  The reference has no accelerator form of either (NotImplementedError,
+ * :888-891 and :964-967).  The descriptor holds HOST arrays; they are copied to the device once.
+ * Segments are disjoint, in increasing order; a start offset < 0 marks a cut detector (its
+ * amplitudes come out as zeros). */
+#define TB_PRECOND_TOEPLITZ 1
+#define TB_PRECOND_BANDED 2
+typedef struct {
+    int64_t n_amp;              /* length of the local amplitude vector */
+    int64_t n_seg;              /* number of segments */
+    const int64_t *seg_start;   /* [n_seg] first amplitude of the segment */
+    const int64_t *seg_len;     /* [n_seg] n_amp_view */
+    const int64_t *filt_start;  /* [n_seg] offset of the noise filter in `filters`, or -1 */
+    const int64_t *filt_len;    /* [n_seg] its (odd) length */
+    const double *filters;      /* [n_filter_values] concatenated filters (offset.py:466-468) */
+    int64_t n_filter_values;
+    int precond_mode;           /* TB_PRECOND_TOEPLITZ or TB_PRECOND_BANDED */
+    const int64_t *prec_start;  /* [n_seg] offset in `precond`, or -1 */
+    const int64_t *prec_width;  /* [n_seg] banded: rows w of the factor; Toeplitz: kernel length */
+    const double *precond;      /* banded: per segment the [w, n_amp_view] row-major array that
+                                   scipy.linalg.cholesky_banded(lower=True) returns
+                                   (ab[k][j] = L[j+k][j]); Toeplitz: the kernels */
+    int64_t n_precond_values;
+} tb_offset_prior_desc;
+typedef struct tb_offset_prior tb_offset_prior;
+tb_offset_prior *tb_offset_prior_create(const tb_offset_prior_desc *desc);
+void tb_offset_prior_destroy(tb_offset_prior *prior);
+/* amplitudes_out[seg] += convolve(amplitudes_in[seg], filter[seg], "same"); flagged -> 0 */
+int tb_offset_prior_add(const tb_offset_prior *prior, const double *amplitudes_in,
+                        const uint8_t *amplitude_flags, double *amplitudes_out, int mem,
+                        void *stream);
+/* amplitudes_out = M^-1 amplitudes_in segment by segment; flagged -> 0 */
+int tb_offset_prior_precond(const tb_offset_prior *prior, const double *amplitudes_in,
+                            const uint8_t *amplitude_flags, double *amplitudes_out, int mem,
+                            void *stream);
+
 /* ---- a6 fused with its collective: map reduction + covariance over NVLink peer memory ------
  * Replaces  accel_update_host -> PixelData.sync_allreduce (MPI) -> accel_update_device ->
  * covariance_apply  (ops/mapmaker_utils/mapmaker_utils.py:885-925, pixels.py:710-779,

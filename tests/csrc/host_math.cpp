@@ -50,3 +50,41 @@ void tbm_stokes_iqu(int64_t n, const double *quats, double cal, double eps, doub
     }
 }
 }
+
+// ---- Offset noise prior cores (toast_b200/csrc/tb_prior.cuh), looped the way the kernels do ----
+#include "../../toast_b200/csrc/tb_prior.cuh"
+
+extern "C" {
+
+// mode 0: out += conv, flagged -> 0 (add_prior); mode 1: out = conv, flagged -> 0 (Toeplitz)
+void tbp_conv_segments(int64_t n_seg, const int64_t *seg_start, const int64_t *seg_len,
+                       const int64_t *f_start, const int64_t *f_len, const double *taps,
+                       const double *in, const uint8_t *flags, double *out, int mode) {
+    for (int64_t s = 0; s < n_seg; ++s) {
+        for (int64_t i = 0; i < seg_len[s]; ++i) {
+            const int64_t g = seg_start[s] + i;
+            double v = 0.0;
+            if (f_start[s] >= 0 && flags[g] == 0) {
+                v = tbp::conv_same_at(in + seg_start[s], seg_len[s], taps + f_start[s], f_len[s], i);
+                if (mode == 0) v += out[g];
+            }
+            out[g] = v;
+        }
+    }
+}
+
+void tbp_banded_segments(int64_t n_seg, const int64_t *seg_start, const int64_t *seg_len,
+                         const int64_t *p_start, const int64_t *p_width, const double *factors,
+                         const double *in, const uint8_t *flags, double *out) {
+    for (int64_t s = 0; s < n_seg; ++s) {
+        const int64_t n = seg_len[s], s0 = seg_start[s];
+        if (p_start[s] < 0) {
+            for (int64_t j = 0; j < n; ++j) out[s0 + j] = 0.0;
+            continue;
+        }
+        tbp::banded_cho_solve(factors + p_start[s], p_width[s], n, in + s0, out + s0);
+        for (int64_t j = 0; j < n; ++j)
+            if (flags[s0 + j] != 0) out[s0 + j] = 0.0;
+    }
+}
+}

@@ -96,3 +96,22 @@ def assert_history_matches(hist, hist_ref, env, what=""):
     assert dev[0] <= RTOL, f"{what}: first iteration deviates {dev[0]}"
     bound = np.maximum(RTOL, 1.0e3 * env[:n])
     assert np.all(dev[:n] <= bound), f"{what}: history deviates {dev[:n]} > {bound}"
+
+
+def host_math_lib():
+    """g++ build of the product's host/device cores (tests/csrc/host_math.cpp: tb_math.cuh and
+    tb_prior.cuh compiled for the host, -ffp-contract=off) for the CPU suite."""
+    import ctypes as ct
+    import subprocess
+
+    csrc = os.path.join(ROOT, "tests", "csrc")
+    so = os.path.join(csrc, "libhostmath.so")
+    src = os.path.join(csrc, "host_math.cpp")
+    deps = [src] + [os.path.join(ROOT, "toast_b200", "csrc", h)
+                    for h in ("tb_math.cuh", "tb_prior.cuh")]
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-x", "c++", "-o", so, src, "-lm"])
+    lib = ct.CDLL(so)
+    lib.tbm_quat2pix.restype = ct.c_int64
+    return lib

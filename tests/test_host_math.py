@@ -17,16 +17,7 @@ CSRC = os.path.join(H.ROOT, "tests", "csrc")
 
 @pytest.fixture(scope="module")
 def hm():
-    so = os.path.join(CSRC, "libhostmath.so")
-    src = os.path.join(CSRC, "host_math.cpp")
-    hdr = os.path.join(H.ROOT, "toast_b200", "csrc", "tb_math.cuh")
-    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src),
-                                                             os.path.getmtime(hdr)):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-x", "c++", "-o", so, src, "-lm"])
-    lib = ct.CDLL(so)
-    lib.tbm_quat2pix.restype = ct.c_int64
-    return lib
+    return H.host_math_lib()
 
 
 def _p(a):

@@ -1,0 +1,173 @@
+"""CPU tests of the Offset noise prior:
+  * the oracle's PSD helpers against the reference's own method bodies (golden fixture made by
+    tests/golden/make_golden_prior.py from /root/reference),
+  * the product's host-side assembly (toast_b200/templates/offset_prior.py) against the oracle,
+  * the product's per-element kernel cores (csrc/tb_prior.cuh compiled for the host) against the
+    scipy calls the reference makes (offset.py:884-1010)."""
+
+import ctypes as ct
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import offset_prior as OP
+from toast_b200.templates import offset_prior as PP
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(f"{H.GOLDEN}/offset_prior.npz")
+
+
+def test_oracle_helpers_match_reference_methods(golden):
+    g = golden
+    step = float(g["step_time"])
+    for d in range(len(g["sigma"])):
+        np.testing.assert_array_equal(OP.remove_white_noise(g["psdfreq"], g["psds"][d].copy()),
+                                      g["corrpsd"][d])
+        np.testing.assert_array_equal(
+            OP.get_offset_psd(g["psdfreq"], g["psds"][d].copy(), g["freq"], step),
+            g["offset_psd"][d])
+    np.testing.assert_array_equal(
+        OP.interpolate_psd(g["interp_x"], np.log(g["freq"]), np.log(g["offset_psd"][0])),
+        g["interp_y"])
+    np.testing.assert_array_equal(OP.truncate(g["filter_raw"].copy()), g["filter_truncated"])
+    np.testing.assert_array_equal(OP.truncate(g["filter_raw"].copy(), lim=1e-2),
+                                  g["filter_truncated_1e2"])
+    np.testing.assert_array_equal(
+        OP.prior_frequencies(float(g["obstime"]), step, float(g["rate"])), g["freq"])
+    assert OP.prior_frequencies(1.0, 2.0, 10.0) is None  # a single baseline: prior disabled
+
+
+def test_product_psd_helpers_match_reference_methods(golden):
+    g = golden
+    step = float(g["step_time"])
+    for d in range(len(g["sigma"])):
+        np.testing.assert_array_equal(PP.offset_psd(g["psdfreq"], g["psds"][d], g["freq"], step),
+                                      g["offset_psd"][d])
+    np.testing.assert_array_equal(PP._symmetric_cut(g["filter_raw"].copy()),
+                                  g["filter_truncated"])
+    np.testing.assert_array_equal(PP._symmetric_cut(g["filter_raw"].copy(), lim=1e-2),
+                                  g["filter_truncated_1e2"])
+    np.testing.assert_array_equal(
+        PP.prior_frequencies(float(g["obstime"]), step, float(g["rate"])), g["freq"])
+
+
+def make_case(precond_width, n_amp_views=(120, 37, 143, 5), n_det=3, seed=0):
+    """Three detectors, four views (one shorter than the band), random amplitude variance."""
+    rate, step_time, obstime = 10.0, 2.0, 600.0
+    rng = np.random.default_rng(seed)
+    sigma = 1.0 + 0.1 * rng.random(n_det)
+    psdfreq, psds = OP.analytic_psd(sigma, rate, fknee=0.05, fmin=1e-4, alpha=1.5, n_freq=300)
+    nav = np.array(n_amp_views, dtype=np.int64)
+    per = int(nav.sum())
+    var = 1.0 / rng.uniform(10, 20, size=n_det * per)
+    detnoise = 1.0 / sigma**2
+    prior = OP.build_prior(psdfreq, psds, detnoise, var, nav, obstime, step_time, rate,
+                           precond_width=precond_width)
+    return dict(rate=rate, step_time=step_time, obstime=obstime, psdfreq=psdfreq, psds=psds,
+                nav=nav, per=per, var=var, detnoise=detnoise, n_det=n_det, n_amp=n_det * per,
+                prior=prior, precond_width=precond_width)
+
+
+def build_product(case, cut=()):
+    b = PP.OffsetPriorBuilder(case["n_amp"], case["precond_width"])
+    freq = PP.prior_frequencies(case["obstime"], case["step_time"], case["rate"])
+    for d in range(case["n_det"]):
+        if d in cut:
+            b.add_cut_detector(d * case["per"], case["nav"])
+        else:
+            b.add_detector(d * case["per"], case["nav"], case["psdfreq"], case["psds"][d],
+                           case["detnoise"][d], case["var"], freq, case["step_time"])
+    return b
+
+
+@pytest.mark.parametrize("precond_width", [20, 4, 1])
+def test_product_assembly_matches_oracle(precond_width):
+    case = make_case(precond_width)
+    b = build_product(case)
+    k = 0
+    for d in range(case["n_det"]):
+        for v in range(len(case["nav"])):
+            np.testing.assert_array_equal(b.filters[k], case["prior"].filters[d][v])
+            np.testing.assert_array_equal(
+                b.precond[k], np.asarray(case["prior"].precond[d][v][0]).reshape(-1))
+            assert b.seg_start[k] == d * case["per"] + int(case["nav"][:v].sum())
+            k += 1
+    assert b._nf == sum(f.size for f in b.filters) and b._np == sum(p.size for p in b.precond)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(a):
+    return ct.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("precond_width", [20, 4, 1])
+def test_kernel_cores_match_scipy(precond_width):
+    """tb_prior.cuh (conv_same_at, banded_cho_solve) looped over the segments exactly as the
+    kernels do, against scipy.signal.convolve / cho_solve_banded through the oracle."""
+    hm = H.host_math_lib()
+    case = make_case(precond_width)
+    b = build_product(case)
+    n = case["n_amp"]
+    rng = np.random.default_rng(3)
+    a_in = rng.standard_normal(n)
+    flags = (rng.random(n) < 0.1).astype(np.uint8)
+    seg_start, seg_len = _i64(b.seg_start), _i64(b.seg_len)
+    f_start, f_len = _i64(b.filt_start), _i64(b.filt_len)
+    p_start, p_width = _i64(b.prec_start), _i64(b.prec_width)
+    taps, pre = np.concatenate(b.filters), np.concatenate(b.precond)
+
+    # add_prior accumulates onto what is already there
+    out = rng.standard_normal(n)
+    ref = out.copy()
+    OP.add_prior(case["prior"], a_in, flags, ref)
+    hm.tbp_conv_segments(ct.c_int64(len(seg_start)), _ptr(seg_start), _ptr(seg_len),
+                         _ptr(f_start), _ptr(f_len), _ptr(taps), _ptr(a_in), _ptr(flags),
+                         _ptr(out), ct.c_int(0))
+    H.assert_close_norm(out, ref, rtol=1e-13, what="add_prior")
+    assert np.all(out[flags != 0] == 0.0)
+
+    ref = np.full(n, np.nan)
+    OP.apply_precond(case["prior"], a_in, flags, ref)
+    out = np.full(n, np.nan)
+    if precond_width == 1:
+        hm.tbp_conv_segments(ct.c_int64(len(seg_start)), _ptr(seg_start), _ptr(seg_len),
+                             _ptr(p_start), _ptr(p_width), _ptr(pre), _ptr(a_in), _ptr(flags),
+                             _ptr(out), ct.c_int(1))
+    else:
+        hm.tbp_banded_segments(ct.c_int64(len(seg_start)), _ptr(seg_start), _ptr(seg_len),
+                               _ptr(p_start), _ptr(p_width), _ptr(pre), _ptr(a_in), _ptr(flags),
+                               _ptr(out))
+    H.assert_close_norm(out, ref, rtol=1e-12, what="apply_precond")
+    assert np.all(out[flags != 0] == 0.0)
+
+
+def test_filter_longer_than_the_segment_and_cut_detectors():
+    """"same" convolution keeps the length of the AMPLITUDES even when the filter is longer
+    (5-baseline view, 35-tap filter); a cut detector comes out as zeros."""
+    hm = H.host_math_lib()
+    case = make_case(20, n_amp_views=(5, 3, 1, 64))
+    b = build_product(case, cut=(1,))
+    n = case["n_amp"]
+    rng = np.random.default_rng(4)
+    a_in = rng.standard_normal(n)
+    flags = np.zeros(n, dtype=np.uint8)
+    ref = np.zeros(n)
+    OP.add_prior(case["prior"], a_in, flags, ref)
+    per = case["per"]
+    ref[per:2 * per] = 0.0
+    out = np.zeros(n)
+    seg_start, seg_len = _i64(b.seg_start), _i64(b.seg_len)
+    f_start, f_len = _i64(b.filt_start), _i64(b.filt_len)
+    taps = np.concatenate(b.filters)
+    assert min(seg_len) == 1 and max(f_len) > 5
+    hm.tbp_conv_segments(ct.c_int64(len(seg_start)), _ptr(seg_start), _ptr(seg_len),
+                         _ptr(f_start), _ptr(f_len), _ptr(taps), _ptr(a_in), _ptr(flags),
+                         _ptr(out), ct.c_int(0))
+    H.assert_close_norm(out, ref, rtol=1e-13, what="short segments")
+    assert np.all(out[per:2 * per] == 0.0)

@@ -51,6 +51,18 @@ class tb_obs_desc(ct.Structure):
     ]
 
 
+class tb_offset_prior_desc(ct.Structure):
+    _fields_ = [
+        ("n_amp", I64), ("n_seg", I64),
+        ("seg_start", P), ("seg_len", P), ("filt_start", P), ("filt_len", P),
+        ("filters", P), ("n_filter_values", I64),
+        ("precond_mode", INT),
+        ("prec_start", P), ("prec_width", P), ("precond", P), ("n_precond_values", I64),
+    ]
+
+
+TB_PRECOND_TOEPLITZ, TB_PRECOND_BANDED = 1, 2
+
 # name -> (restype, argtypes); every symbol declared in include/toast_b200.h
 PROTOTYPES = {
     "tb_last_error": (STR, []),
@@ -105,6 +117,10 @@ PROTOTYPES = {
     "tb_lhs_pass2_chunk": (INT, [P, P, P, I64, P]),
     "tb_rhs_project": (INT, [P, P, P, P, P, INT, P]),
     "tb_bin_signal": (INT, [P, P, P, INT, P]),
+    "tb_offset_prior_create": (P, [ct.POINTER(tb_offset_prior_desc)]),
+    "tb_offset_prior_destroy": (None, [P]),
+    "tb_offset_prior_add": (INT, [P, P, P, P, INT, P]),
+    "tb_offset_prior_precond": (INT, [P, P, P, P, INT, P]),
     "tb_peer_create": (P, [INT, INT, SZ]),
     "tb_peer_get_handles": (INT, [P, P]),
     "tb_peer_open": (INT, [P, P]),
