@@ -481,9 +481,34 @@ def solver_rhs(pb, K, signal, covapply=None):
     return rhs
 
 
-def solve(pb, K, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, covapply=None):
+def solve(pb, K, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, covapply=None,
+          prior=None):
     """The PCG loop of mapmaker_solve.py:524-755, zero starting guess.  Returns
-    (amplitudes, [relative residual per iteration])."""
+    (amplitudes, [relative residual per iteration]).  ``prior``: an
+    ``oracle.offset_prior.OraclePrior`` -- the LHS then includes the noise prior
+    (mapmaker_solve.py:395-412) and the preconditioner is Offset._apply_precond's banded /
+    Toeplitz form (offset.py:962-1010)."""
+    fl = pb.amp_flags
+    _lhs, _diag = solver_lhs, K.template_offset_apply_diag_precond
+    if prior is not None:
+        from . import offset_prior as _OP
+
+        def solver_lhs_p(pb, K, amps, covapply=None):
+            out = np.zeros_like(amps)
+            _OP.add_prior(prior, amps, fl, out)
+            return out + _lhs(pb, K, amps, covapply)
+
+        class _KP:
+            @staticmethod
+            def template_offset_apply_diag_precond(var, a_in, flags, a_out, use_accel):
+                _OP.apply_precond(prior, a_in, flags, a_out)
+
+        return _solve(pb, _KP, rhs, convergence, n_iter_max, n_iter_min, covapply,
+                      lambda pb_, K_, a, c=None: solver_lhs_p(pb_, K, a, c))
+    return _solve(pb, K, rhs, convergence, n_iter_max, n_iter_min, covapply, solver_lhs)
+
+
+def _solve(pb, K, rhs, convergence, n_iter_max, n_iter_min, covapply, solver_lhs):
     fl = pb.amp_flags
     result = np.zeros_like(rhs)
     lhs_out = solver_lhs(pb, K, result, covapply)

@@ -70,7 +70,7 @@ def ang_to_quat(theta, phi):
     return np.ascontiguousarray(iso_quat(theta, phi, np.zeros_like(theta)))
 
 
-def pcg_envelope(pb, rhs, n_iter):
+def pcg_envelope(pb, rhs, n_iter, prior=None):
     """How reproducible the reference's OWN residual history is: relative deviation of the
     oracle's history under a 1-ulp random perturbation of the RHS (running maximum).  CG
     amplifies rounding noise exponentially, so beyond the first iterations the history is not
@@ -78,8 +78,8 @@ def pcg_envelope(pb, rhs, n_iter):
     project_signal uses OpenMP atomics: template_offset.cpp:301-327)."""
     rng = np.random.default_rng(0)
     rhs2 = rhs * (1.0 + 2.2e-16 * rng.choice([-1.0, 1.0], size=rhs.shape))
-    _, h1 = O.solve(pb, O, rhs, n_iter_max=n_iter)
-    _, h2 = O.solve(pb, O, rhs2, n_iter_max=n_iter)
+    _, h1 = O.solve(pb, O, rhs, n_iter_max=n_iter, prior=prior)
+    _, h2 = O.solve(pb, O, rhs2, n_iter_max=n_iter, prior=prior)
     n = min(len(h1), len(h2))
     env = np.abs(np.array(h2[:n]) - np.array(h1[:n])) / np.array(h1[:n])
     return np.maximum.accumulate(env)

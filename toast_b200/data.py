@@ -138,13 +138,26 @@ class DetDataManager(dict):
 
 class NoiseModel:
     """Only what the hot path reads: the per-detector inverse-variance weight
-    (noise.py ``detector_weight``)."""
+    (noise.py ``detector_weight``) and -- for the Offset noise prior -- the PSD of each detector
+    (``freq(det)`` in Hz, ``psd(det)`` in signal-units^2 s; plain arrays, no astropy units)."""
 
-    def __init__(self, weights):
+    def __init__(self, weights, freqs=None, psds=None):
         self._w = dict(weights)
+        self._f = dict(freqs) if freqs is not None else None
+        self._p = dict(psds) if psds is not None else None
 
     def detector_weight(self, det):
         return self._w[det]
+
+    def freq(self, det):
+        if self._f is None:
+            raise RuntimeError("this noise model carries no PSDs")
+        return self._f[det]
+
+    def psd(self, det):
+        if self._p is None:
+            raise RuntimeError("this noise model carries no PSDs")
+        return self._p[det]
 
 
 class Observation:

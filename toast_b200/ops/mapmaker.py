@@ -119,6 +119,7 @@ class MapMaker(Operator):
         self.template_matrix.det_data = self.det_data
         self.template_matrix.det_flags = None  # solver flags are applied on the device below
         self.template_matrix.reset()
+        tmpl._defer_prior = True  # built below, from the variance under the full solver flags
         self.template_matrix._init_templates(data, detectors)
 
         # --- device observations, solver flags bit 0 (mapmaker_templates.py:764-810) -----------
@@ -239,8 +240,10 @@ class MapMaker(Operator):
         tmpl._amp_flags = ~keep
 
         # --- RHS, PCG ----------------------------------------------------------------------------
+        if tmpl.use_noise_prior:
+            tmpl._build_prior(data)  # offset.py:356-560, uploaded once
         ds = Destriper(dobs, n_loc, nps, cov, offset_var, amp_flags,
-                       regen=self.regenerate_pointing, device=dev)
+                       regen=self.regenerate_pointing, device=dev, prior=tmpl.prior())
         rhs = ds.rhs(signals)
         amps_dev, self.history = ds.solve(rhs, convergence=self.convergence,
                                           n_iter_max=self.iter_max, n_iter_min=self.iter_min)

@@ -303,8 +303,12 @@ class Destriper:
     recomputes pointing inside every pass instead of reading stored pixels/weights."""
 
     def __init__(self, observations, n_local_submap, n_pix_submap, cov, offset_var, amp_flags,
-                 regen=False, group=None, device="cuda", fused_reduce=True):
+                 regen=False, group=None, device="cuda", fused_reduce=True, prior=None):
         self.obs = list(observations)
+        # templates.offset_prior.OffsetPrior or None: with a noise prior the LHS gains the
+        # inverse amplitude covariance (offset.py:884-960) and the preconditioner becomes the
+        # banded / Toeplitz solve (offset.py:962-1010)
+        self.prior = prior
         self.device = torch.device(device)
         self.lib = L.load()
         self.regen = 1 if regen else 0
@@ -487,7 +491,8 @@ class Destriper:
         """SolverLHS: amps_out = F^T N^-1 Z F amps_in.  ``timers``: optional list that receives
         four CUDA events (pass 1 start/end, pass 2 start/end) of the un-pipelined form."""
         if self.pipeline and timers is None:
-            return self._lhs_pipelined(amps_in, amps_out)
+            self._lhs_pipelined(amps_in, amps_out)
+            return self._add_prior(amps_in, amps_out)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers is not None \
             else None
         self.zmap.zero_()
@@ -511,7 +516,24 @@ class Destriper:
         if ev:
             ev[3].record()
             timers.append(ev)
+        return self._add_prior(amps_in, amps_out)
+
+    def _add_prior(self, amps_in, amps_out):
+        # mapmaker_solve.py:395-412 adds the prior BEFORE the projection accumulates into the same
+        # vector; the sum is the same and flagged amplitudes receive nothing from either term
+        if self.prior is not None:
+            self.prior.add(amps_in, self.amp_flags, amps_out)
         return amps_out
+
+    def precond(self, r, s):
+        """s = M^-1 r: diagonal offset variance (template_offset.cpp:375-402), or the noise-prior
+        preconditioner."""
+        if self.prior is not None:
+            self.prior.precond(r, self.amp_flags, s)
+        else:
+            L.check(self.lib.tb_template_offset_apply_diag_precond(
+                L.ptr(self.offset_var), L.ptr(r), L.ptr(self.amp_flags), L.ptr(s), self.n_amp,
+                L.TB_MEM_DEVICE, None))
 
     def rhs(self, signals):
         """SolverRHS: F^T N^-1 Z d."""
@@ -540,6 +562,11 @@ class Destriper:
                                        L.ptr(st.d), L.ptr(st.q), L.ptr(st.s),
                                        L.ptr(self.offset_var), L.ptr(self.amp_flags), self.n_amp,
                                        L.ptr(st.sums), None))
+        if self.prior is not None:
+            # the fused update applied the diagonal preconditioner: redo s and s.r with the prior's
+            self.precond(st.r, st.s)
+            L.check(self.lib.tb_amp_dot(L.ptr(st.s), L.ptr(st.r), L.ptr(self.amp_flags),
+                                        self.n_amp, L.ptr(st.sums[1:]), None))
         self._allreduce(st.sums)
 
     def iteration(self, st):
@@ -568,9 +595,7 @@ class Destriper:
         self.lhs(st.x, st.q)
         st.r.copy_(rhs)
         st.r.sub_(st.q)
-        L.check(self.lib.tb_template_offset_apply_diag_precond(
-            L.ptr(self.offset_var), L.ptr(st.r), L.ptr(self.amp_flags), L.ptr(st.s), n,
-            L.TB_MEM_DEVICE, None))
+        self.precond(st.r, st.s)
         st.d.copy_(st.s)
         tmp = torch.zeros(1, dtype=torch.float64, device=dev)
         self.dot(rhs, rhs, tmp)

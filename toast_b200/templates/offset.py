@@ -1,5 +1,5 @@
-"""templates.Offset (``templates/offset/offset.py:28-1030``) without the noise prior: step-wise
-constant baselines per detector and view.
+"""templates.Offset (``templates/offset/offset.py:28-1030``): step-wise constant baselines per
+detector and view, optionally with the noise prior (``use_noise_prior``; ``offset_prior.py``).
 
 Amplitude layout (``offset.py:166-176, 245-253``): detector-major; per observation and view
 ``ceil(view_len / step_length)`` amplitudes with ``step_length = rint(step_time * rate)``
@@ -13,6 +13,7 @@ import numpy as np
 from .. import _libtoast as K
 from .. import kernels as KC
 from .amplitudes import Amplitudes
+from .offset_prior import OffsetPriorBuilder, prior_frequencies
 
 
 class Template:
@@ -66,8 +67,9 @@ class Offset(Template):
         return int(np.rint(stime * rate))
 
     def _initialize(self, new_data, detectors=None):
-        if self.use_noise_prior:
-            raise NotImplementedError("the Offset noise prior is not implemented (SURVEY 8f.3)")
+        if self.use_noise_prior and self.noise_model is None:
+            raise RuntimeError("cannot use the noise prior without a noise model")  # :136-138
+        self._prior = None
         self._obs_views, self._obs_view_flags = {}, {}
         self._obs_rate, self._obs_dets = {}, {}
         all_dets = {}
@@ -151,6 +153,34 @@ class Offset(Template):
             keep = (frac > self.good_fraction) & (detnoise > 0)
             self._offsetvar[:] = np.where(keep, 1.0 / (detnoise * n_good), 0.0)
         self._amp_flags[:] = ~keep
+        # (MapMaker recomputes the variance from the full solver flags first and builds the
+        # prior itself: _defer_prior)
+        if self.use_noise_prior and not getattr(self, "_defer_prior", False):
+            self._build_prior(new_data)
+
+    def _build_prior(self, data):
+        """offset.py:203-222 + 356-560: per (detector, observation, view) the real-space noise
+        filter and the preconditioner, uploaded once; applied by tb_offset_prior_add / _precond."""
+        b = OffsetPriorBuilder(self._n_local, self.precond_width)
+        any_prior = False
+        for det in self._all_dets:
+            for iob, ob in enumerate(data.obs):
+                if det not in self._obs_dets[iob]:
+                    continue
+                t = ob.shared[self.times]
+                freq = prior_frequencies(float(t[-1] - t[0]), self.step_time, self._obs_rate[iob])
+                start = self._obs_amp_offset(det, iob)
+                if freq is None:
+                    # a single baseline in this observation: the reference disables the prior
+                    # for it (:208-214) and its amplitudes come out as zeros (:946-947)
+                    b.add_cut_detector(start, self._obs_views[iob])
+                    continue
+                noise = ob[self.noise_model]
+                b.add_detector(start, self._obs_views[iob], noise.freq(det), noise.psd(det),
+                               noise.detector_weight(det), self._offsetvar, freq, self.step_time)
+                any_prior = True
+        if any_prior or self._n_local > 0:
+            self._prior = b.finish()
 
     def _obs_amp_offset(self, det, iob):
         off = self._det_start[det]
@@ -198,11 +228,23 @@ class Offset(Template):
                 self._obs_amp_offset(detector, iob), self._obs_views[iob], amplitudes.local,
                 amplitudes.local_flags, ob.intervals[self.view], use_accel)
 
+    def prior(self):
+        """The device-resident noise prior (None without ``use_noise_prior``), for Destriper."""
+        return self._prior
+
     def _add_prior(self, amplitudes_in, amplitudes_out, use_accel=False):
-        return  # offset.py:884-887: nothing without a noise prior
+        if not self.use_noise_prior or self._prior is None:
+            return  # offset.py:884-887: nothing without a noise prior
+        # (the reference raises NotImplementedError for use_accel here, :888-891)
+        self._prior.add(amplitudes_in.local, amplitudes_in.local_flags, amplitudes_out.local,
+                        use_accel=use_accel)
 
     def _apply_precond(self, amplitudes_in, amplitudes_out, use_accel=False):
         if self._n_local == 0:
+            return
+        if self.use_noise_prior and self._prior is not None:
+            self._prior.precond(amplitudes_in.local, amplitudes_in.local_flags,
+                                amplitudes_out.local, use_accel=use_accel)
             return
         K.template_offset_apply_diag_precond(self._offsetvar, amplitudes_in.local,
                                              amplitudes_in.local_flags, amplitudes_out.local,
