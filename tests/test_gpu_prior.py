@@ -141,3 +141,58 @@ def test_pcg_with_noise_prior(name, n_det, n_samp, nside, precond_width):
     _, hist = ds.solve(torch.from_numpy(rhs_ref).cuda(), n_iter_max=10)
     H.assert_history_matches(hist, hist_ref, H.pcg_envelope(pb, rhs_ref, 10, prior=oprior),
                              what=f"{name} with prior")
+
+
+@pytest.mark.parametrize("precond_width,det_flags", [(20, None), (1, "flags")])
+@pytest.mark.parametrize("use_accel", [False, True])
+def test_offset_template_with_noise_prior(precond_width, det_flags, use_accel):
+    """templates.Offset(use_noise_prior=True).add_prior / apply_precond -- which the reference
+    can only run on the host (offset.py:888-891, 964-967) -- against the oracle restatement,
+    with host arrays and with amplitudes registered in the accel table.  The Toeplitz form is
+    run with detector flags (some baselines flagged); the banded form cannot be built then."""
+    from toast_b200.data import Data, NoiseModel, observation_from_synthetic
+    from toast_b200.templates import Offset
+
+    obs = S.make_observation("c2", n_det=4, n_samp=24000, nside=64, eps_max=0.03)
+    data = Data()
+    ob = observation_from_synthetic(obs)
+    data.obs.append(ob)
+    dets = ob.local_detectors
+    rate = obs["rate"]
+    psdfreq, psds = OP.analytic_psd(obs["sigma"], rate, fknee=0.05, fmin=1e-4, alpha=1.5,
+                                    n_freq=300)
+    ob["noise_model"] = NoiseModel({d: float(w) for d, w in zip(dets, obs["detweight"])},
+                                   {d: psdfreq for d in dets},
+                                   {d: psds[i] for i, d in enumerate(dets)})
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model", det_flags=det_flags, det_flag_mask=1,
+                  view="scanning", use_noise_prior=True, precond_width=precond_width)
+    tmpl.initialize(data)
+    nav, det_start, n_amp = O.offset_layout(4, obs["intervals"], obs["step_length"])
+    t = ob.shared["times"]
+    oprior = OP.build_prior(psdfreq, psds, obs["detweight"], tmpl._offsetvar, nav,
+                            float(t[-1] - t[0]), obs["step_time"], rate,
+                            precond_width=precond_width)
+    a_in, out, pre = tmpl.zeros(), tmpl.zeros(), tmpl.zeros()
+    if det_flags is not None:
+        a_in.local_flags[::5] = 1   # flagged baselines: outputs zeroed, inputs still convolved
+    rng = np.random.default_rng(12)
+    a_in.local[:] = rng.standard_normal(n_amp)
+    out.local[:] = rng.standard_normal(n_amp)
+    ref_add = out.local.copy()
+    OP.add_prior(oprior, a_in.local, a_in.local_flags, ref_add)
+    ref_pre = np.zeros(n_amp)
+    OP.apply_precond(oprior, a_in.local, a_in.local_flags, ref_pre)
+    if use_accel:
+        for amp in (a_in, out, pre):
+            amp.accel_create()
+            amp.accel_update_device()
+    tmpl.add_prior(a_in, out, use_accel=use_accel)
+    tmpl.apply_precond(a_in, pre, use_accel=use_accel)
+    if use_accel:
+        for amp in (out, pre):
+            amp.accel_update_host()
+        for amp in (a_in, out, pre):
+            amp.accel_delete()
+    assert_close_norm(out.local, ref_add, rtol=1e-12, what="Offset.add_prior")
+    assert_close_norm(pre.local, ref_pre, rtol=1e-12, what="Offset.apply_precond")
