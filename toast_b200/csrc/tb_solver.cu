@@ -1045,19 +1045,27 @@ __device__ __forceinline__ bool amp_is_flagged(double v) {
     return (unsigned long long)__double_as_longlong(v) == kAmpFlagBits;
 }
 
-// grid = (tiles of the baselines of one detector, n_det)
+// The prescaled copy is laid out by ROW of the crossing list: unpaired rows are detectors,
+// [det][baseline] doubles; paired rows hold both detectors of a polarisation pair INTERLEAVED,
+// [pair][baseline][2], so that the passes fetch both amplitudes of a crossing with ONE 16-byte
+// gather (the scattered 8-byte gathers were 79 M of the 92 M sectors k_bin_xs loads: ncu, session
+// 3).  grid = (tiles of the baselines of one detector, slots); slots = 2 x pairs when paired (the
+// missing partner of an odd detector count is written as "flagged").
 __global__ void __launch_bounds__(kThreads)
-k_amp_prescale(ObsDev o, int64_t n_amp_det, const double *__restrict__ amps,
+k_amp_prescale(ObsDev o, int64_t n_amp_det, int paired, const double *__restrict__ amps,
                const uint8_t *__restrict__ aflags, double *__restrict__ dscaled) {
     const int64_t det = blockIdx.y;
-    const int64_t a0 = __ldg(o.amp_offsets + det);
-    const double scale = __ldg(o.det_scale + det);
+    const bool real = det < o.n_det;
+    const int64_t a0 = real ? __ldg(o.amp_offsets + det) : 0;
+    const double scale = real ? __ldg(o.det_scale + det) : 0.0;
+    const double tagged = __longlong_as_double((long long)kAmpFlagBits);
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_amp_det;
          i += (int64_t)gridDim.x * kThreads) {
         const int64_t a = a0 + i;
-        dscaled[det * n_amp_det + i] = (__ldg(aflags + a) == 0)
-                                           ? __ldg(amps + a) * scale
-                                           : __longlong_as_double((long long)kAmpFlagBits);
+        const double v = (real && __ldg(aflags + a) == 0) ? __ldg(amps + a) * scale : tagged;
+        const int64_t slot = paired ? ((det >> 1) * n_amp_det + i) * 2 + (det & 1)
+                                    : det * n_amp_det + i;
+        dscaled[slot] = v;
     }
 }
 
@@ -1105,8 +1113,9 @@ k_xs_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
         int n = r.z & 0xFF, row = (int)((unsigned)r.z >> 8);
         int n0 = (r.x >= 0 && mode != 2) ? n : 0;
         int n1 = (r.y >= 0 && mode != 1 && (mode == 2 || r.x < 0 || r.y == r.x)) ? n : 0;
-        int64_t d0 = paired ? 2 * (int64_t)row : row;
-        srec[j] = make_int4(keys[j], (int32_t)(d0 * n_amp_det + r.w), n0 | (n1 << 8) | (row << 16), 0);
+        (void)paired; // slot = row * n_amp_det + baseline in both layouts (see k_amp_prescale)
+        srec[j] = make_int4(keys[j], (int32_t)((int64_t)row * n_amp_det + r.w),
+                            n0 | (n1 << 8) | (row << 16), 0);
         squ[j] = xqu[i];
     }
 }
@@ -1114,10 +1123,10 @@ k_xs_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
 #ifndef TB_XS_CTAS
 #define TB_XS_CTAS 8
 #endif
-template <bool UNIFORM>
+template <bool UNIFORM, bool PAIRED>
 __global__ void __launch_bounds__(kThreads, TB_XS_CTAS)
 k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
-         int64_t n_srec, const double *__restrict__ dscaled, int32_t delta, double4 cst,
+         int64_t n_srec, const double *__restrict__ dscaled, double4 cst,
          const double4 *__restrict__ table, double *__restrict__ zmap) {
     const int lane = threadIdx.x & 31;
 #pragma unroll 2
@@ -1136,8 +1145,14 @@ k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t
                 double2 ca = __ldg(tp), cb = __ldg(tp + 1);
                 c = make_double4(ca.x, ca.y, cb.x, cb.y);
             }
-            double t0 = n0 ? __ldg(dscaled + r.y) : 0.0;
-            double t1 = n1 ? __ldg(dscaled + r.y + delta) : 0.0;
+            double t0, t1 = 0.0;
+            if (PAIRED) {
+                const double2 t = __ldg(reinterpret_cast<const double2 *>(dscaled) + r.y);
+                t0 = n0 ? t.x : 0.0;
+                t1 = n1 ? t.y : 0.0;
+            } else {
+                t0 = n0 ? __ldg(dscaled + r.y) : 0.0;
+            }
             if (amp_is_flagged(t0)) t0 = 0.0;
             if (amp_is_flagged(t1)) t1 = 0.0;
             v0 = t0 * (c.x * (double)n0) + t1 * (c.y * (double)n1);
@@ -1167,12 +1182,12 @@ int g_use_xs = 1; // tb_set_option("sorted", 0/1)
 #ifndef TB_XS2_CTAS
 #define TB_XS2_CTAS 6
 #endif
-template <bool UNIFORM>
+template <bool UNIFORM, bool PAIRED>
 __global__ void __launch_bounds__(kThreads, TB_XS2_CTAS)
 k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
           int64_t rec_end, const double *__restrict__ dscaled, int32_t delta, double4 cst,
           const double4 *__restrict__ table, const double *__restrict__ det_scale,
-          const int64_t *__restrict__ amp_offsets, int paired, int n_det,
+          const int64_t *__restrict__ amp_offsets, int n_det,
           const double *__restrict__ binned, double *__restrict__ out) {
 #pragma unroll 2
     for (int k = 0; k < kXPer; ++k) {
@@ -1188,13 +1203,17 @@ k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_
             double2 ca = __ldg(tp), cb = __ldg(tp + 1);
             c = make_double4(ca.x, ca.y, cb.x, cb.y);
         }
-        const int d0 = paired ? 2 * row : row;
-        const int d1 = (paired && d0 + 1 < n_det) ? d0 + 1 : d0;
-        const int64_t arel = (int64_t)r.y - (int64_t)d0 * delta;
+        const int d0 = PAIRED ? 2 * row : row;
+        const int d1 = (PAIRED && d0 + 1 < n_det) ? d0 + 1 : d0;
+        const int64_t arel = (int64_t)r.y - (int64_t)row * delta;
         const double *m = binned + 3 * (int64_t)r.x;
         const double m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+        // amplitude x detector weight of both detectors of the row, NaN-tagged if flagged
+        double2 av = make_double2(0.0, 0.0);
+        if (PAIRED) av = __ldg(reinterpret_cast<const double2 *>(dscaled) + r.y);
+        else av.x = __ldg(dscaled + r.y);
         if (n0) {
-            const double a = __ldg(dscaled + r.y); // amplitude x detector weight, NaN-tagged if flagged
+            const double a = av.x;
             if (!amp_is_flagged(a)) {
                 double sc = 0.0;
                 sc += (c.x * (double)n0) * m0;
@@ -1204,8 +1223,8 @@ k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_
                           (double)n0 * a - sc * __ldg(det_scale + d0));
             }
         }
-        if (n1) {
-            const double a = __ldg(dscaled + r.y + delta);
+        if (PAIRED && n1) {
+            const double a = av.y;
             if (!amp_is_flagged(a)) {
                 const double q1 = c.z * qu.x - c.w * qu.y, u1 = c.w * qu.x + c.z * qu.y;
                 double sc = 0.0;
@@ -1454,42 +1473,59 @@ void launch_prescale(const tb_obs *obs, const ObsDev &o, const double *amps, con
     const int64_t nad = obs->n_amp_det;
     int64_t gx = (nad + kThreads * 4 - 1) / (kThreads * 4);
     if (gx < 1) gx = 1;
-    TB_REQUIRE(o.n_det < 65536, "too many detectors for the prescale grid");
-    dim3 grid((unsigned)gx, (unsigned)o.n_det);
-    k_amp_prescale<<<grid, kThreads, 0, (cudaStream_t)stream>>>(o, nad, amps, aflags, obs->dscaled);
+    const int64_t slots = obs->x_paired ? 2 * obs->n_xrows : o.n_det;
+    TB_REQUIRE(slots < 65536, "too many detectors for the prescale grid");
+    dim3 grid((unsigned)gx, (unsigned)slots);
+    k_amp_prescale<<<grid, kThreads, 0, (cudaStream_t)stream>>>(o, nad, obs->x_paired, amps, aflags,
+                                                                obs->dscaled);
     TB_CUDA(cudaGetLastError());
     tbr::count_launch();
 }
 
-void launch_bin_sorted(const tb_obs *obs, int64_t rec_first, int64_t rec_end, double *zmap,
-                       void *stream) {
+template <bool UNIFORM, bool PAIRED>
+void launch_bin_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_end, double *zmap,
+                         void *stream) {
     int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
     double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    auto k = k_bin_xs<UNIFORM, PAIRED>;
+    TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
+               obs->stable, zmap);
+}
+
+void launch_bin_sorted(const tb_obs *obs, int64_t rec_first, int64_t rec_end, double *zmap,
+                       void *stream) {
     if (obs->s_uniform) {
-        auto k = k_bin_xs<true>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
-                   (int32_t)obs->n_amp_det, cst, obs->stable, zmap);
+        if (obs->x_paired) launch_bin_sorted_t<true, true>(obs, rec_first, rec_end, zmap, stream);
+        else launch_bin_sorted_t<true, false>(obs, rec_first, rec_end, zmap, stream);
     } else {
-        auto k = k_bin_xs<false>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
-                   (int32_t)obs->n_amp_det, cst, obs->stable, zmap);
+        if (obs->x_paired) launch_bin_sorted_t<false, true>(obs, rec_first, rec_end, zmap, stream);
+        else launch_bin_sorted_t<false, false>(obs, rec_first, rec_end, zmap, stream);
     }
+}
+
+template <bool UNIFORM, bool PAIRED>
+void launch_project_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_end,
+                             const double *binned, double *out, void *stream) {
+    int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
+    double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    auto k = k_proj_xs<UNIFORM, PAIRED>;
+    TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
+               (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
+               (int)obs->d.n_det, binned, out);
 }
 
 void launch_project_sorted(const tb_obs *obs, int64_t rec_first, int64_t rec_end,
                            const double *binned, double *out, void *stream) {
-    int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
-    double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
     if (obs->s_uniform) {
-        auto k = k_proj_xs<true>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
-                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
-                   obs->x_paired, (int)obs->d.n_det, binned, out);
+        if (obs->x_paired)
+            launch_project_sorted_t<true, true>(obs, rec_first, rec_end, binned, out, stream);
+        else
+            launch_project_sorted_t<true, false>(obs, rec_first, rec_end, binned, out, stream);
     } else {
-        auto k = k_proj_xs<false>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
-                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
-                   obs->x_paired, (int)obs->d.n_det, binned, out);
+        if (obs->x_paired)
+            launch_project_sorted_t<false, true>(obs, rec_first, rec_end, binned, out, stream);
+        else
+            launch_project_sorted_t<false, false>(obs, rec_first, rec_end, binned, out, stream);
     }
 }
 
@@ -1890,7 +1926,8 @@ static void build_sorted(tb_obs *obs, cudaStream_t st) {
     }
     TB_CUDA(cudaMalloc(&obs->stable, sizeof(double4) * n_rows));
     TB_CUDA(cudaMemcpy(obs->stable, tab.data(), sizeof(double4) * n_rows, cudaMemcpyHostToDevice));
-    TB_CUDA(cudaMalloc(&obs->dscaled, sizeof(double) * n_det * nad));
+    TB_CUDA(cudaMalloc(&obs->dscaled,
+                       sizeof(double) * (obs->x_paired ? 2 * n_rows : n_det) * nad));
     obs->s_uniform = uniform ? 1 : 0;
     obs->s_const[0] = tab[0].x;
     obs->s_const[1] = tab[0].y;
