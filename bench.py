@@ -555,6 +555,7 @@ def main_gpu(args):
                                  if ds.peer is not None else
                                  ("NCCL all-reduce + cov_apply" if world > 1 else "cov_apply"),
                 "zmap_bytes": int(ds.zmap.numel() * 8),
+                "pipeline_tuning_ms": getattr(ds, "pipe_tune_ms", None),
                 "pipeline": (f"{ds.n_chunks} pixel chunks: pass 1 -> NVLink reduction -> pass 2 "
                              "overlapped on two streams; pass1/pass2/reduce_cov_ms are from "
                              "un-pipelined applications outside the timed region")

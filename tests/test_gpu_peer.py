@@ -188,7 +188,6 @@ def _solve_worker(rank, world, port, out):
                 for _ in range(3):
                     ds.lhs(a, q_pipe)
                 ds.pipeline = False
-                L_.check(L_.load().tb_set_option(b"peer_ctas", 12))
                 ds.lhs(a, q_ser)
                 torch.cuda.synchronize()
                 res["pipe_err"] = max(res.get("pipe_err", 0.0),

@@ -349,11 +349,20 @@ class Destriper:
         else:
             self.zmap = torch.zeros((self.n_local_submap, self.n_pix_submap, 3),
                                     dtype=torch.float64, device=self.device)
-        # The chunk pipeline is OPT-IN (TB_PIPE_CHUNKS=4): measured on 2 GPUs it gains 9-14 %
-        # (1.46-1.54 ms against 1.69 ms per iteration) because the reduction kernel and the
-        # passes compete for the same L1/LSU and L2 bandwidth; not yet measured on 4 / 8 GPUs.
+        # Chunk pipeline (multi-GPU): TB_PIPE_CHUNKS = "auto" (default: set it up with 4 chunks,
+        # time it against the serial LHS on this node and keep the faster form), 0 (off) or K.
+        # Measured on 2 GPUs: 1.46-1.54 ms against 1.69 ms per iteration with 4 chunks, slower
+        # than serial with 8-16.
         self.pipeline = False
-        self._setup_pipeline(int(_os.environ.get("TB_PIPE_CHUNKS", "0")))
+        self.pipe_tune_ms = None
+        self._ctas_set = None
+        mode = _os.environ.get("TB_PIPE_CHUNKS", "auto")
+        if mode == "auto":
+            self._setup_pipeline(4)
+            if self.pipeline:
+                self._tune_pipeline()
+        else:
+            self._setup_pipeline(int(mode))
 
     # -- chunk pipeline -------------------------------------------------------------------------
     def _sorted_passes(self):
@@ -383,17 +392,54 @@ class Destriper:
         self.chunk_bounds = bounds
         self.n_chunks = n_chunks
         self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
-        # leave most of every SM to the passes the reduction overlaps (measured best: 3)
-        L.check(self.lib.tb_set_option(b"peer_ctas", int(_os.environ.get("TB_PEER_CTAS", "3"))))
+        # overlapped, the reduction leaves most of every SM to the passes (measured best: 3
+        # CTAs per SM); stand-alone it takes 12
+        self.pipe_ctas = int(_os.environ.get("TB_PEER_CTAS", "3"))
         self.ev_binned = [torch.cuda.Event() for _ in range(n_chunks)]
         self.ev_reduced = [torch.cuda.Event() for _ in range(n_chunks)]
         self.pipeline = True
         self.use_graph = _os.environ.get("TB_GRAPH", "1") != "0"
         self._graphs = {}
 
+    def _peer_ctas(self, n):
+        if self.peer is not None and self._ctas_set != n:
+            L.check(self.lib.tb_set_option(b"peer_ctas", n))
+            self._ctas_set = n
+
+    def _tune_pipeline(self, reps=3):
+        """Time the pipelined against the serial LHS (max over ranks, so that every rank takes
+        the same decision) and keep the faster one."""
+        import torch.distributed as dist
+
+        g = torch.Generator(device=self.device)
+        g.manual_seed(1234)
+        a = torch.randn(self.n_amp, generator=g, device=self.device, dtype=torch.float64)
+        a[self.amp_flags != 0] = 0.0
+        q = torch.zeros_like(a)
+        times = []
+        for pipelined in (True, False):
+            self.pipeline = pipelined
+            self.lhs(a, q)  # warm-up (and graph capture)
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize(self.device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                self.lhs(a, q)
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            times.append(e0.elapsed_time(e1) / reps)
+        t = torch.tensor(times, dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.pipe_tune_ms = {"pipelined": float(t[0]), "serial": float(t[1])}
+        self.pipeline = bool(t[0] < t[1])
+        self._graphs = {}
+        dist.barrier(group=self.group)
+
     def _lhs_pipelined(self, amps_in, amps_out):
-        """The pipelined LHS, replayed from a CUDA graph: 3 launches + 2 cross-stream edges per
-        chunk are launch-bound from Python (measured: ~30 us of host time per chunk)."""
+        """The pipelined LHS, replayed from a CUDA graph (3 launches + 2 cross-stream edges per
+        chunk)."""
+        self._peer_ctas(self.pipe_ctas)
         if not self.use_graph:
             return self._enqueue_pipelined(amps_in, amps_out)
         key = (amps_in.data_ptr(), amps_out.data_ptr())
@@ -462,6 +508,7 @@ class Destriper:
         (mapmaker_utils.py:885-925 + covariance.py:262-306), fused over NVLink peer memory when
         there is more than one rank."""
         if self.peer is not None:
+            self._peer_ctas(12)
             self.peer.reduce_cov(self.cov)
             return
         self._allreduce(self.zmap)
