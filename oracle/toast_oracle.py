@@ -286,8 +286,10 @@ def cov_eigendecompose_diag(nsub, subsize, nnz, data, cond, threshold, invert=Tr
     """libtoast/src/toast_map_cov.cpp:246-396 restated with numpy.linalg.eigh.
 
     ``data`` is [nsub*subsize, nnz(nnz+1)/2] upper triangle row-major, modified in place.
-    LAPACK ``dsyev`` is absent from this image, so this one function is UNPINNED against the
-    compiled reference (setup-time only).
+    PINNED: the reference's own implementation runs in the build container with its LAPACK calls
+    forwarded to the OpenBLAS scipy bundles (oracle/ref_shim/lapack_shim.cpp); its outputs are
+    the fixture tests/golden/cov_invert.npz (tests/test_oracle.py: rcond to 1e-12, the same
+    pixels kept, inverses within 1e-13 / rcond).
     """
     npix = nsub * subsize
     block = nnz * (nnz + 1) // 2

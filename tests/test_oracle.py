@@ -104,6 +104,60 @@ def test_c_port_covariance_matches_reference():
     np.testing.assert_array_equal(v1, v2)
 
 
+def _check_cov_inverse(inv, rc, inv_ref, rc_ref, threshold, what):
+    """rcond to 1e-12; the same pixels kept (except where rcond sits on the threshold); the
+    inverse of a kept pixel within 1e-13 / rcond of the reference's (its conditioning)."""
+    near = np.abs(rc_ref - threshold) < 1e-6 * threshold
+    np.testing.assert_array_equal((rc > 0)[~near], (rc_ref > 0)[~near], err_msg=what)
+    kept = (rc > 0) & (rc_ref > 0)
+    assert kept.sum() > 100
+    np.testing.assert_allclose(rc[kept], rc_ref[kept], rtol=1e-12, err_msg=what)
+    scale = np.max(np.abs(inv_ref), axis=1)
+    err = np.max(np.abs(inv - inv_ref), axis=1)
+    assert np.all(err[kept] <= 1e-13 / rc_ref[kept] * scale[kept]), what
+    dropped = (rc == 0) & (rc_ref == 0)
+    assert np.all(inv[dropped] == 0.0) and np.all(inv_ref[dropped] == 0.0)
+
+
+@pytest.mark.parametrize("thr", ["1e-3", "1e-8"])
+def test_cov_eigendecompose_matches_reference_golden(thr):
+    """The numpy restatement of cov_eigendecompose_diag against the outputs of the reference's
+    own LAPACK-based implementation (tests/golden/make_golden_cov.py)."""
+    g = np.load(f"{H.GOLDEN}/cov_invert.npz")
+    blocks = g["blocks"]
+    d = blocks.reshape(-1).copy()
+    rc = np.zeros(len(blocks))
+    O.cov_eigendecompose_diag(1, len(blocks), 3, d, rc, float(thr), True)
+    _check_cov_inverse(d.reshape(-1, 6), rc, g[f"inverse_{thr}"], g[f"rcond_{thr}"], float(thr),
+                       f"golden {thr}")
+    d2 = blocks.reshape(-1).copy()
+    rc2 = np.zeros(len(blocks))
+    O.cov_eigendecompose_diag(1, len(blocks), 3, d2, rc2, 1e-3, False)
+    np.testing.assert_array_equal(d2.reshape(-1, 6), blocks)
+    np.testing.assert_allclose(rc2, g["rcond_noinvert"], rtol=1e-12, atol=0)
+
+
+@needs_ref
+def test_cov_eigendecompose_matches_compiled_reference():
+    """Live, when oracle/_ref was built with LAPACK (scipy's OpenBLAS through
+    oracle/ref_shim/lapack_shim.cpp): other matrices than the fixture's."""
+    rng = np.random.default_rng(11)
+    npix = 3000
+    w = rng.standard_normal((npix, 6, 3))
+    w[:, :, 0] = 1.0
+    m = np.einsum("pki,pkj->pij", w, w)
+    iu = np.triu_indices(3)
+    blocks = np.ascontiguousarray(m[:, iu[0], iu[1]])
+    d1, d2 = blocks.reshape(-1).copy(), blocks.reshape(-1).copy()
+    r1, r2 = np.zeros(npix), np.zeros(npix)
+    try:
+        REF.cov_eigendecompose_diag(1, npix, 3, d2, r2, 1e-4, True)
+    except RuntimeError as exc:  # reference built without LAPACK
+        pytest.skip(f"reference eigendecomposition unavailable: {exc}")
+    O.cov_eigendecompose_diag(1, npix, 3, d1, r1, 1e-4, True)
+    _check_cov_inverse(d1.reshape(-1, 6), r1, d2.reshape(-1, 6), r2, 1e-4, "live")
+
+
 @pytest.mark.parametrize("fixture", ["c1_tiny", "c2_slice", "c5_slice"])
 def test_c_port_reproduces_golden_reference_outputs(fixture):
     """Pins the C restatement on machines where /root/reference does not exist."""
