@@ -7,7 +7,10 @@ PixelDistribution, the PCG ``solve()`` loop, ``SolverLHS``/``SolverRHS``).  Used
 The product package ``toast_b200`` never imports this module.
 
 Parity status: PINNED against the reference's compiled kernels (``oracle/_ref``) by
-``tests/test_oracle_vs_ref.py`` and the committed fixtures in ``tests/golden``.
+``tests/test_oracle.py`` and the committed fixtures in ``tests/golden``; the PCG loop ``solve``
+is pinned bit for bit against the reference's own ``solve()`` executed from its source
+(``tests/golden/make_golden_solve.py``), ``cov_eigendecompose_diag`` against the reference's
+LAPACK-based implementation (``tests/golden/make_golden_cov.py``).
 
 The keyword names and argument order of the kernel wrappers follow the reference's
 ``_libtoast`` signatures so a test can call either this module,

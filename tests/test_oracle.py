@@ -244,3 +244,23 @@ def test_lhs_equals_rhs_of_template_signal():
     O.template_add(pb, O, a, sig)
     np.testing.assert_allclose(O.solver_lhs(pb, O, a), O.solver_rhs(pb, O, sig), rtol=0,
                                atol=1e-12 * np.abs(a).max() * pb.det_scale.max() * 100)
+
+
+@pytest.mark.parametrize("tag,name", [("c1", "c1"), ("c2", "c2")])
+def test_solve_restatement_is_bit_identical_to_reference_solve(tag, name):
+    """The oracle's PCG loop against the reference's OWN ``solve()``
+    (ops/mapmaker_solve.py:524-755), which tests/golden/make_golden_solve.py executes from the
+    reference source with the compiled reference kernels behind its LHS operator: residual
+    history (every iteration, including the convergence break of c1) and amplitudes, bit for
+    bit."""
+    g = np.load(f"{H.GOLDEN}/solve_reference.npz")
+    n_det, n_samp, nside, n_iter = [int(x) for x in g[f"{tag}_args"]]
+    obs = S.make_observation(name, n_det=n_det, n_samp=n_samp, nside=nside, eps_max=0.03)
+    pb = O.build_problem(obs, O)
+    rhs = O.solver_rhs(pb, O, obs["signal"])
+    np.testing.assert_array_equal(rhs, g[f"{tag}_rhs"])
+    amps, hist = O.solve(pb, O, rhs, n_iter_max=n_iter)
+    np.testing.assert_array_equal(np.array(hist), g[f"{tag}_history"])
+    np.testing.assert_array_equal(amps, g[f"{tag}_amplitudes"])
+    if tag == "c1":
+        assert len(hist) < n_iter and hist[-1] < 1e-12   # the convergence test fired
