@@ -7,13 +7,13 @@ these in Python on the host -- numpy + ``scipy.signal.convolve`` + ``scipy.linal
 calls the same library routines in the same order, segment by segment, so it is the reference's
 algorithm verbatim up to variable names.
 
-Parity status: the four PSD helpers (``interpolate_psd``, ``truncate``, ``remove_white_noise``,
-``get_offset_psd``) are PINNED against the reference's own method bodies, executed from
-``/root/reference`` by ``tests/golden/make_golden_prior.py`` (fixture
-``tests/golden/offset_prior.npz``).  The filter / preconditioner assembly loop and the two
-application loops live inside ``Offset._initialize`` / ``_add_prior`` / ``_apply_precond``, which
-cannot run without the full TOAST package: they are restated here line by line (file:line cited
-at each step) and are the checker for the CUDA kernels.
+Parity status: PINNED.  ``tests/golden/make_golden_prior.py`` and
+``tests/golden/make_golden_offset_init.py`` execute the reference's OWN method bodies from
+``/root/reference`` (lifted out of offset.py with ``ast`` and bound to duck-typed stand-ins for
+the template, the data, astropy units and the noise model): the PSD helpers, the whole
+``_initialize`` (layout, amplitude flags / variance, filters, banded and Toeplitz preconditioners),
+``_add_prior`` and ``_apply_precond``.  Every function of this module reproduces those outputs
+bit for bit (tests/test_offset_prior.py; fixtures ``offset_prior.npz``, ``offset_template.npz``).
 
 The product package ``toast_b200`` never imports this module.
 """

@@ -171,3 +171,107 @@ def test_filter_longer_than_the_segment_and_cut_detectors():
                          _ptr(out), ct.c_int(0))
     H.assert_close_norm(out, ref, rtol=1e-13, what="short segments")
     assert np.all(out[per:2 * per] == 0.0)
+
+
+# ---- the reference's own Offset methods, executed from its source --------------------------------
+# tests/golden/make_golden_offset_init.py runs Offset._initialize / _add_prior / _apply_precond of
+# /root/reference with duck-typed stand-ins; the oracle restatements reproduce them bit for bit.
+OFFSET_CASES = [("plain_c2", "c2", False, 20, True), ("plain_c1", "c1", False, 20, True),
+                ("prior_banded_c1", "c1", True, 20, False),
+                ("prior_banded4_c4", "c4", True, 4, False),
+                ("prior_toeplitz_c2", "c2", True, 1, True)]
+
+
+def reference_offset_case(tag, name, prior, use_det_flags):
+    """Inputs of one fixture case, rebuilt exactly as the generator built them, and the oracle's
+    layout / variance for them."""
+    from helpers import O, S
+
+    g = np.load(f"{H.GOLDEN}/offset_template.npz")
+    n_det, n_samp = [int(x) for x in g[f"{tag}_args"]]
+    obs = S.make_observation(name, n_det=n_det, n_samp=n_samp, nside=64, eps_max=0.03)
+    # with a noise prior the baselines span the observation, the view only flags samples
+    # (offset.py:136-141)
+    bounds = O.make_intervals([(0, n_samp)]) if prior else obs["intervals"]
+    nav, det_start, n_amp = O.offset_layout(n_det, bounds, obs["step_length"])
+    in_view = np.zeros(n_samp, dtype=bool)
+    for v in obs["intervals"]:
+        in_view[v["first"]:v["last"]] = True
+    sf = np.zeros((n_det, n_samp), dtype=np.uint8)
+    if use_det_flags:
+        sf |= obs["det_flags"] & 1
+    sf |= (~in_view).astype(np.uint8)[None, :]
+    var, fl = O.offset_variance(n_det, n_samp, bounds, obs["step_length"], nav, obs["detweight"],
+                                sf, 1)
+    return g, obs, bounds, nav, det_start, n_amp, sf, var, fl
+
+
+@pytest.mark.parametrize("tag,name,prior,precond_width,use_det_flags", OFFSET_CASES)
+def test_oracle_offset_glue_is_bit_identical_to_reference_methods(tag, name, prior,
+                                                                  precond_width, use_det_flags):
+    g, obs, bounds, nav, det_start, n_amp, sf, var, fl = reference_offset_case(
+        tag, name, prior, use_det_flags)
+    np.testing.assert_array_equal(nav, g[f"{tag}_n_amp_views"])
+    np.testing.assert_array_equal(det_start, g[f"{tag}_det_start"])
+    np.testing.assert_array_equal(fl, g[f"{tag}_amp_flags"])
+    np.testing.assert_array_equal(var, g[f"{tag}_offset_var"])
+    if not prior:
+        return
+    # the rate the template derives from the timestamps (1 / median dt: 9.999999999999858 Hz)
+    n_samp, rate = obs["n_samp"], float(g[f"{tag}_rate"])
+    assert abs(rate - obs["rate"]) < 1e-9
+    assert rate == 1.0 / np.median(np.diff(np.arange(n_samp, dtype=np.float64) / obs["rate"]))
+    psdfreq, psds = OP.analytic_psd(obs["sigma"], obs["rate"], fknee=0.05, fmin=1e-4, alpha=1.5,
+                                    n_freq=300)
+    t = np.arange(n_samp, dtype=np.float64) / obs["rate"]
+    obstime = float(t[-1] - t[0])
+    np.testing.assert_array_equal(
+        OP.prior_frequencies(obstime, float(obs["step_time"]), rate), g[f"{tag}_freq"])
+    pr = OP.build_prior(psdfreq, psds, obs["detweight"], var, nav, obstime,
+                        float(obs["step_time"]), rate, precond_width=precond_width)
+    for i in range(obs["n_det"]):
+        for v in range(len(nav)):
+            np.testing.assert_array_equal(pr.filters[i][v], g[f"{tag}_filter_{i}_{v}"])
+            np.testing.assert_array_equal(np.asarray(pr.precond[i][v][0]),
+                                          g[f"{tag}_precond_{i}_{v}"])
+    out = g[f"{tag}_amps_out0"].copy()
+    OP.add_prior(pr, g[f"{tag}_amps_in"], g[f"{tag}_flags_in"], out)
+    np.testing.assert_array_equal(out, g[f"{tag}_add_prior"])
+    pre = np.zeros_like(out)
+    OP.apply_precond(pr, g[f"{tag}_amps_in"], g[f"{tag}_flags_in"], pre)
+    np.testing.assert_array_equal(pre, g[f"{tag}_apply_precond"])
+
+    # the product's assembly and kernel cores on the same case
+    b = PP.OffsetPriorBuilder(n_amp, precond_width)
+    freq = PP.prior_frequencies(obstime, float(obs["step_time"]), rate)
+    for d in range(obs["n_det"]):
+        b.add_detector(int(det_start[d]), nav, psdfreq, psds[d], obs["detweight"][d], var, freq,
+                       float(obs["step_time"]))
+    k = 0
+    for i in range(obs["n_det"]):
+        for v in range(len(nav)):
+            np.testing.assert_array_equal(b.filters[k], g[f"{tag}_filter_{i}_{v}"])
+            np.testing.assert_array_equal(b.precond[k], g[f"{tag}_precond_{i}_{v}"].reshape(-1))
+            k += 1
+    hm = H.host_math_lib()
+    seg_start, seg_len = _i64(b.seg_start), _i64(b.seg_len)
+    f_start, f_len = _i64(b.filt_start), _i64(b.filt_len)
+    p_start, p_width = _i64(b.prec_start), _i64(b.prec_width)
+    taps, pre_v = np.concatenate(b.filters), np.concatenate(b.precond)
+    a_in = np.ascontiguousarray(g[f"{tag}_amps_in"])
+    flags = np.ascontiguousarray(g[f"{tag}_flags_in"])
+    out = g[f"{tag}_amps_out0"].copy()
+    hm.tbp_conv_segments(ct.c_int64(len(seg_start)), _ptr(seg_start), _ptr(seg_len),
+                         _ptr(f_start), _ptr(f_len), _ptr(taps), _ptr(a_in), _ptr(flags),
+                         _ptr(out), ct.c_int(0))
+    H.assert_close_norm(out, g[f"{tag}_add_prior"], rtol=1e-13, what="add_prior core")
+    res = np.zeros_like(out)
+    if precond_width == 1:
+        hm.tbp_conv_segments(ct.c_int64(len(seg_start)), _ptr(seg_start), _ptr(seg_len),
+                             _ptr(p_start), _ptr(p_width), _ptr(pre_v), _ptr(a_in), _ptr(flags),
+                             _ptr(res), ct.c_int(1))
+    else:
+        hm.tbp_banded_segments(ct.c_int64(len(seg_start)), _ptr(seg_start), _ptr(seg_len),
+                               _ptr(p_start), _ptr(p_width), _ptr(pre_v), _ptr(a_in),
+                               _ptr(flags), _ptr(res))
+    H.assert_close_norm(res, g[f"{tag}_apply_precond"], rtol=1e-12, what="apply_precond core")
