@@ -143,17 +143,21 @@ def test_pcg_with_noise_prior(name, n_det, n_samp, nside, precond_width):
                              what=f"{name} with prior")
 
 
-@pytest.mark.parametrize("precond_width,det_flags", [(20, None), (1, "flags")])
+@pytest.mark.parametrize("precond_width,det_flags,name,n_samp",
+                         [(20, None, "c1", 6000), (1, "flags", "c2", 24000)])
 @pytest.mark.parametrize("use_accel", [False, True])
-def test_offset_template_with_noise_prior(precond_width, det_flags, use_accel):
+def test_offset_template_with_noise_prior(precond_width, det_flags, name, n_samp, use_accel):
     """templates.Offset(use_noise_prior=True).add_prior / apply_precond -- which the reference
     can only run on the host (offset.py:888-891, 964-967) -- against the oracle restatement,
-    with host arrays and with amplitudes registered in the accel table.  The Toeplitz form is
-    run with detector flags (some baselines flagged); the banded form cannot be built then."""
+    with host arrays and with amplitudes registered in the accel table.  With the prior the
+    baselines span the observation and the view only flags samples (offset.py:136-141).  The
+    Toeplitz form runs on the ground scan with detector flags and turnarounds (flagged
+    baselines); the banded form cannot be built with flagged baselines (the reference's
+    cholesky_banded rejects 1 / offsetvar = inf), so it runs on the gap-free satellite scan."""
     from toast_b200.data import Data, NoiseModel, observation_from_synthetic
     from toast_b200.templates import Offset
 
-    obs = S.make_observation("c2", n_det=4, n_samp=24000, nside=64, eps_max=0.03)
+    obs = S.make_observation(name, n_det=4, n_samp=n_samp, nside=64, eps_max=0.03)
     data = Data()
     ob = observation_from_synthetic(obs)
     data.obs.append(ob)
@@ -168,10 +172,13 @@ def test_offset_template_with_noise_prior(precond_width, det_flags, use_accel):
                   noise_model="noise_model", det_flags=det_flags, det_flag_mask=1,
                   view="scanning", use_noise_prior=True, precond_width=precond_width)
     tmpl.initialize(data)
-    nav, det_start, n_amp = O.offset_layout(4, obs["intervals"], obs["step_length"])
+    nav, det_start, n_amp = O.offset_layout(4, O.make_intervals([(0, n_samp)]),
+                                            obs["step_length"])
+    np.testing.assert_array_equal(tmpl._obs_views[0], nav)
+    assert tmpl._n_local == n_amp
     t = ob.shared["times"]
     oprior = OP.build_prior(psdfreq, psds, obs["detweight"], tmpl._offsetvar, nav,
-                            float(t[-1] - t[0]), obs["step_time"], rate,
+                            float(t[-1] - t[0]), obs["step_time"], tmpl._obs_rate[0],
                             precond_width=precond_width)
     a_in, out, pre = tmpl.zeros(), tmpl.zeros(), tmpl.zeros()
     if det_flags is not None:

@@ -275,3 +275,68 @@ def test_oracle_offset_glue_is_bit_identical_to_reference_methods(tag, name, pri
                                _ptr(p_start), _ptr(p_width), _ptr(pre_v), _ptr(a_in),
                                _ptr(flags), _ptr(res))
     H.assert_close_norm(res, g[f"{tag}_apply_precond"], rtol=1e-12, what="apply_precond core")
+
+
+def _numpy_project_batch(data_index, det_data, flag_index, flag_data, flag_mask, step_length,
+                         amp_offsets, n_amp_views, amplitudes, amplitude_flags, intervals):
+    """numpy stand-in of the CUDA kernel behind kernels.template_offset_project_signal_batch
+    (template_offset.cpp:243-327), so that the template's HOST logic can run without a GPU."""
+    view_off = np.concatenate([[0], np.cumsum(n_amp_views)[:-1]])
+    for k, row in enumerate(data_index):
+        for v, iv in enumerate(intervals):
+            first, last = int(iv["first"]), int(iv["last"])
+            s = np.arange(first, last)
+            amp = int(amp_offsets[k]) + int(view_off[v]) + (s - first) // int(step_length)
+            good = np.ones(len(s), dtype=bool)
+            if flag_data is not None:
+                good = (flag_data[int(flag_index[k]), first:last] & flag_mask) == 0
+            good &= amplitude_flags[amp] == 0
+            np.add.at(amplitudes, amp[good], det_data[int(row), first:last][good])
+
+
+@pytest.mark.parametrize("tag,name,prior,precond_width,use_det_flags", OFFSET_CASES)
+def test_template_mirror_host_logic_matches_reference_initialize(tag, name, prior,
+                                                                 precond_width, use_det_flags,
+                                                                 monkeypatch):
+    """templates.Offset._initialize of the product (layout, amplitude flags, variance, and --
+    with use_noise_prior -- baselines spanning the observation plus the filter / preconditioner
+    assembly) against the reference's own _initialize, the CUDA projection kernel replaced by a
+    numpy stand-in."""
+    from toast_b200.data import Data, NoiseModel, observation_from_synthetic
+    from toast_b200.templates import Offset
+    from toast_b200.templates import offset as offset_module
+
+    monkeypatch.setattr(offset_module.KC, "template_offset_project_signal_batch",
+                        _numpy_project_batch)
+    g, obs, bounds, nav, det_start, n_amp, sf, var, fl = reference_offset_case(
+        tag, name, prior, use_det_flags)
+    data = Data()
+    ob = observation_from_synthetic(obs)
+    data.obs.append(ob)
+    dets = ob.local_detectors
+    psdfreq, psds = OP.analytic_psd(obs["sigma"], obs["rate"], fknee=0.05, fmin=1e-4, alpha=1.5,
+                                    n_freq=300)
+    ob["noise_model"] = NoiseModel({d: float(w) for d, w in zip(dets, obs["detweight"])},
+                                   {d: psdfreq for d in dets},
+                                   {d: psds[i] for i, d in enumerate(dets)})
+    tmpl = Offset(name="baselines", step_time=float(obs["step_time"]), times="times",
+                  noise_model="noise_model", det_flags="flags" if use_det_flags else None,
+                  det_flag_mask=1, view="scanning", use_noise_prior=prior,
+                  precond_width=precond_width)
+    tmpl._defer_prior = True   # OffsetPrior.finish() uploads to the device
+    tmpl.initialize(data)
+    np.testing.assert_array_equal(tmpl._obs_views[0], g[f"{tag}_n_amp_views"])
+    np.testing.assert_array_equal([tmpl._det_start[d] for d in dets], g[f"{tag}_det_start"])
+    assert tmpl._obs_rate[0] == float(g[f"{tag}_rate"])
+    np.testing.assert_array_equal(tmpl._amp_flags.astype(np.uint8), g[f"{tag}_amp_flags"])
+    np.testing.assert_array_equal(tmpl._offsetvar, g[f"{tag}_offset_var"])
+    if not prior:
+        return
+    b = tmpl._prior_builder(data)
+    k = 0
+    for i in range(obs["n_det"]):
+        for v in range(len(nav)):
+            np.testing.assert_array_equal(b.filters[k], g[f"{tag}_filter_{i}_{v}"])
+            np.testing.assert_array_equal(b.precond[k], g[f"{tag}_precond_{i}_{v}"].reshape(-1))
+            assert b.seg_start[k] == det_start[i] + int(nav[:v].sum()) and b.seg_len[k] == nav[v]
+            k += 1

@@ -127,7 +127,9 @@ class MapMaker(Operator):
         for iob, ob in enumerate(data.obs):
             dets = [d for d in tmpl._all_dets if d in tmpl._obs_dets[iob]]
             fp = ob[dp.focalplane_key]
-            iv = ob.intervals[view]
+            # with a noise prior the baselines span the observation and the view only flags
+            # samples (offset.py:136-141; the view flags are ORed into the solver flags below)
+            iv = ob.intervals[tmpl._bounds_view if tmpl.use_noise_prior else view]
             sflag = ob.shared[self.shared_flags] if self.shared_flags is not None else None
             flags = np.zeros((len(dets), ob.n_local_samples), dtype=np.uint8)
             if self.det_flags is not None:

@@ -70,6 +70,10 @@ class Offset(Template):
         if self.use_noise_prior and self.noise_model is None:
             raise RuntimeError("cannot use the noise prior without a noise model")  # :136-138
         self._prior = None
+        # offset.py:136-141: with a noise prior the baselines span the whole observation and the
+        # view only flags samples; without it the view defines the baseline boundaries
+        self._bounds_view = None if self.use_noise_prior else self.view
+        self._obs_flags = {}
         self._obs_views, self._obs_view_flags = {}, {}
         self._obs_rate, self._obs_dets = {}, {}
         all_dets = {}
@@ -79,7 +83,7 @@ class Offset(Template):
             self._obs_rate[iob] = rate
             step = self._step_length(self.step_time, rate)
             views = []
-            for vw in ob.intervals[self.view]:
+            for vw in ob.intervals[self._bounds_view]:
                 ln = int(vw["last"] - vw["first"])
                 n = ln // step
                 if n * step < ln:
@@ -131,19 +135,27 @@ class Offset(Template):
             offs = np.array([self._obs_amp_offset(d, iob) for d in dets], dtype=np.int64)
             ones = np.ones((len(dets), ob.n_local_samples))
             didx = np.arange(len(dets), dtype=np.int32)
-            if self.det_flags is not None:
+            bounds = ob.intervals[self._bounds_view]
+            if self.use_noise_prior:
+                # the view is not what the kernel iterates over: its complement is a flag
+                # (offset.py:318-325), kept per observation for project_signal as well
+                self._obs_flags[iob] = self._combined_flags(ob, iob)
+                fd = self._obs_flags[iob]
+                fidx = np.array([self._flag_row(ob, d) for d in dets], dtype=np.int32)
+                KC.template_offset_project_signal_batch(didx, ones, fidx, fd, 1, step, offs, nav,
+                                                        n_good, zero_flags, bounds)
+            elif self.det_flags is not None:
                 fl = np.ascontiguousarray(
                     ob.detdata[self.det_flags].data[ob.detdata[self.det_flags].indices(dets)])
                 KC.template_offset_project_signal_batch(didx, ones, didx, fl, self.det_flag_mask,
                                                         step, offs, nav, n_good, zero_flags,
-                                                        ob.intervals[self.view])
+                                                        bounds)
             else:
                 KC.template_offset_project_signal_batch(didx, ones, None, None, 0, step, offs,
-                                                        nav, n_good, zero_flags,
-                                                        ob.intervals[self.view])
+                                                        nav, n_good, zero_flags, bounds)
             lens = np.concatenate([
                 np.minimum(step, int(vw["last"] - vw["first"]) - step * np.arange(na))
-                for vw, na in zip(ob.intervals[self.view], nav)]) if per_det else np.zeros(0)
+                for vw, na in zip(bounds, nav)]) if per_det else np.zeros(0)
             for d, o in zip(dets, offs):
                 amplen[o:o + per_det] = lens
                 if self.noise_model is not None:
@@ -158,9 +170,32 @@ class Offset(Template):
         if self.use_noise_prior and not getattr(self, "_defer_prior", False):
             self._build_prior(new_data)
 
+    def _flag_row(self, ob, det):
+        """Row of ``det`` in the combined flag array of its observation."""
+        if self.det_flags is not None:
+            return int(ob.detdata[self.det_flags].indices([det])[0])
+        return 0
+
+    def _combined_flags(self, ob, iob):
+        """(det_flags & mask != 0) | outside-the-view as one uint8 array in the layout of the
+        flag detdata (a single shared row without detector flags): what the reference builds
+        per call at offset.py:829-832."""
+        vf = self._obs_view_flags[iob]
+        if self.det_flags is None:
+            return np.ascontiguousarray(vf[None, :])
+        fd = ob.detdata[self.det_flags].data
+        return np.ascontiguousarray(((fd & self.det_flag_mask) != 0).astype(np.uint8)
+                                    | vf[None, :])
+
     def _build_prior(self, data):
         """offset.py:203-222 + 356-560: per (detector, observation, view) the real-space noise
         filter and the preconditioner, uploaded once; applied by tb_offset_prior_add / _precond."""
+        b = self._prior_builder(data)
+        if b is not None:
+            self._prior = b.finish()
+
+    def _prior_builder(self, data):
+        """Host-side assembly only (no device needed)."""
         b = OffsetPriorBuilder(self._n_local, self.precond_width)
         any_prior = False
         for det in self._all_dets:
@@ -179,8 +214,7 @@ class Offset(Template):
                 b.add_detector(start, self._obs_views[iob], noise.freq(det), noise.psd(det),
                                noise.detector_weight(det), self._offsetvar, freq, self.step_time)
                 any_prior = True
-        if any_prior or self._n_local > 0:
-            self._prior = b.finish()
+        return b if (any_prior or self._n_local > 0) else None
 
     def _obs_amp_offset(self, det, iob):
         off = self._det_start[det]
@@ -204,7 +238,7 @@ class Offset(Template):
             K.template_offset_add_to_signal(
                 step, self._obs_amp_offset(detector, iob), self._obs_views[iob], amplitudes.local,
                 amplitudes.local_flags, int(ob.detdata[self.det_data].indices([detector])[0]),
-                ob.detdata[self.det_data].data, ob.intervals[self.view], use_accel)
+                ob.detdata[self.det_data].data, ob.intervals[self._bounds_view], use_accel)
 
     def _project_signal(self, detector, amplitudes, use_accel=False):
         if detector not in self._all_dets:
@@ -213,7 +247,15 @@ class Offset(Template):
             if detector not in self._obs_dets[iob]:
                 continue
             step = self._step_length(self.step_time, self._obs_rate[iob])
-            if self.det_flags is not None:
+            fmask = self.det_flag_mask
+            if self.use_noise_prior:
+                # baselines span the observation: samples outside the view are cut by the
+                # combined flags built at initialisation (registered on first accel use)
+                fidx, fdata, fmask = self._flag_row(ob, detector), self._obs_flags[iob], 1
+                if use_accel and not K.accel_present(fdata, "offset_flags"):
+                    K.accel_create(fdata, "offset_flags")
+                    K.accel_update_device(fdata, "offset_flags")
+            elif self.det_flags is not None:
                 # the reference ORs the view flags into a per-call host copy of the whole flag
                 # array (offset.py:829-832); the view is already what the kernel iterates over,
                 # so the registered flag buffer can be used directly (SURVEY 8b vi)
@@ -224,9 +266,9 @@ class Offset(Template):
                 fdata = np.zeros((1, 1), dtype=np.uint8)
             K.template_offset_project_signal(
                 int(ob.detdata[self.det_data].indices([detector])[0]),
-                ob.detdata[self.det_data].data, fidx, fdata, self.det_flag_mask, step,
+                ob.detdata[self.det_data].data, fidx, fdata, fmask, step,
                 self._obs_amp_offset(detector, iob), self._obs_views[iob], amplitudes.local,
-                amplitudes.local_flags, ob.intervals[self.view], use_accel)
+                amplitudes.local_flags, ob.intervals[self._bounds_view], use_accel)
 
     def prior(self):
         """The device-resident noise prior (None without ``use_noise_prior``), for Destriper."""
