@@ -4,8 +4,9 @@ CPU restatement of the Offset template's noise prior and banded / Toeplitz preco
 (``templates/offset/offset.py:203-222,356-712,884-1010`` of the reference).  The reference runs
 these in Python on the host -- numpy + ``scipy.signal.convolve`` + ``scipy.linalg.cho_solve_banded``
 -- and raises NotImplementedError on an accelerator (``offset.py:888-891,964-967``); this module
-calls the same library routines in the same order, segment by segment, so it is the reference's
-algorithm verbatim up to variable names.
+restates that algorithm with the same library routines in the same order, segment by segment
+(each step cites the reference lines it follows), so that its results can be -- and are --
+bit-identical to the reference's.
 
 Parity status: PINNED.  ``tests/golden/make_golden_prior.py`` and
 ``tests/golden/make_golden_offset_init.py`` execute the reference's OWN method bodies from
