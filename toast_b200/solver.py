@@ -360,7 +360,14 @@ class Destriper:
         if mode == "auto":
             self._setup_pipeline(4)
             if self.pipeline:
-                self._tune_pipeline()
+                try:
+                    self._tune_pipeline()
+                except Exception as exc:  # noqa: BLE001  (e.g. graph capture refused)
+                    import warnings
+
+                    warnings.warn(f"chunk pipeline unavailable ({exc}); using the serial LHS")
+                    self.pipeline = False
+                    self._graphs = {}
         else:
             self._setup_pipeline(int(mode))
 
