@@ -295,6 +295,11 @@ int tb_lhs_pass1_chunk(const tb_obs *obs, const double *amplitudes, const uint8_
                        double *zmap, int64_t chunk, void *stream);
 int tb_lhs_pass2_chunk(const tb_obs *obs, const double *binned, double *amplitudes_out,
                        int64_t chunk, void *stream);
+/* EXPERIMENTAL (not yet validated on hardware): pass 2 for the amplitudes of the preceding
+ * tb_lhs_pass1 with covariance_apply (covariance.py:262-306, toast_map_cov.cpp:471-528) folded in:
+ * zmap is the RAW noise-weighted map of pass 1, cov the [n_pix,6] pixel covariance.  One GPU. */
+int tb_lhs_pass2_cov(const tb_obs *obs, const double *zmap, const double *cov,
+                     double *amplitudes_out, void *stream);
 /* RHS projection (SolverRHS, mapmaker_solve.py:107-229): out += F^T N^-1 (signal - P m). */
 int tb_rhs_project(const tb_obs *obs, const double *signal, const uint8_t *amp_flags,
                    const double *binned, double *amplitudes_out, int regen, void *stream);

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "tb_obs_set_pixel_chunks": (INT, [P, I64, P]),
     "tb_lhs_pass1_chunk": (INT, [P, P, P, P, I64, P]),
     "tb_lhs_pass2_chunk": (INT, [P, P, P, I64, P]),
+    "tb_lhs_pass2_cov": (INT, [P, P, P, P, P]),
     "tb_rhs_project": (INT, [P, P, P, P, P, INT, P]),
     "tb_bin_signal": (INT, [P, P, P, INT, P]),
     "tb_offset_prior_create": (P, [ct.POINTER(tb_offset_prior_desc)]),

@@ -353,6 +353,7 @@ class Destriper:
         # time it against the serial LHS on this node and keep the faster form), 0 (off) or K.
         # Measured on 2 GPUs: 1.46-1.54 ms against 1.69 ms per iteration with 4 chunks, slower
         # than serial with 8-16.
+        self.fuse_cov = _os.environ.get("TB_FUSE_COV", "0") == "1"
         self.pipeline = False
         self.pipe_tune_ms = None
         self._ctas_set = None
@@ -557,12 +558,24 @@ class Destriper:
                                           L.ptr(self.zmap), self.regen, None))
         if ev:
             ev[1].record()
+        reuse = self._sorted_passes() == 2
+        if self.fuse_cov and reuse and self.world == 1 and len(self.obs) == 1:
+            # EXPERIMENTAL (TB_FUSE_COV=1; not validated on hardware yet): the covariance
+            # product is formed inside pass 2, the stand-alone covariance pass disappears
+            amps_out.zero_()
+            if ev:
+                ev[2].record()
+            L.check(self.lib.tb_lhs_pass2_cov(self.obs[0].handle().h, L.ptr(self.zmap),
+                                              L.ptr(self.cov), L.ptr(amps_out), None))
+            if ev:
+                ev[3].record()
+                timers.append(ev)
+            return self._add_prior(amps_in, amps_out)
         self.reduce_and_apply_cov()
         amps_out.zero_()
         if ev:
             ev[2].record()
         # both passes pixel-sorted: pass 2 reuses the prescaled amplitudes of pass 1
-        reuse = self._sorted_passes() == 2
         for o in self.obs:
             L.check(self.lib.tb_lhs_pass2(o.handle().h, None if reuse else L.ptr(amps_in),
                                           L.ptr(self.amp_flags), L.ptr(self.zmap),
