@@ -258,6 +258,39 @@ class SymmPeerMap:
         L.check(self.lib.tb_peer_set_multimem(1 if self.use_multimem else 0))
         L.check(self.lib.tb_map_reduce_cov_range(self.h, pix_first, n_pix, L.ptr(cov), stream))
 
+    def reduce_cov_ce(self, cov_apply, pix_first=0, n_pix=None):
+        """EXPERIMENTAL (TB_REDUCE=ce; written without GPU access, not validated or timed yet):
+        the same reduction with the NVLink traffic on the COPY ENGINES instead of SMs, so that
+        it can overlap the LHS passes without competing for their L1/LSU and L2 bandwidth (the
+        SM-resident kernel runs at 45 % of its stand-alone rate when overlapped: DESIGN.md 5).
+        Runs on the current stream: barrier -> pull the peers' copies of my slice into staging
+        -> local sum + covariance (``cov_apply(pix_first, n_pix)`` on my slice) -> push the
+        finished slice into every peer's map -> barrier."""
+        n_pix = self.n_pix - pix_first if n_pix is None else n_pix
+        w, r = self.world, self.rank
+        per = ((n_pix // 256 + w - 1) // w) * 256
+        a = pix_first + min(r * per, n_pix)
+        b = pix_first + min((r + 1) * per, n_pix)
+        n = (b - a) * 3
+        if getattr(self, "_peer_tensors", None) is None:
+            total = self.n_pix * 3
+            self._peer_tensors = [self._hdl.get_buffer(q, (total,), torch.float64, 0)
+                                  for q in range(w)]
+            self._stage = torch.empty((max(w - 1, 1), ((self.n_pix // 256 + w - 1) // w) * 768),
+                                      dtype=torch.float64, device=self.tensor.device)
+        self._hdl.barrier(channel=0)   # every rank has finished pass 1 of this pixel range
+        others = [q for q in range(w) if q != r]
+        if n > 0:
+            own = self.tensor[a * 3:b * 3]
+            for k, q in enumerate(others):
+                self._stage[k, :n].copy_(self._peer_tensors[q][a * 3:b * 3], non_blocking=True)
+            for k in range(len(others)):
+                own.add_(self._stage[k, :n])
+            cov_apply(a, b - a)
+            for q in others:
+                self._peer_tensors[q][a * 3:b * 3].copy_(own, non_blocking=True)
+        self._hdl.barrier(channel=0)   # every rank's slice has landed everywhere
+
     def tune(self, cov, reps=3):
         """Measure the in-switch (multimem) and the P2P form of the kernel on this node and map
         size and keep the faster one (max over ranks, so every rank takes the same decision):
@@ -354,6 +387,9 @@ class Destriper:
         # Measured on 2 GPUs: 1.46-1.54 ms against 1.69 ms per iteration with 4 chunks, slower
         # than serial with 8-16.
         self.fuse_cov = _os.environ.get("TB_FUSE_COV", "0") == "1"
+        # EXPERIMENTAL: copy-engine form of the chunk reduction (needs the symmetric-memory map)
+        self.reduce_ce = (_os.environ.get("TB_REDUCE", "") == "ce"
+                          and isinstance(self.peer, SymmPeerMap))
         self.pipeline = False
         self.pipe_tune_ms = None
         self._ctas_set = None
@@ -408,6 +444,14 @@ class Destriper:
         self.pipeline = True
         self.use_graph = _os.environ.get("TB_GRAPH", "1") != "0"
         self._graphs = {}
+
+    def _cov_apply_range(self, pix_first, n_pix):
+        """zmap[pix_first : pix_first + n_pix] <- cov . zmap[...] on the CURRENT stream."""
+        if n_pix > 0:
+            L.check(self.lib.tb_cov_apply_diag(
+                1, n_pix, 3, self.cov.data_ptr() + pix_first * 48,
+                self.zmap.data_ptr() + pix_first * 24, L.TB_MEM_DEVICE,
+                torch.cuda.current_stream(self.device).cuda_stream))
 
     def _peer_ctas(self, n):
         if self.peer is not None and self._ctas_set != n:
@@ -491,9 +535,15 @@ class Destriper:
             self.ev_binned[c].record(main)
             self.comm_stream.wait_event(self.ev_binned[c])
             first = int(self.chunk_bounds[c])
-            timed(f"reduce[{c}]", self.comm_stream,
-                  lambda: self.peer.reduce_cov(self.cov, first,
-                                               int(self.chunk_bounds[c + 1]) - first, cs))
+            count = int(self.chunk_bounds[c + 1]) - first
+            if self.reduce_ce:
+                def ce(first=first, count=count):
+                    with torch.cuda.stream(self.comm_stream):
+                        self.peer.reduce_cov_ce(self._cov_apply_range, first, count)
+                timed(f"reduce[{c}]", self.comm_stream, ce)
+            else:
+                timed(f"reduce[{c}]", self.comm_stream,
+                      lambda: self.peer.reduce_cov(self.cov, first, count, cs))
             self.ev_reduced[c].record(self.comm_stream)
         for c in range(self.n_chunks):
             main.wait_event(self.ev_reduced[c])
