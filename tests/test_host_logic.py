@@ -133,3 +133,37 @@ def test_operator_mirror_has_reference_names_and_traits():
     assert t._step_length(10.0, 10.0) == 100
     with pytest.raises(RuntimeError):
         ops.MapMaker(name="mm").apply(data)      # binning / template_matrix traits missing
+
+
+def test_pointing_detector_fp():
+    """ops/pointing_detector_fp.py:82-121: every sample of a detector gets its
+    focalplane quaternion; existing quats are left alone; ignored traits only warn; the operator
+    is host-only (no accelerator support), as in the reference."""
+    import warnings
+
+    from toast_b200 import ops
+
+    obs = S.make_observation("c1", n_det=4, n_samp=500, nside=64)
+    data = Data()
+    ob = observation_from_synthetic(obs)
+    data.obs.append(ob)
+    op = ops.PointingDetectorFP(quats="quats_fp")
+    assert not op.supports_accel()
+    assert op.provides() == {"meta": [], "shared": [], "detdata": ["quats_fp"]}
+    assert op.requires() == {"meta": [], "shared": [], "detdata": [], "intervals": []}
+    dets = ob.local_detectors[1:3]
+    op.apply(data, detectors=dets)
+    q = ob.detdata["quats_fp"]
+    assert q.detectors == dets and q.data.shape == (2, 500, 4)
+    for i, d in enumerate(dets):
+        np.testing.assert_array_equal(q.data[i], np.tile(obs["focalplane"][i + 1], (500, 1)))
+    q.data[:] = 7.0
+    op.apply(data, detectors=dets)        # exists for these detectors: skipped
+    assert np.all(q.data == 7.0)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ops.PointingDetectorFP(quats="q2", boresight="boresight_radec", coord_in="C").apply(data)
+    assert len(w) == 2 and "will not use" in str(w[0].message)
+    assert ob.detdata["q2"].data.shape == (4, 500, 4)
+    with pytest.raises(AttributeError):
+        ops.PointingDetectorFP(nside=64)

@@ -2,7 +2,12 @@
 reference's operator names and trait (keyword) names."""
 
 from .operator import Operator, Pipeline  # noqa: F401
-from .pointing import PointingDetectorSimple, PixelsHealpix, StokesWeights  # noqa: F401
+from .pointing import (  # noqa: F401
+    PixelsHealpix,
+    PointingDetectorFP,
+    PointingDetectorSimple,
+    StokesWeights,
+)
 from .mapmaker_utils import (  # noqa: F401
     BinMap,
     BuildHitMap,

@@ -47,6 +47,46 @@ class PointingDetectorSimple(Operator):
         return {"detdata": [self.quats]}
 
 
+class PointingDetectorFP(Operator):
+    """``ops/pointing_detector_fp.py:14-139``: detector pointing in the focalplane frame -- every
+    sample of a detector gets its focalplane quaternion (boresight constantly at the zenith).
+    Host-only in the reference too (it has no kernel and no accelerator support); same traits,
+    ``boresight`` / ``coord_in`` / ``coord_out`` accepted and ignored as there."""
+
+    _defaults = dict(view=None, shared_flags="flags", shared_flag_mask=1, det_mask=1,
+                     boresight=None, quats="quats", coord_in=None, coord_out=None,
+                     focalplane_key="focalplane")
+
+    def _exec(self, data, detectors=None, use_accel=False, **kwargs):
+        import warnings
+
+        for trait in ("boresight", "coord_in", "coord_out"):
+            if getattr(self, trait) is not None:
+                warnings.warn(f"PointingDetectorFP will not use the provided {trait} = "
+                              f"{getattr(self, trait)}")  # pointing_detector_fp.py:86-93
+        for ob in data.obs:
+            dets = ob.select_local_detectors(detectors, flagmask=self.det_mask)
+            if len(dets) == 0:
+                continue
+            exists = ob.detdata.ensure(self.quats, sample_shape=(4,), dtype=np.float64,
+                                       detectors=dets)
+            if exists:
+                continue  # pointing_detector_fp.py:104-111
+            fp = ob[self.focalplane_key]
+            qd = ob.detdata[self.quats]
+            for det in dets:
+                qd[det] = np.asarray(fp[det]["quat"], dtype=np.float64)
+
+    def supports_accel(self):
+        return False
+
+    def _requires(self):
+        return {"meta": [], "shared": [], "detdata": [], "intervals": []}
+
+    def _provides(self):
+        return {"meta": [], "shared": [], "detdata": [self.quats]}
+
+
 class PixelsHealpix(Operator):
     _defaults = dict(detector_pointing=None, nside=64, nside_submap=16, nest=True, view=None,
                      pixels="pixels", create_dist=None, single_precision=False)
