@@ -300,8 +300,8 @@ def test_off_map_samples_keep_the_time_ordered_pass2():
                            "TB_TEST_EXPERIMENTAL=1 to validate it")
 @pytest.mark.parametrize("eps_max", [0.0, 0.03])
 def test_experimental_pass2_with_fused_covariance(eps_max):
-    """tb_lhs_pass2_cov (covariance product folded into the pixel-ordered pass 2) against the
-    shipped LHS and the oracle."""
+    """tb_lhs_pass2_cov (covariance product folded into the pixel-ordered pass 2) and the
+    prefetch variants against the shipped LHS and the oracle."""
     ck = H.checker()
     obs = S.make_observation("c4", n_det=6, n_samp=30000, eps_max=eps_max, nside=128)
     pb = O.build_problem(obs, ck, rcond_threshold=1e-5)
@@ -316,6 +316,16 @@ def test_experimental_pass2_with_fused_covariance(eps_max):
     ds.lhs(a_d, q1)
     assert_close_norm(q1.cpu().numpy(), ref, what="LHS (fused covariance)")
     assert_close_norm(q1.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="fused vs shipped")
+    # the L2-prefetch variants of both pixel-ordered passes (option "prefetch")
+    lib = L.load()
+    ds.fuse_cov = False
+    q2 = torch.zeros_like(a_d)
+    try:
+        L.check(lib.tb_set_option(b"prefetch", 1))
+        ds.lhs(a_d, q2)
+    finally:
+        lib.tb_set_option(b"prefetch", 0)
+    assert_close_norm(q2.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="prefetch vs shipped")
 
 
 def test_full_size_properties_c4_shard():

@@ -1123,12 +1123,29 @@ k_xs_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
 #ifndef TB_XS_CTAS
 #define TB_XS_CTAS 8
 #endif
-template <bool UNIFORM, bool PAIRED>
+// PF (EXPERIMENTAL, tb_set_option("prefetch", 1), not validated or timed on hardware yet): both
+// pixel-ordered passes are latency-bound on record load -> gather (profiles/README.md); PF = 1
+// asks the L2 for the records of the later loop iterations before the first one is processed.
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <bool UNIFORM, bool PAIRED, int PF = 0>
 __global__ void __launch_bounds__(kThreads, TB_XS_CTAS)
 k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
          int64_t n_srec, const double *__restrict__ dscaled, double4 cst,
          const double4 *__restrict__ table, double *__restrict__ zmap) {
     const int lane = threadIdx.x & 31;
+    if (PF) {
+#pragma unroll
+        for (int k = 2; k < kXPer; ++k) {
+            const int64_t j = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
+            if (j < n_srec) {
+                prefetch_l2(srec + j);
+                prefetch_l2(squ + j);
+            }
+        }
+    }
 #pragma unroll 2
     for (int k = 0; k < kXPer; ++k) {
         const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
@@ -1173,6 +1190,7 @@ k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t
 }
 
 int g_use_xs = 1; // tb_set_option("sorted", 0/1)
+int g_use_prefetch = 0; // tb_set_option("prefetch", 0/1): EXPERIMENTAL, see prefetch_l2
 
 // Pass 2 on the same pixel-sorted list: the binned map is read SEQUENTIALLY (every pixel once,
 // adjacent records share the load) instead of one cold 24-byte gather per crossing, and the
@@ -1182,13 +1200,23 @@ int g_use_xs = 1; // tb_set_option("sorted", 0/1)
 #ifndef TB_XS2_CTAS
 #define TB_XS2_CTAS 6
 #endif
-template <bool UNIFORM, bool PAIRED>
+template <bool UNIFORM, bool PAIRED, int PF = 0>
 __global__ void __launch_bounds__(kThreads, TB_XS2_CTAS)
 k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
           int64_t rec_end, const double *__restrict__ dscaled, int32_t delta, double4 cst,
           const double4 *__restrict__ table, const double *__restrict__ det_scale,
           const int64_t *__restrict__ amp_offsets, int n_det,
           const double *__restrict__ binned, double *__restrict__ out) {
+    if (PF) {
+#pragma unroll
+        for (int k = 2; k < kXPer; ++k) {
+            const int64_t j = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
+            if (j < rec_end) {
+                prefetch_l2(srec + j);
+                prefetch_l2(squ + j);
+            }
+        }
+    }
 #pragma unroll 2
     for (int k = 0; k < kXPer; ++k) {
         const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
@@ -1563,6 +1591,12 @@ void launch_bin_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_end, 
                          void *stream) {
     int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
     double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    if (g_use_prefetch) {
+        auto k = k_bin_xs<UNIFORM, PAIRED, 1>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
+                   obs->stable, zmap);
+        return;
+    }
     auto k = k_bin_xs<UNIFORM, PAIRED>;
     TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
                obs->stable, zmap);
@@ -1584,6 +1618,13 @@ void launch_project_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_e
                              const double *binned, double *out, void *stream) {
     int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
     double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    if (g_use_prefetch) {
+        auto k = k_proj_xs<UNIFORM, PAIRED, 1>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
+                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
+                   (int)obs->d.n_det, binned, out);
+        return;
+    }
     auto k = k_proj_xs<UNIFORM, PAIRED>;
     TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
                (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
@@ -2221,6 +2262,7 @@ int tb_get_option(const char *name) {
     if (n == "sorted") return g_use_xs;
     if (n == "sorted2") return g_use_xs2;
     if (n == "peer_ctas") return tb_peer_ctas_per_sm;
+    if (n == "prefetch") return g_use_prefetch;
     return -1;
 }
 
@@ -2241,6 +2283,8 @@ int tb_set_option(const char *name, int value) {
         g_use_xs = value;
     } else if (std::string(name) == "sorted2") {
         g_use_xs2 = value;
+    } else if (std::string(name) == "prefetch") {
+        g_use_prefetch = value;
     } else if (std::string(name) == "peer_ctas") {
         TB_REQUIRE(value >= 1 && value <= 16, "peer_ctas must be in [1, 16]");
         tb_peer_ctas_per_sm = value;
