@@ -34,6 +34,7 @@ if [ "$N" = "1" ]; then
   tail -5 $OUT/pytest_exp_$TAG.log
   bench shipped X=1
   bench prefetch TB_OPTIONS=prefetch=1
+  bench unroll4 TB_OPTIONS=prefetch=2
   bench fusecov TB_FUSE_COV=1
   bench fusecov_prefetch TB_FUSE_COV=1 TB_OPTIONS=prefetch=1
 else

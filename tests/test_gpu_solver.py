@@ -319,13 +319,15 @@ def test_experimental_pass2_with_fused_covariance(eps_max):
     # the L2-prefetch variants of both pixel-ordered passes (option "prefetch")
     lib = L.load()
     ds.fuse_cov = False
-    q2 = torch.zeros_like(a_d)
-    try:
-        L.check(lib.tb_set_option(b"prefetch", 1))
-        ds.lhs(a_d, q2)
-    finally:
-        lib.tb_set_option(b"prefetch", 0)
-    assert_close_norm(q2.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="prefetch vs shipped")
+    for mode in (1, 2):   # 1: L2 prefetch of the later records; 2: all four iterations in flight
+        q2 = torch.zeros_like(a_d)
+        try:
+            L.check(lib.tb_set_option(b"prefetch", mode))
+            ds.lhs(a_d, q2)
+        finally:
+            lib.tb_set_option(b"prefetch", 0)
+        assert_close_norm(q2.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12,
+                          what=f"prefetch={mode} vs shipped")
 
 
 def test_full_size_properties_c4_shard():

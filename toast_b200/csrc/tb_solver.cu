@@ -1130,13 +1130,15 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// PF = 2 (EXPERIMENTAL as well): all four loop iterations in flight at once (unroll 4) with the
+// register budget of 4 CTAs per SM instead of 8.
 template <bool UNIFORM, bool PAIRED, int PF = 0>
-__global__ void __launch_bounds__(kThreads, TB_XS_CTAS)
+__global__ void __launch_bounds__(kThreads, PF == 2 ? 4 : TB_XS_CTAS)
 k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
          int64_t n_srec, const double *__restrict__ dscaled, double4 cst,
          const double4 *__restrict__ table, double *__restrict__ zmap) {
     const int lane = threadIdx.x & 31;
-    if (PF) {
+    if (PF == 1) {
 #pragma unroll
         for (int k = 2; k < kXPer; ++k) {
             const int64_t j = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
@@ -1146,7 +1148,7 @@ k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t
             }
         }
     }
-#pragma unroll 2
+#pragma unroll(PF == 2 ? 4 : 2)
     for (int k = 0; k < kXPer; ++k) {
         const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
         int64_t key = -1;
@@ -1190,7 +1192,7 @@ k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t
 }
 
 int g_use_xs = 1; // tb_set_option("sorted", 0/1)
-int g_use_prefetch = 0; // tb_set_option("prefetch", 0/1): EXPERIMENTAL, see prefetch_l2
+int g_use_prefetch = 0; // tb_set_option("prefetch", 0/1/2): EXPERIMENTAL, see prefetch_l2
 
 // Pass 2 on the same pixel-sorted list: the binned map is read SEQUENTIALLY (every pixel once,
 // adjacent records share the load) instead of one cold 24-byte gather per crossing, and the
@@ -1201,13 +1203,13 @@ int g_use_prefetch = 0; // tb_set_option("prefetch", 0/1): EXPERIMENTAL, see pre
 #define TB_XS2_CTAS 6
 #endif
 template <bool UNIFORM, bool PAIRED, int PF = 0>
-__global__ void __launch_bounds__(kThreads, TB_XS2_CTAS)
+__global__ void __launch_bounds__(kThreads, PF == 2 ? 4 : TB_XS2_CTAS)
 k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
           int64_t rec_end, const double *__restrict__ dscaled, int32_t delta, double4 cst,
           const double4 *__restrict__ table, const double *__restrict__ det_scale,
           const int64_t *__restrict__ amp_offsets, int n_det,
           const double *__restrict__ binned, double *__restrict__ out) {
-    if (PF) {
+    if (PF == 1) {
 #pragma unroll
         for (int k = 2; k < kXPer; ++k) {
             const int64_t j = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
@@ -1217,7 +1219,7 @@ k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_
             }
         }
     }
-#pragma unroll 2
+#pragma unroll(PF == 2 ? 4 : 2)
     for (int k = 0; k < kXPer; ++k) {
         const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
         if (i >= rec_end) continue;
@@ -1591,6 +1593,12 @@ void launch_bin_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_end, 
                          void *stream) {
     int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
     double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    if (g_use_prefetch == 2) {
+        auto k = k_bin_xs<UNIFORM, PAIRED, 2>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
+                   obs->stable, zmap);
+        return;
+    }
     if (g_use_prefetch) {
         auto k = k_bin_xs<UNIFORM, PAIRED, 1>;
         TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
@@ -1618,6 +1626,13 @@ void launch_project_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_e
                              const double *binned, double *out, void *stream) {
     int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
     double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    if (g_use_prefetch == 2) {
+        auto k = k_proj_xs<UNIFORM, PAIRED, 2>;
+        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
+                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
+                   (int)obs->d.n_det, binned, out);
+        return;
+    }
     if (g_use_prefetch) {
         auto k = k_proj_xs<UNIFORM, PAIRED, 1>;
         TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
