@@ -300,6 +300,13 @@ int tb_lhs_pass2_chunk(const tb_obs *obs, const double *binned, double *amplitud
  * zmap is the RAW noise-weighted map of pass 1, cov the [n_pix,6] pixel covariance.  One GPU. */
 int tb_lhs_pass2_cov(const tb_obs *obs, const double *zmap, const double *cov,
                      double *amplitudes_out, void *stream);
+/* EXPERIMENTAL (not yet validated on hardware): the covariance product written to a padded copy
+ * of the map (binned4: [n_pix,4] doubles = I, Q, U, 0; 32-byte aligned) and the time-ordered
+ * crossing-list pass 2 that gathers one 32-byte sector per crossing from it.  One GPU. */
+int tb_cov_apply_pad(int64_t n_pix, const double *cov, const double *zmap, double *binned4,
+                     void *stream);
+int tb_lhs_pass2_pad(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                     const double *binned4, double *amplitudes_out, void *stream);
 /* RHS projection (SolverRHS, mapmaker_solve.py:107-229): out += F^T N^-1 (signal - P m). */
 int tb_rhs_project(const tb_obs *obs, const double *signal, const uint8_t *amp_flags,
                    const double *binned, double *amplitudes_out, int regen, void *stream);

@@ -36,6 +36,8 @@ if [ "$N" = "1" ]; then
   bench prefetch TB_OPTIONS=prefetch=1
   bench unroll4 TB_OPTIONS=prefetch=2
   bench fusecov TB_FUSE_COV=1
+  bench padmap TB_PADMAP=1
+  bench padmap_prefetch TB_PADMAP=1 TB_OPTIONS=prefetch=1
   bench fusecov_prefetch TB_FUSE_COV=1 TB_OPTIONS=prefetch=1
 else
   bench auto X=1

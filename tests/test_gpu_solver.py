@@ -316,6 +316,14 @@ def test_experimental_pass2_with_fused_covariance(eps_max):
     ds.lhs(a_d, q1)
     assert_close_norm(q1.cpu().numpy(), ref, what="LHS (fused covariance)")
     assert_close_norm(q1.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="fused vs shipped")
+    # covariance product into a padded map + time-ordered pass 2 gathering from it
+    ds.fuse_cov = False
+    ds.pad_map = True
+    q3 = torch.zeros_like(a_d)
+    ds.lhs(a_d, q3)
+    ds.pad_map = False
+    assert_close_norm(q3.cpu().numpy(), ref, what="LHS (padded map)")
+    assert_close_norm(q3.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="padded vs shipped")
     # the L2-prefetch variants of both pixel-ordered passes (option "prefetch")
     lib = L.load()
     ds.fuse_cov = False

@@ -1349,7 +1349,11 @@ k_proj_xs_cov(const int4 *__restrict__ srec, const double2 *__restrict__ squ, in
 #ifndef TB_X_CTAS
 #define TB_X_CTAS 8
 #endif
-template <bool PASS2>
+// PAD (EXPERIMENTAL, pass 2 only, Destriper TB_PADMAP=1, not validated or timed on hardware yet):
+// `binned` holds FOUR doubles per pixel (I, Q, U, 0), 32-byte aligned, so that the cold map gather
+// of a crossing is exactly one sector instead of the 1.75 a 24-byte pixel straddles on average
+// (2.0 of the 3.3 GB this kernel reads from DRAM are those gathers: profiles/README.md).
+template <bool PASS2, bool PAD = false>
 __global__ void __launch_bounds__(kThreads, TB_X_CTAS)
 k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ aflags,
         const double *__restrict__ binned, double *__restrict__ out) {
@@ -1408,10 +1412,18 @@ k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ a
                 bool have = false;
                 double v0 = n * tod0, v1 = n * tod1;
                 if (need0 && lp0 >= 0) {
-                    const double *m = binned + 3 * (int64_t)lp0;
-                    m0 = __ldg(m);
-                    m1 = __ldg(m + 1);
-                    m2 = __ldg(m + 2);
+                    if (PAD) {
+                        const double2 *m = reinterpret_cast<const double2 *>(binned) + 2 * (int64_t)lp0;
+                        const double2 ma = __ldg(m), mb = __ldg(m + 1);
+                        m0 = ma.x;
+                        m1 = ma.y;
+                        m2 = mb.x;
+                    } else {
+                        const double *m = binned + 3 * (int64_t)lp0;
+                        m0 = __ldg(m);
+                        m1 = __ldg(m + 1);
+                        m2 = __ldg(m + 2);
+                    }
                     have = true;
                     double sc = 0.0;
                     sc += (c0 * n) * m0;
@@ -1421,10 +1433,18 @@ k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ a
                 }
                 if (need1 && lp1 >= 0) {
                     if (!(have && lp1 == lp0)) {
-                        const double *m = binned + 3 * (int64_t)lp1;
-                        m0 = __ldg(m);
-                        m1 = __ldg(m + 1);
-                        m2 = __ldg(m + 2);
+                        if (PAD) {
+                            const double2 *m = reinterpret_cast<const double2 *>(binned) + 2 * (int64_t)lp1;
+                            const double2 ma = __ldg(m), mb = __ldg(m + 1);
+                            m0 = ma.x;
+                            m1 = ma.y;
+                            m2 = mb.x;
+                        } else {
+                            const double *m = binned + 3 * (int64_t)lp1;
+                            m0 = __ldg(m);
+                            m1 = __ldg(m + 1);
+                            m2 = __ldg(m + 2);
+                        }
                     }
                     double sc = 0.0;
                     sc += (c1 * n) * m0;
@@ -1479,6 +1499,32 @@ __global__ void k_xs_lower_bound(const int4 *__restrict__ srec, int64_t n_srec,
     }
     rec[c] = lo;
 }
+
+// EXPERIMENTAL (see k_lhs_x PAD): binned4[p] = (C z[p], 0) -- k_cov_apply's arithmetic
+// (toast_map_cov.cpp:509-517 order) written to a padded copy instead of in place.
+__global__ void __launch_bounds__(kThreads)
+k_cov_apply_pad(int64_t npix, const double *__restrict__ cov, const double *__restrict__ z,
+                double *__restrict__ out4) {
+    int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (p >= npix) return;
+    const double *m = cov + p * 6;
+    const double v0 = z[3 * p], v1 = z[3 * p + 1], v2 = z[3 * p + 2];
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    t0 += m[0] * v0;
+    t0 += m[1] * v1;
+    t1 += m[1] * v0;
+    t0 += m[2] * v2;
+    t2 += m[2] * v0;
+    t1 += m[3] * v1;
+    t1 += m[4] * v2;
+    t2 += m[4] * v1;
+    t2 += m[5] * v2;
+    double2 *o = reinterpret_cast<double2 *>(out4) + 2 * p;
+    o[0] = make_double2(t0, t1);
+    o[1] = make_double2(t2, 0.0);
+}
+
+
 
 ObsDev make_dev(const tb_obs *obs, int regen) {
     const tb_obs_desc &d = obs->d;
@@ -2384,6 +2430,32 @@ int tb_lhs_pass2_chunk(const tb_obs *obs, const double *binned, double *amplitud
     TB_REQUIRE(chunk >= 0 && chunk + 1 < (int64_t)obs->chunk_rec.size(), "bad chunk index");
     launch_project_sorted(obs, obs->chunk_rec[chunk], obs->chunk_rec[chunk + 1], binned,
                           amplitudes_out, stream);
+    TB_API_END
+}
+
+// EXPERIMENTAL (see k_lhs_x PAD): covariance product into a padded (4 doubles per pixel) copy of
+// the map, and the time-ordered crossing-list pass 2 gathering from it.  One GPU.
+int tb_cov_apply_pad(int64_t n_pix, const double *cov, const double *zmap, double *binned4,
+                     void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(cov && zmap && binned4 && n_pix >= 0, "bad argument");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(binned4) & 31u) == 0, "binned4 must be 32-byte aligned");
+    int64_t nb = (n_pix + kThreads - 1) / kThreads;
+    TBS_LAUNCH(k_cov_apply_pad, nb, stream, n_pix, cov, zmap, binned4);
+    TB_API_END
+}
+
+int tb_lhs_pass2_pad(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                     const double *binned4, double *amplitudes_out, void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs && amplitudes && amp_flags && binned4 && amplitudes_out, "NULL argument");
+    TB_REQUIRE(g_use_compact && g_use_x && obs->xrec != nullptr,
+               "tb_lhs_pass2_pad needs the crossing list");
+    ObsDev o = make_dev(obs, 0);
+    auto k = k_lhs_x<true, true>;
+    TBS_LAUNCH(k, obs->n_xblocks, stream, o, amplitudes, amp_flags, binned4, amplitudes_out);
     TB_API_END
 }
 

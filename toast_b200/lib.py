@@ -116,6 +116,8 @@ PROTOTYPES = {
     "tb_lhs_pass1_chunk": (INT, [P, P, P, P, I64, P]),
     "tb_lhs_pass2_chunk": (INT, [P, P, P, I64, P]),
     "tb_lhs_pass2_cov": (INT, [P, P, P, P, P]),
+    "tb_cov_apply_pad": (INT, [I64, P, P, P, P]),
+    "tb_lhs_pass2_pad": (INT, [P, P, P, P, P, P]),
     "tb_rhs_project": (INT, [P, P, P, P, P, INT, P]),
     "tb_bin_signal": (INT, [P, P, P, INT, P]),
     "tb_offset_prior_create": (P, [ct.POINTER(tb_offset_prior_desc)]),

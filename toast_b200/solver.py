@@ -387,6 +387,8 @@ class Destriper:
         # Measured on 2 GPUs: 1.46-1.54 ms against 1.69 ms per iteration with 4 chunks, slower
         # than serial with 8-16.
         self.fuse_cov = _os.environ.get("TB_FUSE_COV", "0") == "1"
+        self.pad_map = _os.environ.get("TB_PADMAP", "0") == "1"
+        self._binned4 = None
         # EXPERIMENTAL: copy-engine form of the chunk reduction (needs the symmetric-memory map)
         self.reduce_ce = (_os.environ.get("TB_REDUCE", "") == "ce"
                           and isinstance(self.peer, SymmPeerMap))
@@ -617,6 +619,27 @@ class Destriper:
                 ev[2].record()
             L.check(self.lib.tb_lhs_pass2_cov(self.obs[0].handle().h, L.ptr(self.zmap),
                                               L.ptr(self.cov), L.ptr(amps_out), None))
+            if ev:
+                ev[3].record()
+                timers.append(ev)
+            return self._add_prior(amps_in, amps_out)
+        if self.pad_map and self.world == 1 and len(self.obs) == 1 and not self.regen and \
+                self.obs[0].has_compact_pointing():
+            # EXPERIMENTAL (TB_PADMAP=1; not validated on hardware yet): covariance product into
+            # a 32-byte-per-pixel copy of the map, time-ordered pass 2 gathering one sector per
+            # crossing from it
+            if self._binned4 is None:
+                self._binned4 = torch.zeros(self.n_local_submap * self.n_pix_submap * 4,
+                                            dtype=torch.float64, device=self.device)
+            L.check(self.lib.tb_cov_apply_pad(self.n_local_submap * self.n_pix_submap,
+                                              L.ptr(self.cov), L.ptr(self.zmap),
+                                              L.ptr(self._binned4), None))
+            amps_out.zero_()
+            if ev:
+                ev[2].record()
+            L.check(self.lib.tb_lhs_pass2_pad(self.obs[0].handle().h, L.ptr(amps_in),
+                                              L.ptr(self.amp_flags), L.ptr(self._binned4),
+                                              L.ptr(amps_out), None))
             if ev:
                 ev[3].record()
                 timers.append(ev)
