@@ -88,3 +88,71 @@ void tbp_banded_segments(int64_t n_seg, const int64_t *seg_start, const int64_t 
     }
 }
 }
+
+// ---- partitioned banded solve (tb_prior.cuh), looped the way the device kernels would ----------
+#include <vector>
+
+extern "C" {
+
+// one segment: factor ab [w, n], chunk size m >= w - 1, right-hand side b -> x
+void tbp_banded_partitioned(const double *ab, int64_t w, int64_t n, int64_t m, const double *b,
+                            double *x) {
+    const int64_t q = w - 1;
+    const int64_t P = (n + m - 1) / m;
+    std::vector<double> Gf((size_t)(n * q), 0.0), Gb((size_t)(n * q), 0.0);
+    // set-up (once per factor): responses of every chunk
+    for (int64_t p = 0; p < P; ++p) {
+        const int64_t s = p * m, e = (s + m < n) ? s + m : n;
+        if (p > 0) tbp::fwd_response(ab, w, n, s, e, Gf.data() + s * q);
+        if (p + 1 < P) tbp::bwd_response(ab, w, n, s, e, Gb.data() + s * q);
+    }
+    std::vector<double> t((size_t)(P * (q > 0 ? q : 1)), 0.0);
+    // K1: chunk-local forward solves (parallel over chunks)
+    for (int64_t p = 0; p < P; ++p) {
+        const int64_t s = p * m, e = (s + m < n) ? s + m : n;
+        tbp::fwd_chunk(ab, w, n, s, e, b, x);
+    }
+    // K2: tails, sequential over chunks; t[p] = y[e_p - q : e_p]
+    for (int64_t p = 0; p + 1 < P; ++p) {
+        const int64_t s = p * m, e = s + m;
+        for (int64_t c = 0; c < q; ++c) {
+            const int64_t j = e - q + c;
+            t[p * q + c] = (p == 0) ? x[j]
+                                    : tbp::chunk_correct(Gf.data() + s * q, w, s, j, x[j],
+                                                         t.data() + (p - 1) * q);
+        }
+    }
+    // K3: correction (parallel over rows)
+    for (int64_t p = 1; p < P; ++p) {
+        const int64_t s = p * m, e = (s + m < n) ? s + m : n;
+        for (int64_t j = s; j < e; ++j)
+            x[j] = tbp::chunk_correct(Gf.data() + s * q, w, s, j, x[j], t.data() + (p - 1) * q);
+    }
+    // K4: chunk-local back solves
+    for (int64_t p = 0; p < P; ++p) {
+        const int64_t s = p * m, e = (s + m < n) ? s + m : n;
+        tbp::bwd_chunk(ab, w, n, s, e, x, x);
+    }
+    // K5: heads, sequential from the last chunk; h[p] = x[s_p : s_p + q] (rows >= n are zero)
+    std::vector<double> h((size_t)(P * (q > 0 ? q : 1)), 0.0);
+    for (int64_t p = P - 1; p >= 1; --p) {
+        const int64_t s = p * m, e = (s + m < n) ? s + m : n;
+        for (int64_t c = 0; c < q; ++c) {
+            const int64_t j = s + c;
+            if (j >= e) {
+                h[p * q + c] = 0.0;
+                continue;
+            }
+            h[p * q + c] = (p == P - 1) ? x[j]
+                                        : tbp::chunk_correct(Gb.data() + s * q, w, s, j, x[j],
+                                                             h.data() + (p + 1) * q);
+        }
+    }
+    // K6: correction
+    for (int64_t p = 0; p + 1 < P; ++p) {
+        const int64_t s = p * m, e = s + m;
+        for (int64_t j = s; j < e; ++j)
+            x[j] = tbp::chunk_correct(Gb.data() + s * q, w, s, j, x[j], h.data() + (p + 1) * q);
+    }
+}
+}
