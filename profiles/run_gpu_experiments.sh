@@ -29,8 +29,9 @@ except Exception as e:
 PY
 }
 if [ "$N" = "1" ]; then
-  TB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_solver.py -m gpu -q \
-      -k experimental --timeout 120 > $OUT/pytest_exp_$TAG.log 2>&1
+  TB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_solver.py \
+      tests/test_gpu_prior.py -m gpu -q -k experimental --timeout 120 \
+      > $OUT/pytest_exp_$TAG.log 2>&1
   tail -5 $OUT/pytest_exp_$TAG.log
   bench shipped X=1
   bench prefetch TB_OPTIONS=prefetch=1

@@ -156,3 +156,41 @@ void tbp_banded_partitioned(const double *ab, int64_t w, int64_t n, int64_t m, c
     }
 }
 }
+
+// ---- the partitioned solve exactly as tb_prior.cu launches it: tables + six per-thread loops ----
+extern "C" {
+void tbp_banded_partitioned_segments(int64_t n_seg, const int64_t *seg_start,
+                                     const int64_t *seg_len, const int64_t *p_start,
+                                     const int64_t *p_width, const double *factors, int64_t chunk,
+                                     const double *in, const uint8_t *flags, double *out) {
+    tbp::PartTables T;
+    tbp::build_part_tables(n_seg, seg_len, p_start, p_width, factors, chunk, T);
+    std::vector<double> tails((size_t)(T.n_chunk * T.qmax + 1), 0.0);
+    std::vector<double> heads((size_t)(T.n_chunk * T.qmax + 1), 0.0);
+    tbp::PartView v;
+    v.n_seg = n_seg;
+    v.n_chunk = T.n_chunk;
+    v.qmax = T.qmax;
+    v.seg_start = seg_start;
+    v.seg_len = seg_len;
+    v.p_start = p_start;
+    v.p_width = p_width;
+    v.factors = factors;
+    v.seg_chunk0 = T.seg_chunk0.data();
+    v.seg_m = T.seg_m.data();
+    v.chunk_seg = T.chunk_seg.data();
+    v.g_off = T.g_off.data();
+    v.Gf = T.Gf.data();
+    v.Gb = T.Gb.data();
+    v.tails = tails.data();
+    v.heads = heads.data();
+    for (int64_t g = 0; g < T.n_chunk; ++g) tbp::pb_fwd_local(v, g, in, out);
+    for (int64_t s = 0; s < n_seg; ++s) tbp::pb_tails(v, s, out);
+    for (int64_t s = 0; s < n_seg; ++s)
+        for (int64_t j = 0; j < seg_len[s]; ++j) tbp::pb_fwd_correct(v, s, j, out);
+    for (int64_t g = 0; g < T.n_chunk; ++g) tbp::pb_bwd_local(v, g, out);
+    for (int64_t s = 0; s < n_seg; ++s) tbp::pb_heads(v, s, out);
+    for (int64_t s = 0; s < n_seg; ++s)
+        for (int64_t j = 0; j < seg_len[s]; ++j) tbp::pb_bwd_correct(v, s, j, flags, out);
+}
+}

@@ -203,3 +203,32 @@ def test_offset_template_with_noise_prior(precond_width, det_flags, name, n_samp
             amp.accel_delete()
     assert_close_norm(out.local, ref_add, rtol=1e-12, what="Offset.add_prior")
     assert_close_norm(pre.local, ref_pre, rtol=1e-12, what="Offset.apply_precond")
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TB_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="experimental kernels written without GPU access: run with "
+                           "TB_TEST_EXPERIMENTAL=1 to validate them")
+@pytest.mark.parametrize("chunk", [8, 64, 256])
+def test_experimental_partitioned_banded_solve(chunk):
+    """The six-launch partitioned form of the banded preconditioner (option prior_chunk; its
+    per-thread code is checked on the host in tests/test_offset_prior.py) against the oracle."""
+    from toast_b200 import lib as L
+
+    lib = L.load()
+    case = make_case(20, n_amp_views=(120, 37, 700, 5), n_det=4)
+    try:
+        L.check(lib.tb_set_option(b"prior_chunk", chunk))
+        prior = build_product(case, cut=(2,)).finish()
+    finally:
+        lib.tb_set_option(b"prior_chunk", 0)
+    n, per = case["n_amp"], case["per"]
+    rng = np.random.default_rng(8)
+    a_in = rng.standard_normal(n)
+    flags = (rng.random(n) < 0.1).astype(np.uint8)
+    ref = np.zeros(n)
+    OP.apply_precond(case["prior"], a_in, flags, ref)
+    ref[2 * per:3 * per] = 0.0
+    pre = np.full(n, 7.0)
+    prior.precond(a_in, flags, pre)
+    assert_close_norm(pre, ref, rtol=1e-12, what=f"partitioned precond (chunk {chunk})")
+    assert np.all(pre[flags != 0] == 0.0)

@@ -367,3 +367,32 @@ def test_partitioned_banded_solve_matches_the_sequential_one(n, w, m):
     hm.tbp_banded_partitioned(_ptr(cbc), ct.c_int64(w), ct.c_int64(n), ct.c_int64(m), _ptr(b),
                               _ptr(x))
     H.assert_close_norm(x, ref, rtol=1e-12, what=f"partitioned solve n={n} w={w} m={m}")
+
+
+@pytest.mark.parametrize("chunk", [8, 19, 64, 1000])
+def test_partitioned_segments_match_the_reference_preconditioner(chunk):
+    """The per-thread functions of the partitioned solve (pb_* in tb_prior.cuh), run over all
+    segments in the order of the six launches, against Offset._apply_precond on the banded
+    cases: different widths, views shorter than the band, a cut detector, flagged amplitudes."""
+    hm = H.host_math_lib()
+    for pw, views in ((20, (120, 37, 700, 5)), (4, (50, 3, 1, 64))):
+        case = make_case(pw, n_amp_views=views, n_det=3)
+        b = build_product(case, cut=(1,))
+        n = case["n_amp"]
+        per = case["per"]
+        rng = np.random.default_rng(pw + chunk)
+        a_in = rng.standard_normal(n)
+        flags = (rng.random(n) < 0.1).astype(np.uint8)
+        ref = np.zeros(n)
+        OP.apply_precond(case["prior"], a_in, flags, ref)
+        ref[per:2 * per] = 0.0
+        seg_start, seg_len = _i64(b.seg_start), _i64(b.seg_len)
+        p_start, p_width = _i64(b.prec_start), _i64(b.prec_width)
+        pre = np.concatenate(b.precond)
+        out = np.full(n, np.nan)
+        hm.tbp_banded_partitioned_segments(ct.c_int64(len(seg_start)), _ptr(seg_start),
+                                           _ptr(seg_len), _ptr(p_start), _ptr(p_width),
+                                           _ptr(pre), ct.c_int64(chunk), _ptr(a_in), _ptr(flags),
+                                           _ptr(out))
+        H.assert_close_norm(out, ref, rtol=1e-12, what=f"partitioned precond pw={pw}")
+        assert np.all(out[flags != 0] == 0.0) and np.all(out[per:2 * per] == 0.0)

@@ -32,7 +32,16 @@ struct tb_offset_prior {
     int64_t n_blocks = 0;
     const double *filters = nullptr, *precond = nullptr;
     int precond_mode = 0;
+    // partitioned banded solve (EXPERIMENTAL, tb_set_option("prior_chunk", m) before create)
+    bool has_part = false;
+    void *part_blob = nullptr;
+    tbp::PartView part;
 };
+
+// chunk length of the partitioned banded solve for priors created from now on; 0 = one thread
+// per segment (the validated form).  EXPERIMENTAL: the per-thread code is checked on the host
+// (tests/test_offset_prior.py), the launches have not run on hardware yet.
+int tb_prior_chunk = 0;
 
 namespace {
 
@@ -77,6 +86,76 @@ k_prior_banded(int64_t n_seg, const int64_t *__restrict__ seg_start,
     tbp::banded_cho_solve(factors + ps, p_width[seg], n, in + s0, out + s0);
     for (int64_t j = 0; j < n; ++j)
         if (flags[s0 + j] != 0) out[s0 + j] = 0.0;
+}
+
+// ---- partitioned banded solve: six launches, per-thread code in tb_prior.cuh ---------------------
+template <bool FWD>
+__global__ void __launch_bounds__(kSolveThreads)
+k_pb_chunk(tbp::PartView v, const double *__restrict__ in, double *out) {
+    const int64_t g = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
+    if (g >= v.n_chunk) return;
+    if (FWD) tbp::pb_fwd_local(v, g, in, out);
+    else tbp::pb_bwd_local(v, g, out);
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(kSolveThreads)
+k_pb_seg(tbp::PartView v, const double *out) {
+    const int64_t seg = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
+    if (seg >= v.n_seg) return;
+    if (FWD) tbp::pb_tails(v, seg, out);
+    else tbp::pb_heads(v, seg, out);
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(kConvThreads)
+k_pb_row(tbp::PartView v, const int64_t *__restrict__ blocks, const uint8_t *__restrict__ flags,
+         double *out) {
+    const int64_t seg = blocks[2 * (int64_t)blockIdx.x];
+    const int64_t j = blocks[2 * (int64_t)blockIdx.x + 1] + threadIdx.x;
+    if (j >= v.seg_len[seg]) return;
+    if (FWD) tbp::pb_fwd_correct(v, seg, j, out);
+    else tbp::pb_bwd_correct(v, seg, j, flags, out);
+}
+
+void build_partition(tb_offset_prior *p, const tb_offset_prior_desc *d, int64_t chunk) {
+    tbp::PartTables T;
+    tbp::build_part_tables(d->n_seg, d->seg_len, d->prec_start, d->prec_width, d->precond, chunk, T);
+    const size_t ni = T.seg_chunk0.size() + T.seg_m.size() + T.chunk_seg.size() + T.g_off.size();
+    const size_t nd = T.Gf.size() + T.Gb.size() + 2 * (size_t)(T.n_chunk * T.qmax + 1);
+    TB_CUDA(cudaMalloc(&p->part_blob, ni * sizeof(int64_t) + nd * sizeof(double)));
+    int64_t *di = (int64_t *)p->part_blob;
+    double *dd = (double *)(di + ni);
+    auto up_i = [&](const std::vector<int64_t> &v, int64_t *&dst) {
+        const int64_t *at = dst;
+        if (!v.empty())
+            TB_CUDA(cudaMemcpy(dst, v.data(), v.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        dst += v.size();
+        return at;
+    };
+    tbp::PartView &v = p->part;
+    v.n_seg = d->n_seg;
+    v.n_chunk = T.n_chunk;
+    v.qmax = T.qmax;
+    v.seg_start = p->seg_start;
+    v.seg_len = p->seg_len;
+    v.p_start = p->prec_start;
+    v.p_width = p->prec_width;
+    v.factors = p->precond;
+    v.seg_chunk0 = up_i(T.seg_chunk0, di);
+    v.seg_m = up_i(T.seg_m, di);
+    v.chunk_seg = up_i(T.chunk_seg, di);
+    v.g_off = up_i(T.g_off, di);
+    TB_CUDA(cudaMemcpy(dd, T.Gf.data(), T.Gf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    v.Gf = dd;
+    dd += T.Gf.size();
+    TB_CUDA(cudaMemcpy(dd, T.Gb.data(), T.Gb.size() * sizeof(double), cudaMemcpyHostToDevice));
+    v.Gb = dd;
+    dd += T.Gb.size();
+    v.tails = dd;
+    v.heads = dd + (T.n_chunk * T.qmax + 1);
+    TB_CUDA(cudaMemset(v.tails, 0, 2 * (size_t)(T.n_chunk * T.qmax + 1) * sizeof(double)));
+    p->has_part = true;
 }
 
 } // namespace
@@ -155,6 +234,8 @@ tb_offset_prior *tb_offset_prior_create(const tb_offset_prior_desc *d) {
         p->blocks = di + 6 * ns;
         p->filters = dd;
         p->precond = dd + d->n_filter_values;
+        if (tb_prior_chunk > 0 && d->precond_mode == TB_PRECOND_BANDED && ns > 0)
+            build_partition(p, d, tb_prior_chunk);
         return p;
     } catch (const tbr::Error &e) {
         tbr::set_error(e.code, e.msg);
@@ -165,6 +246,7 @@ tb_offset_prior *tb_offset_prior_create(const tb_offset_prior_desc *d) {
 void tb_offset_prior_destroy(tb_offset_prior *p) {
     if (p == nullptr) return;
     if (p->blob) cudaFree(p->blob);
+    if (p->part_blob) cudaFree(p->part_blob);
     delete p;
 }
 
@@ -210,6 +292,23 @@ int tb_offset_prior_precond(const tb_offset_prior *p, const double *amplitudes_i
                 d_f, d_out);
             TB_CUDA(cudaGetLastError());
             tbr::count_launch();
+        }
+    } else if (p->has_part) {
+        const tbp::PartView &v = p->part;
+        const unsigned nbc = (unsigned)((v.n_chunk + kSolveThreads - 1) / kSolveThreads);
+        const unsigned nbs = (unsigned)((v.n_seg + kSolveThreads - 1) / kSolveThreads);
+        TB_REQUIRE(p->n_blocks < 2147483647LL, "grid too large");
+        const unsigned nbr = (unsigned)p->n_blocks;
+        cudaStream_t st = R.stream();
+        if (v.n_chunk > 0 && nbr > 0) {
+            k_pb_chunk<true><<<nbc, kSolveThreads, 0, st>>>(v, d_in, d_out);
+            k_pb_seg<true><<<nbs, kSolveThreads, 0, st>>>(v, d_out);
+            k_pb_row<true><<<nbr, kConvThreads, 0, st>>>(v, p->blocks, d_f, d_out);
+            k_pb_chunk<false><<<nbc, kSolveThreads, 0, st>>>(v, d_in, d_out);
+            k_pb_seg<false><<<nbs, kSolveThreads, 0, st>>>(v, d_out);
+            k_pb_row<false><<<nbr, kConvThreads, 0, st>>>(v, p->blocks, d_f, d_out);
+            TB_CUDA(cudaGetLastError());
+            tbr::count_launch(6);
         }
     } else if (p->n_seg > 0) {
         const int64_t nb = (p->n_seg + kSolveThreads - 1) / kSolveThreads;

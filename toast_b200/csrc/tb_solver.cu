@@ -2311,6 +2311,7 @@ int tb_obs_has_compact_pointing(const tb_obs *obs) { return (obs && obs->lpix) ?
 int tb_obs_has_pair_weights(const tb_obs *obs) { return (obs && obs->lpp) ? 1 : 0; }
 
 extern int tb_peer_ctas_per_sm; // tb_peer.cu
+extern int tb_prior_chunk;      // tb_prior.cu
 
 int tb_get_option(const char *name) {
     if (name == nullptr) return -1;
@@ -2324,6 +2325,7 @@ int tb_get_option(const char *name) {
     if (n == "sorted2") return g_use_xs2;
     if (n == "peer_ctas") return tb_peer_ctas_per_sm;
     if (n == "prefetch") return g_use_prefetch;
+    if (n == "prior_chunk") return tb_prior_chunk;
     return -1;
 }
 
@@ -2346,6 +2348,9 @@ int tb_set_option(const char *name, int value) {
         g_use_xs2 = value;
     } else if (std::string(name) == "prefetch") {
         g_use_prefetch = value;
+    } else if (std::string(name) == "prior_chunk") {
+        TB_REQUIRE(value >= 0, "prior_chunk must be >= 0");
+        tb_prior_chunk = value;
     } else if (std::string(name) == "peer_ctas") {
         TB_REQUIRE(value >= 1 && value <= 16, "peer_ctas must be in [1, 16]");
         tb_peer_ctas_per_sm = value;
