@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import helpers as H
+from helpers import S
 from oracle import offset_prior as OP
 from toast_b200.templates import offset_prior as PP
 
@@ -396,3 +397,43 @@ def test_partitioned_segments_match_the_reference_preconditioner(chunk):
                                            _ptr(out))
         H.assert_close_norm(out, ref, rtol=1e-12, what=f"partitioned precond pw={pw}")
         assert np.all(out[flags != 0] == 0.0) and np.all(out[per:2 * per] == 0.0)
+
+
+def test_single_baseline_observation_disables_the_prior(monkeypatch):
+    """offset.py:208-214: an observation shorter than one baseline gets no noise prior -- its
+    amplitudes come out of add_prior / apply_precond as zeros (offset.py:946-947, 1003-1005),
+    which the product expresses as cut segments."""
+    from toast_b200.data import Data, NoiseModel, observation_from_synthetic
+    from toast_b200.templates import Offset
+    from toast_b200.templates import offset as offset_module
+
+    monkeypatch.setattr(offset_module.KC, "template_offset_project_signal_batch",
+                        _numpy_project_batch)
+    obs = S.make_observation("c1", n_det=2, n_samp=80, nside=64)   # 8 s at 10 Hz
+    data = Data()
+    ob = observation_from_synthetic(obs)
+    data.obs.append(ob)
+    dets = ob.local_detectors
+    psdfreq, psds = OP.analytic_psd(obs["sigma"], obs["rate"], n_freq=100)
+    ob["noise_model"] = NoiseModel({d: float(w) for d, w in zip(dets, obs["detweight"])},
+                                   {d: psdfreq for d in dets},
+                                   {d: psds[i] for i, d in enumerate(dets)})
+    tmpl = Offset(name="baselines", step_time=10.0, times="times", noise_model="noise_model",
+                  det_flags=None, view="scanning", use_noise_prior=True)
+    tmpl._defer_prior = True
+    tmpl.initialize(data)
+    assert tmpl._n_local == 2 and list(tmpl._obs_views[0]) == [1]
+    assert PP.prior_frequencies(7.9, 10.0, 10.0) is None
+    b = tmpl._prior_builder(data)
+    assert b.filt_start == [-1, -1] and b.prec_start == [-1, -1]
+    assert b.seg_start == [0, 1] and b.seg_len == [1, 1]
+    # the cut segments zero their amplitudes (kernel cores on the host)
+    hm = H.host_math_lib()
+    out = np.array([3.0, 4.0])
+    a_in = np.array([1.0, 2.0])
+    flags = np.zeros(2, dtype=np.uint8)
+    ss, sl, fs, fl = (_i64(v) for v in (b.seg_start, b.seg_len, b.filt_start, b.filt_len))
+    taps = np.zeros(1)
+    hm.tbp_conv_segments(ct.c_int64(2), _ptr(ss), _ptr(sl), _ptr(fs), _ptr(fl), _ptr(taps),
+                         _ptr(a_in), _ptr(flags), _ptr(out), ct.c_int(0))
+    assert np.all(out == 0.0)
