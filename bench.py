@@ -52,7 +52,7 @@ BYTES_PER_SAMPLE_ITER = 66
 # committed `ncu --set full` captures (profiles/r1_ncu_passes.txt, profiles/r1_ncu_crossings.txt)
 NCU_TRAFFIC = {
     "k_lhs_pair<0>": 8.246e9, "k_lhs_pair<1>": 7.572e9,
-    "k_bin_xs": 1.480e9, "k_lhs_x<1>": 3.373e9,
+    "k_bin_xs": 1.480e9, "k_lhs_x<1>": 3.373e9, "k_proj_xs": 1.536e9,
 }
 
 
