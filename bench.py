@@ -7,17 +7,20 @@
 A *step* is one PCG iteration of the Offset-template destriper (SolverLHS.apply + the vector
 updates of solve(), ops/mapmaker_solve.py:665-746) over the rank's shard of synthetic data:
 
-    pass 1   F a -> noise-weighted binning          (k_bin,     33 B / det-sample)
-    NCCL     all-reduce of the noise-weighted map   (N > 1)
-             3x3 pixel covariance apply
-    pass 2   F a - P m -> N^-1 -> F^T               (k_project, 33 B / det-sample)
+    pass 1   F a -> noise-weighted binning          (k_bin_xs:  pixel-sorted crossing list)
+    NVLink   map reduction + 3x3 pixel covariance   (N > 1: fused peer kernel, pipelined with
+             (N = 1: k_cov_apply)                    the passes when that measures faster)
+    pass 2   F a - P m -> N^-1 -> F^T               (k_proj_xs: the same sorted list)
     PCG      d.q, x/r/s update, r.r, s.r, new d     (+ one scalar read-back for convergence)
+
+Algorithmic bytes are the reference layout's 33 B / det-sample per pass; the
+passes stream ~4.6 B / det-sample of crossing records instead.
 
 Default workload ("c4"): BASELINE.json configs[3] detector-sharded -- 128 detectors x 12 h @
 50 Hz (2.76e8 det-samples) per GPU, nside 2048 NEST IQU, 1 s baselines; at N GPUs the job is
 N x 128 detectors with the map all-reduced (weak scaling; N = 8 is the full 1024-detector
-2.2e9-sample configuration).  Inputs (9 GB of stored pointing per GPU) are far larger than the
-126 MB L2, so no explicit L2 flush is needed between steps.
+2.2e9-sample configuration).  Every iteration streams ~5 GB per GPU, far more than the 126 MB L2,
+so no explicit L2 flush is needed between steps.
 """
 
 import argparse
