@@ -5,7 +5,9 @@ import pytest
 
 # The reference's CPU project_signal accumulates with OpenMP atomics (template_offset.cpp:
 # 301-327): only a single-threaded oracle is deterministic / bit-comparable.
-os.environ.setdefault("OMP_NUM_THREADS", "1")
+# Forced (not setdefault): a caller's OMP_NUM_THREADS > 1 would make the bit-for-bit checks against
+# the compiled reference flaky.  TB_TEST_OMP_THREADS overrides it for experiments.
+os.environ["OMP_NUM_THREADS"] = os.environ.get("TB_TEST_OMP_THREADS", "1")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
