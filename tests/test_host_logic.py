@@ -167,3 +167,23 @@ def test_pointing_detector_fp():
     assert ob.detdata["q2"].data.shape == (4, 500, 4)
     with pytest.raises(AttributeError):
         ops.PointingDetectorFP(nside=64)
+
+
+def test_pipeline_chunk_bounds():
+    """The pixel chunks of the multi-GPU pipeline: cover [0, n_pix) without gaps, every inner
+    bound aligned to 256 x world pixels (reduction tile x one slice per rank), None when two
+    chunks are not possible."""
+    import torch  # noqa: F401  (toast_b200.solver imports it)
+    from toast_b200.solver import pipeline_chunk_bounds
+
+    for n_sub, world, want in ((4438, 8, 4), (4438, 2, 4), (25, 4, 8), (3, 8, 4), (78, 2, 16)):
+        n_pix = n_sub * 3072
+        b = pipeline_chunk_bounds(n_pix, world, want)
+        assert b is not None and b[0] == 0 and b[-1] == n_pix
+        assert np.all(np.diff(b) > 0) and len(b) - 1 <= want
+        assert np.all(b[:-1] % (256 * world) == 0)
+        assert n_pix % 256 == 0   # so the last chunk is whole reduction tiles too
+    assert pipeline_chunk_bounds(3072, 8, 4) is None        # 12 tiles: one unit only
+    assert pipeline_chunk_bounds(10 * 3072, 2, 1) is None   # a single chunk requested
+    b = pipeline_chunk_bounds(2 * 3072, 4, 100)             # more chunks wanted than units
+    assert len(b) - 1 == (2 * 3072) // 1024

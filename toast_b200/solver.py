@@ -328,6 +328,21 @@ class SymmPeerMap:
             pass
 
 
+def pipeline_chunk_bounds(n_pix, world, n_chunks):
+    """Local-pixel bounds of the chunks the multi-GPU pipeline works in: every chunk but the last
+    is a multiple of 256 x world pixels (the reduction kernel's tile x one slice per rank), the
+    last one takes the remainder.  None when fewer than two chunks are possible."""
+    unit = 256 * world
+    units = n_pix // unit
+    n_chunks = max(1, min(int(n_chunks), units))
+    if n_chunks < 2:
+        return None
+    bounds = np.array([(c * units) // n_chunks * unit for c in range(n_chunks + 1)],
+                      dtype=np.int64)
+    bounds[-1] = n_pix
+    return bounds
+
+
 class Destriper:
     """Fused SolverRHS / SolverLHS / solve() for one or more device observations.
 
@@ -424,15 +439,11 @@ class Destriper:
         import os as _os
         if self.peer is None or n_chunks < 2 or self._sorted_passes() != 2:
             return
-        n_pix = self.n_local_submap * self.n_pix_submap
-        unit = 256 * self.world          # every chunk splits evenly over the ranks
-        units = n_pix // unit
-        n_chunks = max(1, min(n_chunks, units))
-        if n_chunks < 2:
+        bounds = pipeline_chunk_bounds(self.n_local_submap * self.n_pix_submap, self.world,
+                                       n_chunks)
+        if bounds is None:
             return
-        bounds = np.array([(c * units) // n_chunks * unit for c in range(n_chunks + 1)],
-                          dtype=np.int64)
-        bounds[-1] = n_pix               # (the remainder, < unit pixels, joins the last chunk)
+        n_chunks = len(bounds) - 1
         for o in self.obs:
             L.check(self.lib.tb_obs_set_pixel_chunks(o.handle().h, n_chunks, L.ptr(bounds)))
         self.chunk_bounds = bounds
