@@ -513,7 +513,15 @@ def main_gpu(args):
         n_rec, n_rows, xp = ct.c_int64(0), ct.c_int64(0), ct.c_int(0)
         lib.tb_obs_crossing_stats(dobs.handle().h, ct.byref(n_rec), ct.byref(n_rows), ct.byref(xp))
         crossings = compact and lib.tb_get_option(b"crossings") == 1 and n_rec.value > 0
-        if crossings:
+        blocked = ds._blocked()
+        fused = blocked and world == 1 and ds.fuse_lhs
+        if blocked:
+            names = ("k_bx<0> (pass 1: template -> noise-weighted map, block-ordered crossing "
+                     "list, shared-memory map tiles)",
+                     "k_bx<2> (pass 1 + covariance + pass 2 fused, block-ordered crossing list, "
+                     "shared-memory map tiles)" if fused else
+                     "k_bx<1> (pass 2: scan - weight - project, block-ordered crossing list)")
+        elif crossings:
             sp = int(lib.tb_obs_sorted_passes(dobs.handle().h))
             names = ("k_bin_xs (pass 1: template -> noise-weighted map, pixel-sorted crossing list)"
                      if sp >= 1 else

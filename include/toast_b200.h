@@ -307,6 +307,32 @@ int tb_cov_apply_pad(int64_t n_pix, const double *cov, const double *zmap, doubl
                      void *stream);
 int tb_lhs_pass2_pad(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
                      const double *binned4, double *amplitudes_out, void *stream);
+/* ---- block-ordered crossing list: shared-memory privatised map tiles (tb_blocked.cu) ----------
+ * The same two passes as tb_lhs_pass1 / tb_lhs_pass2 (mapmaker_solve.py:342-506: template
+ * add_to_signal + BuildNoiseWeighted, ops_mapmaker_utils.cpp:15-86,295-377; ScanMap + NoiseWeight
+ * + project_signal, ops_scan_map.cpp:16-78, template_offset.cpp:243-327) on the crossing records
+ * sorted by pixel BLOCK (tb_bx_block_pixels() consecutive local pixels): a CTA keeps the block's
+ * map values in shared memory.
+ *   tb_bx_pass1  writes (accumulate = 0) or adds to (accumulate = 1) the noise-weighted map of the
+ *                amplitudes; with accumulate = 0 EVERY block of the local map is written, no
+ *                zero-fill is needed.  chunk < 0: the whole map; chunk >= 0: the pixel chunk set
+ *                by tb_obs_set_pixel_chunks (bounds must be multiples of the block size).
+ *   tb_bx_pass2  projects the binned map for the amplitudes of the preceding tb_bx_pass1 /
+ *                tb_bx_fused call and ADDS to amplitudes_out.
+ *   tb_bx_fused  one observation on one GPU: pass 1 -> covariance_apply (toast_map_cov.cpp:471-528)
+ *                -> pass 2 inside one kernel, the map never leaves the SM.  zmap_scratch
+ *                ([n_local_pix, 3]) is only touched for blocks that had to be cut into several
+ *                work units (high-contention maps).  ADDS to amplitudes_out. */
+int tb_bx_block_pixels(void);
+int tb_obs_blocked(const tb_obs *obs);
+int tb_obs_blocked_stats(const tb_obs *obs, int64_t *n_records, int64_t *n_units,
+                         int64_t *n_multi_units, int64_t *n_blocks);
+int tb_bx_pass1(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                double *zmap, int accumulate, int64_t chunk, void *stream);
+int tb_bx_pass2(const tb_obs *obs, const double *binned, double *amplitudes_out, int64_t chunk,
+                void *stream);
+int tb_bx_fused(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                const double *cov, double *zmap_scratch, double *amplitudes_out, void *stream);
 /* RHS projection (SolverRHS, mapmaker_solve.py:107-229): out += F^T N^-1 (signal - P m). */
 int tb_rhs_project(const tb_obs *obs, const double *signal, const uint8_t *amp_flags,
                    const double *binned, double *amplitudes_out, int regen, void *stream);

@@ -487,12 +487,15 @@ def solver_rhs(pb, K, signal, covapply=None):
 
 
 def solve(pb, K, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, covapply=None,
-          prior=None):
+          prior=None, trace=None):
     """The PCG loop of mapmaker_solve.py:524-755, zero starting guess.  Returns
     (amplitudes, [relative residual per iteration]).  ``prior``: an
     ``oracle.offset_prior.OraclePrior`` -- the LHS then includes the noise prior
     (mapmaker_solve.py:395-412) and the preconditioner is Offset._apply_precond's banded /
-    Toeplitz form (offset.py:962-1010)."""
+    Toeplitz form (offset.py:962-1010).  ``trace``: optional list that receives, per iteration, a
+    dict with copies of the state BEFORE the iteration (x, r, d, delta) and what the iteration
+    produced (q = A d, alpha, sqsum = r.r after the update) -- the restart-parity tests load the
+    state into the device solver, run ONE iteration there and compare."""
     fl = pb.amp_flags
     _lhs, _diag = solver_lhs, K.template_offset_apply_diag_precond
     if prior is not None:
@@ -509,11 +512,11 @@ def solve(pb, K, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, covappl
                 _OP.apply_precond(prior, a_in, flags, a_out)
 
         return _solve(pb, _KP, rhs, convergence, n_iter_max, n_iter_min, covapply,
-                      lambda pb_, K_, a, c=None: solver_lhs_p(pb_, K, a, c))
-    return _solve(pb, K, rhs, convergence, n_iter_max, n_iter_min, covapply, solver_lhs)
+                      lambda pb_, K_, a, c=None: solver_lhs_p(pb_, K, a, c), trace)
+    return _solve(pb, K, rhs, convergence, n_iter_max, n_iter_min, covapply, solver_lhs, trace)
 
 
-def _solve(pb, K, rhs, convergence, n_iter_max, n_iter_min, covapply, solver_lhs):
+def _solve(pb, K, rhs, convergence, n_iter_max, n_iter_min, covapply, solver_lhs, trace=None):
     fl = pb.amp_flags
     result = np.zeros_like(rhs)
     lhs_out = solver_lhs(pb, K, result, covapply)
@@ -532,11 +535,16 @@ def _solve(pb, K, rhs, convergence, n_iter_max, n_iter_min, covapply, solver_lhs
             raise RuntimeError("Residual is not finite")
         lhs_out = solver_lhs(pb, K, proposal, covapply)
         alpha = delta / amp_dot(proposal, lhs_out, fl)
+        if trace is not None:
+            trace.append(dict(x=result.copy(), r=residual.copy(), d=proposal.copy(),
+                              delta=float(delta), q=lhs_out.copy(), alpha=float(alpha)))
         result += proposal * alpha
         residual -= lhs_out * alpha
         sqsum = amp_dot(residual, residual, fl)
         relative = sqsum / sqsum_init
         history.append(relative)
+        if trace is not None:
+            trace[-1].update(sqsum=float(sqsum), sqsum_init=float(sqsum_init))
         if relative < convergence or sqsum < 1e-30:
             break
         sqsum_best = min(sqsum, sqsum_best)
@@ -569,11 +577,18 @@ def global_to_local(pix, n_pix_submap, g2l):
 
 
 def build_problem(obs, K=None, shared_flag_mask=1, det_flag_mask=1, rcond_threshold=1.0e-3,
-                  IAU=False, hwp=None, use_flags=True):
+                  IAU=False, hwp=None, use_flags=True, external=None):
     """Expand pointing and assemble every buffer one PCG iteration touches.
 
     ``obs`` is a dict from ``toast_b200.synthetic.make_observation``; ``K`` is the kernel
-    namespace (this module, or the compiled reference from ``load_ref()``)."""
+    namespace (this module, or the compiled reference from ``load_ref()``).
+
+    ``external``: dict(hit_submaps, cov [n_local, n_pix_submap, 6], rcond [n_local *
+    n_pix_submap]) computed from a LARGER detector set that contains this observation's
+    detectors.  The pixel distribution, the pixel covariance and the rcond mask are then taken
+    from it instead of being accumulated from these detectors alone, so that a few-detector
+    subset of a production-size problem keeps the production covariance (the full-size parity
+    tests: the compiled reference runs 4 detectors, the covariance comes from the whole shard)."""
     K = K or sys.modules[__name__]
     from toast_b200.synthetic import n_submap_for
 
@@ -593,6 +608,11 @@ def build_problem(obs, K=None, shared_flag_mask=1, det_flag_mask=1, rcond_thresh
     pb.step_length = obs["step_length"]
 
     pb.pixels, pb.weights, pb.hit_submaps = expand_pointing(pb, K)
+    if external is not None:
+        ext_hits = np.asarray(external["hit_submaps"], dtype=np.uint8)
+        assert np.all(ext_hits[pb.hit_submaps != 0] != 0), "external hit map must cover this one"
+        pb.own_hit_submaps = pb.hit_submaps
+        pb.hit_submaps = ext_hits
     pb.local_submaps, pb.global2local = pixel_distribution(pb.hit_submaps)
     pb.n_local_submap = len(pb.local_submaps)
 
@@ -610,8 +630,8 @@ def build_problem(obs, K=None, shared_flag_mask=1, det_flag_mask=1, rcond_thresh
 
     # inverse pixel covariance (mapmaker_utils.py:440-515) -> covariance
     block = 6
-    invcov = np.zeros(pb.n_local_submap * pb.n_pix_submap * block)
-    for d in range(pb.n_det):
+    invcov = np.zeros(pb.n_local_submap * pb.n_pix_submap * block if external is None else 0)
+    for d in range(pb.n_det if external is None else 0):
         for iv in pb.intervals:
             a, b = int(iv["first"]), int(iv["last"])
             sm, lp = global_to_local(pb.pixels[d, a:b], pb.n_pix_submap, pb.global2local)
@@ -619,10 +639,17 @@ def build_problem(obs, K=None, shared_flag_mask=1, det_flag_mask=1, rcond_thresh
             cov_accum_diag_invnpp(pb.n_local_submap, pb.n_pix_submap, 3, sm, lp,
                                   np.ascontiguousarray(pb.weights[d, a:b]).reshape(-1),
                                   float(pb.det_scale[d]), invcov)
-    pb.invcov = invcov.copy()
-    rcond = np.zeros(pb.n_local_submap * pb.n_pix_submap)
-    cov_eigendecompose_diag(pb.n_local_submap, pb.n_pix_submap, 3, invcov, rcond,
-                            rcond_threshold, True)
+    if external is None:
+        pb.invcov = invcov.copy()
+        rcond = np.zeros(pb.n_local_submap * pb.n_pix_submap)
+        cov_eigendecompose_diag(pb.n_local_submap, pb.n_pix_submap, 3, invcov, rcond,
+                                rcond_threshold, True)
+    else:
+        pb.invcov = None
+        invcov = np.ascontiguousarray(external["cov"], dtype=np.float64).reshape(-1)
+        rcond = np.ascontiguousarray(external["rcond"], dtype=np.float64).reshape(-1)
+        assert invcov.size == pb.n_local_submap * pb.n_pix_submap * block
+        assert rcond.size == pb.n_local_submap * pb.n_pix_submap
     pb.cov = invcov.reshape(pb.n_local_submap, pb.n_pix_submap, block)
     pb.rcond = rcond
 

@@ -115,3 +115,51 @@ def host_math_lib():
     lib = ct.CDLL(so)
     lib.tbm_quat2pix.restype = ct.c_int64
     return lib
+
+
+def first_iteration_over(hist, hist_ref, tol=RTOL):
+    """Index of the first PCG iteration whose relative residual deviates from the reference's
+    by more than ``tol`` (relative), or None."""
+    hist, hist_ref = np.asarray(hist), np.asarray(hist_ref)
+    n = min(len(hist), len(hist_ref))
+    dev = np.abs(hist[:n] - hist_ref[:n]) / np.abs(hist_ref[:n])
+    over = np.flatnonzero(dev > tol)
+    return (int(over[0]) if len(over) else None), dev
+
+
+def restart_parity(ds, pb, trace, what=""):
+    """RESTART PARITY of the PCG (the rigorous form of 'residual histories agree to 1e-10'):
+    CG amplifies rounding differences exponentially, so two correct implementations drift apart
+    when they run freely.  Here the device solver is loaded with the ORACLE's state before
+    iteration k (x, r, d, delta: ``trace`` from ``O.solve(..., trace=[])``), runs exactly ONE
+    iteration (LHS, d.q, x/r/s update, r.r) and must reproduce what the reference's iteration k
+    produced -- q = A d, alpha, the new residual norm and the new x, r -- to 1e-10, for EVERY k.
+    Returns the per-iteration worst relative deviation."""
+    import torch
+
+    from toast_b200.solver import _PCGState
+
+    st = _PCGState(pb.n_amp, ds.device)
+    worst = []
+    dev_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ds.device)
+    nrm = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    for k, t in enumerate(trace):
+        st.x.copy_(dev_t(t["x"]))
+        st.r.copy_(dev_t(t["r"]))
+        st.d.copy_(dev_t(t["d"]))
+        st.delta.fill_(t["delta"])
+        ds.lhs_and_dot(st)
+        ds.update(st)
+        e_q = nrm(st.q.cpu().numpy(), t["q"])
+        alpha = t["delta"] / float(st.dq.item())
+        e_alpha = abs(alpha - t["alpha"]) / abs(t["alpha"])
+        e_rr = abs(float(st.sums[0].item()) - t["sqsum"]) / t["sqsum"]
+        x_ref = t["x"] + t["d"] * t["alpha"]
+        r_ref = t["r"] - t["q"] * t["alpha"]
+        e_x = nrm(st.x.cpu().numpy(), x_ref)
+        e_r = nrm(st.r.cpu().numpy(), r_ref) * (np.max(np.abs(r_ref)) / np.max(np.abs(t["r"])))
+        w = max(e_q, e_alpha, e_rr, e_x, e_r)
+        worst.append(w)
+        assert w <= RTOL, (f"{what}: restart parity fails at iteration {k}: q {e_q:.2e} "
+                           f"alpha {e_alpha:.2e} r.r {e_rr:.2e} x {e_x:.2e} r {e_r:.2e}")
+    return worst

@@ -117,6 +117,68 @@ def test_against_golden_reference_outputs(fixture):
     H.assert_history_matches(hist, g["history"], H.pcg_envelope(pb, g["rhs"], 12), what=fixture)
 
 
+@pytest.mark.parametrize("fixture", ["c1_wide", "c2_wide", "c4_wide", "c5_wide"])
+def test_against_wide_golden_reference_outputs(fixture):
+    """The committed reference outputs with thousands of hit pixels
+    (tests/golden/make_golden_wide.py): 16-64 detectors, 1282-4564 non-zero map pixels."""
+    g = np.load(f"{H.GOLDEN}/{fixture}.npz")
+    obs = S.make_observation(str(g["workload"]), n_det=int(g["n_det"]), n_samp=int(g["n_samp"]),
+                             eps_max=0.05, nside=int(g["nside"]))
+    pb = O.build_problem(obs, O)
+    dobs, ds, hits = _device_problem(obs, pb, regen=False)
+    np.testing.assert_array_equal(dobs.pixels.cpu().numpy(), g["pixels"].astype(np.int64))
+    np.testing.assert_array_equal(hits, g["hit_submaps"])
+    ws = int(g["weight_stride"])
+    w = dobs.weights.cpu().numpy()
+    assert_close_norm(w[:, ::ws, :], g["weights_strided"], what="weights")
+    assert_close_norm(w.sum(axis=1), g["weights_colsum"], what="weight column sums")
+
+    from toast_b200 import kernels as K
+    idx = np.arange(pb.n_det, dtype=np.int32)
+    zmap = torch.zeros((pb.n_local_submap, pb.n_pix_submap, 3), dtype=torch.float64, device="cuda")
+    K.build_noise_weighted(pb.global2local, zmap, idx, dobs.pixels, idx, dobs.weights, idx,
+                           torch.from_numpy(obs["signal"]).cuda(), idx,
+                           torch.from_numpy(pb.solver_flags).cuda(), pb.det_scale, 1,
+                           pb.intervals, torch.from_numpy(pb.shared_flags).cuda(), 1)
+    z = zmap.cpu().numpy().reshape(-1, 3)
+    zg = np.zeros_like(z)
+    zg[g["zmap_index"]] = g["zmap_values"]
+    assert len(g["zmap_index"]) >= 1000
+    assert_close_norm(z, zg, what="zmap")
+    sig = torch.from_numpy(obs["signal"]).cuda()
+    assert_close_norm(ds.rhs([sig]).cpu().numpy(), g["rhs"], what="RHS")
+    ones = torch.from_numpy(np.where(pb.amp_flags == 0, 1.0, 0.0)).cuda()
+    q = torch.zeros_like(ones)
+    ds.lhs(ones, q)
+    assert_close_norm(q.cpu().numpy(), g["lhs_of_ones"], what="LHS(1)")
+    amps2, _ = ds.solve(torch.from_numpy(g["rhs"]).cuda(), n_iter_max=2)
+    assert_close_norm(amps2.cpu().numpy(), g["amplitudes_iter2"], what="amplitudes (2 it)")
+    _, hist = ds.solve(torch.from_numpy(g["rhs"]).cuda(), n_iter_max=12)
+    H.assert_history_matches(hist, g["history"], H.pcg_envelope(pb, g["rhs"], 12), what=fixture)
+
+
+@pytest.mark.parametrize("name,n_det,n_samp,nside,rcond", [("c1", 8, 20000, 64, 1e-3),
+                                                           ("c2", 16, 24000, 128, 1e-8),
+                                                           ("c4", 8, 40000, 128, 1e-8),
+                                                           ("c5", 16, 30000, 256, 1e-8)])
+def test_pcg_restart_parity_every_iteration(name, n_det, n_samp, nside, rcond):
+    """helpers.restart_parity for k = 0 .. 19: the oracle's state before iteration k, ONE device
+    iteration, 1e-10 on q, alpha, r.r, x and r -- at the production rcond threshold."""
+    ck = H.checker()
+    obs = S.make_observation(name, n_det=n_det, n_samp=n_samp, eps_max=0.03, nside=nside)
+    pb = O.build_problem(obs, ck, rcond_threshold=rcond)
+    assert np.mean((pb.solver_flags & pb.det_flag_mask) == 0) > 0.25
+    dobs, ds, _ = _device_problem(obs, pb)
+    rhs_ref = O.solver_rhs(pb, ck, obs["signal"], covapply=ck.cov_apply_diag)
+    trace = []
+    _, hist_ref = O.solve(pb, ck, rhs_ref, n_iter_max=20, covapply=ck.cov_apply_diag, trace=trace)
+    worst = H.restart_parity(ds, pb, trace, what=name)
+    _, hist = ds.solve(torch.from_numpy(rhs_ref).cuda(), n_iter_max=20)
+    first, dev = H.first_iteration_over(hist, hist_ref)
+    print(f"PARITY_REPORT {name}: restart parity worst {max(worst):.2e} over {len(trace)} "
+          f"iterations; free-running history leaves 1e-10 at iteration {first}")
+
+
 def test_lhs_equals_rhs_of_template_signal():
     """tests/ops_mapmaker_solve.py:150-265: LHS(a) == RHS(F a)."""
     obs = S.make_observation("c1", n_det=4, n_samp=6000, nside=64)
@@ -178,8 +240,12 @@ def test_lhs_kernel_variants_agree(perm, eps_max):
     lib = L.load()
     results = {}
     try:
-        for name, opts in (("sorted2", dict(sorted=1, sorted2=1, crossings=1, pair=1, pairw=1,
-                                            compact=1, tma=0)),
+        for name, opts in (("blocked", dict(blocked=1, sorted=1, sorted2=1, crossings=1, pair=1,
+                                            pairw=1, compact=1, tma=0)),
+                           ("blocked2", dict(blocked=1, sorted=1, sorted2=1, crossings=1, pair=1,
+                                             pairw=1, compact=1, tma=0)),
+                           ("sorted2", dict(blocked=0, sorted=1, sorted2=1, crossings=1, pair=1,
+                                            pairw=1, compact=1, tma=0)),
                            ("sorted", dict(sorted=1, sorted2=0, crossings=1, pair=1, pairw=1,
                                            compact=1, tma=0)),
                            ("crossings", dict(sorted=0, crossings=1, pair=1, pairw=1, compact=1,
@@ -192,6 +258,10 @@ def test_lhs_kernel_variants_agree(perm, eps_max):
             for k, v in opts.items():
                 L.check(lib.tb_set_option(k.encode(), v))
             dobs, ds, _ = _device_problem(obs, pb)
+            if name.startswith("blocked"):
+                # "blocked": one fused kernel; "blocked2": pass 1 / covariance / pass 2 launches
+                assert lib.tb_obs_blocked(dobs.handle().h) == 1
+                ds.fuse_lhs = name == "blocked"
             q = torch.zeros(pb.n_amp, dtype=torch.float64, device="cuda")
             ds.lhs(torch.from_numpy(a).cuda(), q)
             results[name] = q.cpu().numpy()
@@ -214,10 +284,11 @@ def test_lhs_kernel_variants_agree(perm, eps_max):
                                  for i in range(0, len(perm) - 1, 2))
                 assert bool(lib.tb_obs_has_pair_weights(dobs.handle().h)) == co_pointed
     finally:
-        for k, v in dict(sorted=1, sorted2=1, crossings=1, pair=1, pairw=1, compact=1,
+        for k, v in dict(blocked=1, sorted=1, sorted2=1, crossings=1, pair=1, pairw=1, compact=1,
                          tma=0).items():
             lib.tb_set_option(k.encode(), v)
-    for name in ("sorted2", "sorted", "crossings", "pairw", "compact", "tma", "general"):
+    for name in ("blocked", "blocked2", "sorted2", "sorted", "crossings", "pairw", "compact", "tma",
+                 "general"):
         # (pixels with rcond down to 1e-5 amplify the summation-order differences of the variants)
         assert_close_norm(results[name], results["pair"], rtol=1e-11, what=f"{name} vs pair")
 
@@ -257,6 +328,30 @@ def test_pixel_chunked_passes_sum_to_the_whole():
         assert np.all(qh[pb.amp_flags != 0] == 0.0)
     with pytest.raises(RuntimeError):
         L.check(lib.tb_lhs_pass2_chunk(h, L.ptr(ds.zmap), L.ptr(q), n_chunks, None))
+    # the same on the block-ordered list: bounds on block boundaries; pass 1 writes (does not
+    # add to) every block of its chunk, so the map starts from garbage
+    assert lib.tb_obs_blocked(h) == 1
+    bp = int(lib.tb_bx_block_pixels())
+    for bounds in ([0, n_pix], [0, bp, 2 * bp, n_pix], list(range(0, n_pix, bp)) + [n_pix],
+                   [0, 3 * bp, 3 * bp, n_pix]):
+        b = np.array(bounds, dtype=np.int64)
+        n_chunks = len(b) - 1
+        L.check(lib.tb_obs_set_pixel_chunks(h, n_chunks, L.ptr(b)))
+        ds.zmap.fill_(float("nan"))
+        for c in range(n_chunks):
+            L.check(lib.tb_bx_pass1(h, L.ptr(a_d), L.ptr(ds.amp_flags), L.ptr(ds.zmap), 0, c, None))
+        ds.reduce_and_apply_cov()
+        q = torch.full((pb.n_amp,), 0.0, dtype=torch.float64, device="cuda")
+        for c in reversed(range(n_chunks)):
+            L.check(lib.tb_bx_pass2(h, L.ptr(ds.zmap), L.ptr(q), c, None))
+        qh = q.cpu().numpy()
+        assert_close_norm(qh, ref, what=f"chunked blocked LHS ({n_chunks} chunks)")
+        assert np.all(qh[pb.amp_flags != 0] == 0.0)
+    # bounds off the block grid: the chunked block-ordered calls are refused
+    b = np.array([0, 256, n_pix], dtype=np.int64)
+    L.check(lib.tb_obs_set_pixel_chunks(h, 2, L.ptr(b)))
+    with pytest.raises(RuntimeError):
+        L.check(lib.tb_bx_pass1(h, L.ptr(a_d), L.ptr(ds.amp_flags), L.ptr(ds.zmap), 0, 0, None))
 
 
 def test_off_map_samples_keep_the_time_ordered_pass2():

@@ -185,6 +185,37 @@ def test_c_port_reproduces_golden_reference_outputs(fixture):
     np.testing.assert_array_equal(amps, g["amplitudes"])
 
 
+@pytest.mark.parametrize("fixture", ["c1_wide", "c2_wide", "c4_wide", "c5_wide"])
+def test_c_port_reproduces_wide_golden_reference_outputs(fixture):
+    """The fixtures with thousands of hit pixels (tests/golden/make_golden_wide.py)."""
+    g = np.load(os.path.join(H.GOLDEN, fixture + ".npz"))
+    obs = S.make_observation(str(g["workload"]), n_det=int(g["n_det"]), n_samp=int(g["n_samp"]),
+                             eps_max=0.05, nside=int(g["nside"]))
+    pb = O.build_problem(obs, O)
+    assert len(g["zmap_index"]) >= 1000
+    np.testing.assert_array_equal(pb.pixels, g["pixels"].astype(np.int64))
+    ws = int(g["weight_stride"])
+    np.testing.assert_array_equal(pb.weights[:, ::ws, :], g["weights_strided"])
+    np.testing.assert_array_equal(pb.weights.sum(axis=1), g["weights_colsum"])
+    np.testing.assert_array_equal(pb.hit_submaps, g["hit_submaps"])
+    idx = np.arange(pb.n_det, dtype=np.int32)
+    zmap = np.zeros((pb.n_local_submap, pb.n_pix_submap, 3))
+    O.build_noise_weighted(pb.global2local, zmap, idx, pb.pixels, idx, pb.weights, idx,
+                           obs["signal"], idx, pb.solver_flags, pb.det_scale, 1, pb.intervals,
+                           pb.shared_flags, 1)
+    zg = np.zeros((pb.n_local_submap * pb.n_pix_submap, 3))
+    zg[g["zmap_index"]] = g["zmap_values"]
+    np.testing.assert_array_equal(zmap.reshape(-1, 3), zg)
+    rhs = O.solver_rhs(pb, O, obs["signal"])
+    np.testing.assert_array_equal(rhs, g["rhs"])
+    ones = np.where(pb.amp_flags == 0, 1.0, 0.0)
+    np.testing.assert_array_equal(O.solver_lhs(pb, O, ones), g["lhs_of_ones"])
+    amps2, _ = O.solve(pb, O, rhs, n_iter_max=2)
+    np.testing.assert_array_equal(amps2, g["amplitudes_iter2"])
+    _, hist = O.solve(pb, O, rhs, n_iter_max=12)
+    np.testing.assert_array_equal(np.array(hist), g["history"])
+
+
 def test_healpix_primitives_against_golden():
     """tests/healpix.py:95-184 with the compiled reference's outputs as the authority."""
     g = np.load(os.path.join(H.GOLDEN, "healpix_angles.npz"))

@@ -1,0 +1,661 @@
+// tb_blocked.cu -- the LHS passes on the BLOCK-ORDERED crossing list: shared-memory privatised
+// map tiles (the binning design of the north star).
+//
+// What the reference does per PCG iteration (ops/mapmaker_solve.py:342-506) is, per sample,
+//   pass 1   zmap[pixel] += F a * w_det * weights          (template_offset.cpp:93-121 +
+//                                                            ops_mapmaker_utils.cpp:15-86,295-377)
+//            zmap <- all-reduce;  m = C zmap                (pixels.py:710-779, toast_map_cov.cpp:471-528)
+//   pass 2   out[baseline] += w_det (F a - weights . m)     (ops_scan_map.cpp:16-78,
+//                                                            ops_noise_weight.cpp:101-114,
+//                                                            template_offset.cpp:243-327)
+// The crossing list (tb_solver.cu: k_xbuild) already collapses every run of samples that share
+// (pixel, baseline) into one record; both passes are linear in the record's (n, sum Q, sum U).
+//
+// Here the records are stably sorted by PIXEL BLOCK (kBxPix consecutive local pixels), which
+// leaves them in (block, row, time) order:
+//   * the map side is private to the CTA: the 3 x kBxPix doubles of a block live in shared memory
+//     (48 KB), pass 1 accumulates with shared-memory atomics and flushes the finished tile with
+//     coalesced 16-byte stores -- no zero-fill, no global atomics when the block is one work unit
+//     (blocks with very many records are cut into units of kBxUnitMax records whose tiles are
+//     flushed with fp64 REDs: the high-contention case, one RED per touched pixel and unit instead
+//     of three per record);
+//   * the amplitude side keeps its time locality: consecutive records of a detector's track
+//     through the block share the baseline, so the 16-byte amplitude gather of a warp touches a
+//     handful of sectors and pass 2 issues one RED per baseline run (segmented warp sum) instead
+//     of one per record.
+// On one GPU with one observation nothing has to leave the SM between the passes: the fused
+// kernel accumulates the tile, applies the 3x3 pixel covariance in shared memory and projects the
+// same records (second read served by the L2) -- the map never touches HBM.
+#include <algorithm>
+
+#include "tb_obs.cuh"
+
+using namespace tbd;
+
+namespace tbr {
+void sort_pairs_i32(const int32_t *keys_in, int32_t *keys_out, const int32_t *vals_in,
+                    int32_t *vals_out, int64_t n, int end_bit, cudaStream_t st); // tb_sort.cu
+}
+
+int g_use_bx = 1; // tb_set_option("blocked", 0/1)
+
+namespace {
+
+constexpr int kBxShift = 11;
+constexpr int kBxPix = 1 << kBxShift;   // pixels per block: 3 x 2048 doubles = 48 KB of shared memory
+constexpr int kBxUnitMax = 16384;       // records per work unit
+#ifndef TB_BX_CTAS
+#define TB_BX_CTAS 4
+#endif
+
+// ---- build ---------------------------------------------------------------------------------------
+// keys / values for the stable sort by block.  value = record index | mode << 30 (0: as recorded,
+// 1: detector 0 only, 2: detector 1 only).  TWO_SLOT: entry 2i is the record itself, entry 2i + 1
+// its second pixel when the two detectors of the row fall in different pixels (rare; the one-slot
+// form is used when that never happens).  Entries with nothing on the map get key n_blocks.
+template <bool TWO_SLOT>
+__global__ void __launch_bounds__(kThreads)
+k_bx_keys(const int4 *__restrict__ xrec, int64_t n_rec, int32_t n_blocks, int32_t *__restrict__ keys,
+          int32_t *__restrict__ vals, unsigned int *__restrict__ counters /* {split, invalid, off-map} */) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_rec;
+         i += (int64_t)gridDim.x * kThreads) {
+        const int4 r = xrec[i];
+        int32_t key = n_blocks, val = (int32_t)i, key2 = n_blocks, val2 = (int32_t)i | (2 << 30);
+        if (r.x == -2 || r.y == -2) atomicAdd(counters + 2, 1u);
+        if (r.x >= 0) {
+            key = r.x >> kBxShift;
+            if (r.y >= 0 && r.y != r.x) {
+                val |= (1 << 30);
+                key2 = r.y >> kBxShift;
+                atomicAdd(counters, 1u);
+            }
+        } else if (r.y >= 0) {
+            key = r.y >> kBxShift;
+        }
+        if (key == n_blocks) atomicAdd(counters + 1, 1u);
+        if (TWO_SLOT) {
+            keys[2 * i] = key;
+            vals[2 * i] = val;
+            keys[2 * i + 1] = key2;
+            vals[2 * i + 1] = val2;
+            if (key2 == n_blocks) atomicAdd(counters + 1, 1u);
+        } else {
+            keys[i] = key;
+            vals[i] = val;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_bx_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
+            const int32_t *__restrict__ vals, int64_t n_sorted, int64_t n_amp_det,
+            int2 *__restrict__ brec, double2 *__restrict__ bqu) {
+    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < n_sorted;
+         j += (int64_t)gridDim.x * kThreads) {
+        const int32_t v = vals[j];
+        const int32_t i = v & 0x3FFFFFFF, mode = (v >> 30) & 3;
+        const int4 r = xrec[i];
+        const int n = r.z & 0xFF, row = (int)((unsigned)r.z >> 8);
+        const int n0 = (r.x >= 0 && mode != 2) ? n : 0;
+        const int n1 = (r.y >= 0 && mode != 1 && (mode == 2 || r.x < 0 || r.y == r.x)) ? n : 0;
+        const int32_t pix = (mode == 2 || r.x < 0) ? r.y : r.x;
+        brec[j] = make_int2((pix & (kBxPix - 1)) | (n0 << kBxShift) | (n1 << (kBxShift + 6)),
+                            (int32_t)((int64_t)row * n_amp_det + r.w));
+        bqu[j] = xqu[i];
+    }
+}
+
+// first sorted entry whose key is >= b, for b = 0 .. n_blocks
+__global__ void k_bx_block_starts(const int32_t *__restrict__ keys, int64_t n, int32_t n_blocks,
+                                  int32_t *__restrict__ start) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_blocks) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < b) lo = mid + 1;
+        else hi = mid;
+    }
+    start[b] = (int32_t)lo;
+}
+
+// ---- the passes ----------------------------------------------------------------------------------
+struct BxArgs {
+    const int4 *units;        // {block, first record, end record, multi}
+    const int2 *brec;
+    const double2 *bqu;
+    const double *dscaled;    // prescaled amplitudes (k_amp_prescale)
+    double4 cst;              // {cal0, cal1, A, B} when uniform
+    const double4 *table;     // per row otherwise
+    double inv_nad;           // 1 / n_amp_det
+    int32_t nad;
+    const double *det_scale;
+    const int64_t *amp_offsets;
+    int n_det;
+    int64_t n_pix;            // local map size
+    double *zmap;             // pass 1: output;  pass 2: the binned map;  fused: unused
+    const double *cov;        // fused: [n_pix, 6]
+    double *out;              // pass 2 / fused: amplitudes
+    int accumulate;           // pass 1: add to zmap (REDs) even for single-unit blocks
+};
+
+struct BxRow {
+    double4 c;
+    int row;
+};
+
+template <bool UNIFORM>
+__device__ __forceinline__ BxRow bx_row(const BxArgs &a, int32_t slot) {
+    BxRow r;
+    r.row = (int)fast_div((int64_t)slot, a.inv_nad);
+    r.c = a.cst;
+    if (!UNIFORM) {
+        const double2 *tp = reinterpret_cast<const double2 *>(a.table + r.row);
+        const double2 ca = __ldg(tp), cb = __ldg(tp + 1);
+        r.c = make_double4(ca.x, ca.y, cb.x, cb.y);
+    }
+    return r;
+}
+
+// amplitude x detector weight of both detectors of the record's row (0 if flagged / absent)
+template <bool PAIRED>
+__device__ __forceinline__ double2 bx_amps(const BxArgs &a, int32_t slot, int n0, int n1,
+                                           bool &ok0, bool &ok1) {
+    double2 av = make_double2(0.0, 0.0);
+    if (PAIRED) av = __ldg(reinterpret_cast<const double2 *>(a.dscaled) + slot);
+    else av.x = __ldg(a.dscaled + slot);
+    ok0 = n0 != 0 && !amp_is_flagged(av.x);
+    ok1 = PAIRED && n1 != 0 && !amp_is_flagged(av.y);
+    if (!ok0) av.x = 0.0;
+    if (!ok1) av.y = 0.0;
+    return av;
+}
+
+// pass 1 over the records [first, end) of one unit: tile += a w (n cal, sum Q, sum U)
+template <bool UNIFORM, bool PAIRED, bool KEEP_IN_L2>
+__device__ __forceinline__ void bx_accumulate(const BxArgs &a, double *tile, int first, int end) {
+#pragma unroll 2
+    for (int i = first + (int)threadIdx.x; i < end; i += kThreads) {
+        const int2 r = KEEP_IN_L2 ? __ldg(a.brec + i) : __ldcs(a.brec + i);
+        const double2 qu = KEEP_IN_L2 ? __ldg(a.bqu + i) : __ldcs(a.bqu + i);
+        const int p = r.x & (kBxPix - 1);
+        const int n0 = (r.x >> kBxShift) & 63, n1 = (r.x >> (kBxShift + 6)) & 63;
+        double4 c = a.cst;
+        if (!UNIFORM) c = bx_row<false>(a, r.y).c;
+        bool ok0, ok1;
+        const double2 t = bx_amps<PAIRED>(a, r.y, n0, n1, ok0, ok1);
+        if (!(ok0 || ok1)) continue;
+        const double v0 = t.x * (c.x * (double)n0) + t.y * (c.y * (double)n1);
+        const double v1 = t.x * qu.x + t.y * (c.z * qu.x - c.w * qu.y);
+        const double v2 = t.x * qu.y + t.y * (c.w * qu.x + c.z * qu.y);
+        double *z = tile + 3 * p;
+        atomicAdd(z, v0);
+        atomicAdd(z + 1, v1);
+        atomicAdd(z + 2, v2);
+    }
+}
+
+// pass 2 over the records of one unit: out[baseline] += w (n a - (n cal, sum Q, sum U) . m), one
+// RED per run of records that share the baseline (they are consecutive: (row, time) order)
+template <bool UNIFORM, bool PAIRED>
+__device__ __forceinline__ void bx_project(const BxArgs &a, const double *tile, int first, int end) {
+    const int lane = threadIdx.x & 31;
+    for (int base = first; base < end; base += kThreads) { // uniform trip count: shuffles inside
+        const int i = base + (int)threadIdx.x;
+        int64_t key = -1 - lane; // idle lanes: distinct keys, nothing to add
+        double val0 = 0.0, val1 = 0.0;
+        int row = 0, arel = 0;
+        bool ok0 = false, ok1 = false;
+        if (i < end) {
+            const int2 r = __ldcs(a.brec + i);
+            const double2 qu = __ldcs(a.bqu + i);
+            const int p = r.x & (kBxPix - 1);
+            const int n0 = (r.x >> kBxShift) & 63, n1 = (r.x >> (kBxShift + 6)) & 63;
+            const BxRow br = bx_row<UNIFORM>(a, r.y);
+            const double4 c = br.c;
+            row = br.row;
+            arel = r.y - row * a.nad;
+            key = r.y;
+            const double2 av = bx_amps<PAIRED>(a, r.y, n0, n1, ok0, ok1);
+            const double m0 = tile[3 * p], m1 = tile[3 * p + 1], m2 = tile[3 * p + 2];
+            const int d0 = PAIRED ? 2 * row : row;
+            if (ok0) {
+                double sc = 0.0;
+                sc += (c.x * (double)n0) * m0;
+                sc += qu.x * m1;
+                sc += qu.y * m2;
+                val0 = (double)n0 * av.x - sc * __ldg(a.det_scale + d0);
+            }
+            if (PAIRED && ok1) {
+                const double q1 = c.z * qu.x - c.w * qu.y, u1 = c.w * qu.x + c.z * qu.y;
+                double sc = 0.0;
+                sc += (c.y * (double)n1) * m0;
+                sc += q1 * m1;
+                sc += u1 * m2;
+                val1 = (double)n1 * av.y - sc * __ldg(a.det_scale + d0 + 1);
+            }
+        }
+        const Runs rr = find_runs<8>(key, lane);
+        val0 = seg_sum<8>(val0, rr);
+        if (PAIRED) val1 = seg_sum<8>(val1, rr);
+        if (rr.is_tail && i < end) {
+            const int d0 = PAIRED ? 2 * row : row;
+            if (val0 != 0.0) atomicAdd(a.out + __ldg(a.amp_offsets + d0) + arel, val0);
+            if (PAIRED && val1 != 0.0)
+                atomicAdd(a.out + __ldg(a.amp_offsets + d0 + 1) + arel, val1);
+        }
+    }
+}
+
+// MODE 0: pass 1 (tile -> zmap), 1: pass 2 (binned map -> tile -> amplitudes), 2: fused
+template <int MODE, bool UNIFORM, bool PAIRED>
+__global__ void __launch_bounds__(kThreads, TB_BX_CTAS)
+k_bx(const BxArgs a) {
+    __shared__ __align__(16) double tile[3 * kBxPix];
+    const int4 u = __ldg(a.units + blockIdx.x);
+    const int64_t g0 = (int64_t)u.x * (3 * kBxPix);          // first map double of the block
+    const int64_t g_end = 3 * a.n_pix;
+    double2 *tile2 = reinterpret_cast<double2 *>(tile);
+    if (MODE == 1) {
+        const double2 *src = reinterpret_cast<const double2 *>(a.zmap + g0);
+        for (int k = threadIdx.x; k < 3 * kBxPix / 2; k += kThreads) {
+            const int64_t g = g0 + 2 * k;
+            double2 v = make_double2(0.0, 0.0);
+            if (g + 1 < g_end) v = __ldcs(src + k);
+            else if (g < g_end) v.x = __ldcs(a.zmap + g);
+            tile2[k] = v;
+        }
+    } else {
+        for (int k = threadIdx.x; k < 3 * kBxPix / 2; k += kThreads)
+            tile2[k] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (MODE == 1) {
+        bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z);
+        return;
+    }
+    bx_accumulate<UNIFORM, PAIRED, MODE == 2>(a, tile, u.y, u.z);
+    __syncthreads();
+    if (MODE == 0) {
+        if (u.w == 0 && !a.accumulate) {
+            // the only unit of its block: the tile IS the block of the map
+            double2 *dst = reinterpret_cast<double2 *>(a.zmap + g0);
+            for (int k = threadIdx.x; k < 3 * kBxPix / 2; k += kThreads) {
+                const int64_t g = g0 + 2 * k;
+                if (g + 1 < g_end) __stcs(dst + k, tile2[k]);
+                else if (g < g_end) a.zmap[g] = tile2[k].x;
+            }
+        } else {
+            for (int k = threadIdx.x; k < 3 * kBxPix; k += kThreads) {
+                const double v = tile[k];
+                if (v != 0.0 && g0 + k < g_end) atomicAdd(a.zmap + g0 + k, v);
+            }
+        }
+        return;
+    }
+    // fused: m = C z in place (toast_map_cov.cpp:509-517 operation order, as k_cov_apply)
+    for (int p = threadIdx.x; p < kBxPix; p += kThreads) {
+        const int64_t gp = (int64_t)u.x * kBxPix + p;
+        const double z0 = tile[3 * p], z1 = tile[3 * p + 1], z2 = tile[3 * p + 2];
+        if (gp >= a.n_pix || (z0 == 0.0 && z1 == 0.0 && z2 == 0.0)) continue;
+        const double2 *cm = reinterpret_cast<const double2 *>(a.cov + 6 * gp);
+        const double2 ca = __ldcs(cm), cb = __ldcs(cm + 1), cc = __ldcs(cm + 2);
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        m0 += ca.x * z0;
+        m0 += ca.y * z1;
+        m1 += ca.y * z0;
+        m0 += cb.x * z2;
+        m2 += cb.x * z0;
+        m1 += cb.y * z1;
+        m1 += cc.x * z2;
+        m2 += cc.x * z1;
+        m2 += cc.y * z2;
+        tile[3 * p] = m0;
+        tile[3 * p + 1] = m1;
+        tile[3 * p + 2] = m2;
+    }
+    __syncthreads();
+    bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z);
+}
+
+// zero / covariance product on whole blocks of the global map (the multi-unit blocks of the fused
+// path: their units meet in global memory)
+__global__ void __launch_bounds__(kThreads)
+k_bx_zero_blocks(const int32_t *__restrict__ blocks, int64_t n_pix, double *__restrict__ zmap) {
+    const int64_t g0 = (int64_t)__ldg(blocks + blockIdx.x) * (3 * kBxPix);
+    for (int k = threadIdx.x; k < 3 * kBxPix; k += kThreads)
+        if (g0 + k < 3 * n_pix) zmap[g0 + k] = 0.0;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_bx_cov_blocks(const int32_t *__restrict__ blocks, int64_t n_pix, const double *__restrict__ cov,
+                double *__restrict__ zmap) {
+    const int64_t p0 = (int64_t)__ldg(blocks + blockIdx.x) * kBxPix;
+    for (int p = threadIdx.x; p < kBxPix; p += kThreads) {
+        const int64_t gp = p0 + p;
+        if (gp >= n_pix) continue;
+        double *z = zmap + 3 * gp;
+        const double z0 = z[0], z1 = z[1], z2 = z[2];
+        const double *m = cov + 6 * gp;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        t0 += m[0] * z0;
+        t0 += m[1] * z1;
+        t1 += m[1] * z0;
+        t0 += m[2] * z2;
+        t2 += m[2] * z0;
+        t1 += m[3] * z1;
+        t1 += m[4] * z2;
+        t2 += m[4] * z1;
+        t2 += m[5] * z2;
+        z[0] = t0;
+        z[1] = t1;
+        z[2] = t2;
+    }
+}
+
+BxArgs make_args(const tb_obs *obs, const int4 *units) {
+    BxArgs a;
+    a.units = units;
+    a.brec = obs->brec;
+    a.bqu = obs->bqu;
+    a.dscaled = obs->dscaled;
+    a.cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
+    a.table = obs->stable;
+    a.inv_nad = 1.0 / (double)obs->n_amp_det;
+    a.nad = (int32_t)obs->n_amp_det;
+    a.det_scale = obs->det_scale;
+    a.amp_offsets = obs->amp_offsets;
+    a.n_det = (int)obs->d.n_det;
+    a.n_pix = obs->n_local_pix;
+    a.zmap = nullptr;
+    a.cov = nullptr;
+    a.out = nullptr;
+    a.accumulate = 0;
+    return a;
+}
+
+template <int MODE>
+void launch_bx(const tb_obs *obs, const BxArgs &a, int64_t n_units, void *stream) {
+    if (n_units <= 0) return;
+    TB_REQUIRE(n_units < 2147483647LL, "grid too large");
+    const unsigned g = (unsigned)n_units;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool configured = false; // (per MODE instantiation)
+    if (!configured) {
+        // 4 CTAs x 48 KB of static shared memory per SM: ask for the large carve-out
+        auto pref = [](const void *f) {
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared);
+        };
+        pref((const void *)k_bx<MODE, true, true>);
+        pref((const void *)k_bx<MODE, true, false>);
+        pref((const void *)k_bx<MODE, false, true>);
+        pref((const void *)k_bx<MODE, false, false>);
+        configured = true;
+    }
+    if (obs->s_uniform) {
+        if (obs->x_paired) k_bx<MODE, true, true><<<g, kThreads, 0, st>>>(a);
+        else k_bx<MODE, true, false><<<g, kThreads, 0, st>>>(a);
+    } else {
+        if (obs->x_paired) k_bx<MODE, false, true><<<g, kThreads, 0, st>>>(a);
+        else k_bx<MODE, false, false><<<g, kThreads, 0, st>>>(a);
+    }
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
+}
+
+inline bool bx_ok(const tb_obs *obs) { return g_use_bx && obs != nullptr && obs->brec != nullptr; }
+
+// units [first, end) of chunk c (tb_obs_set_pixel_chunks), or all of them for c < 0
+void chunk_units(const tb_obs *obs, int64_t chunk, int64_t &first, int64_t &end) {
+    first = 0;
+    end = obs->n_bunits;
+    if (chunk < 0) return;
+    TB_REQUIRE(chunk + 1 < (int64_t)obs->bchunk_unit.size(),
+               "bad chunk index (or pixel chunk bounds not aligned to the block size)");
+    first = obs->bchunk_unit[chunk];
+    end = obs->bchunk_unit[chunk + 1];
+}
+
+} // namespace
+
+void tb_free_blocked(tb_obs *obs) {
+    if (obs->brec) cudaFree(obs->brec);
+    if (obs->bqu) cudaFree(obs->bqu);
+    if (obs->bunits) cudaFree(obs->bunits);
+    if (obs->bunits_single) cudaFree(obs->bunits_single);
+    if (obs->bunits_multi) cudaFree(obs->bunits_multi);
+    if (obs->bmulti_blocks) cudaFree(obs->bmulti_blocks);
+    obs->brec = nullptr;
+    obs->bqu = nullptr;
+    obs->bunits = obs->bunits_single = obs->bunits_multi = nullptr;
+    obs->bmulti_blocks = nullptr;
+    obs->n_brec = obs->n_bunits = obs->n_bunits_single = obs->n_bunits_multi = 0;
+    obs->n_bmulti_blocks = 0;
+    obs->bunits_host.clear();
+    obs->bchunk_unit.clear();
+}
+
+// Build the block-ordered list from the time-ordered one.  Not built (the other kernels then
+// run) when a packed field would overflow or an unflagged sample lies off the local map (the
+// reference itself indexes out of bounds there: ops_scan_map.cpp:44-52).
+void tb_build_blocked(tb_obs *obs, cudaStream_t st) {
+    tb_free_blocked(obs);
+    const int64_t n_rec = obs->n_xrec, nad = obs->n_amp_det, n_det = obs->d.n_det;
+    const int64_t n_pix = obs->n_local_pix;
+    if (obs->xrec == nullptr || obs->stable == nullptr || obs->dscaled == nullptr) return;
+    if (n_rec <= 0 || n_rec >= (1LL << 29) || n_det * nad >= 2147483647LL || n_pix <= 0 ||
+        n_pix >= (1LL << 31) - kBxPix)
+        return;
+    const int32_t n_blocks = (int32_t)((n_pix + kBxPix - 1) >> kBxShift);
+    const int grid = tbr::sm_count() * 8;
+    unsigned int *counters = nullptr;
+    TB_CUDA(cudaMalloc(&counters, 3 * sizeof(unsigned int)));
+    int32_t *kin = nullptr, *vin = nullptr, *kout = nullptr, *vout = nullptr, *starts = nullptr;
+    auto cleanup = [&]() {
+        if (counters) cudaFree(counters);
+        if (kin) cudaFree(kin);
+        if (vin) cudaFree(vin);
+        if (kout) cudaFree(kout);
+        if (vout) cudaFree(vout);
+        if (starts) cudaFree(starts);
+    };
+    try {
+        unsigned int hc[3] = {0, 0, 0};
+        int64_t n_entries = n_rec;
+        TB_CUDA(cudaMalloc(&kin, sizeof(int32_t) * 2 * n_rec));
+        TB_CUDA(cudaMalloc(&vin, sizeof(int32_t) * 2 * n_rec));
+        for (int two_slot = 0; two_slot < 2; ++two_slot) {
+            TB_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st));
+            if (two_slot) k_bx_keys<true><<<grid, kThreads, 0, st>>>(obs->xrec, n_rec, n_blocks, kin, vin, counters);
+            else k_bx_keys<false><<<grid, kThreads, 0, st>>>(obs->xrec, n_rec, n_blocks, kin, vin, counters);
+            TB_CUDA(cudaGetLastError());
+            tbr::count_launch();
+            TB_CUDA(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            TB_CUDA(cudaStreamSynchronize(st));
+            n_entries = two_slot ? 2 * n_rec : n_rec;
+            if (hc[0] == 0 || two_slot) break; // no split crossings: one slot per record suffices
+        }
+        const int64_t n_sorted = n_entries - (int64_t)hc[1];
+        if (hc[2] != 0 || n_sorted <= 0) { // off-map samples: keep the time-ordered pass 2
+            cleanup();
+            return;
+        }
+        TB_CUDA(cudaMalloc(&kout, sizeof(int32_t) * n_entries));
+        TB_CUDA(cudaMalloc(&vout, sizeof(int32_t) * n_entries));
+        int end_bit = 1;
+        while ((1LL << end_bit) <= n_blocks) ++end_bit;
+        tbr::sort_pairs_i32(kin, kout, vin, vout, n_entries, end_bit, st); // stable
+        cudaFree(kin);
+        cudaFree(vin);
+        kin = vin = nullptr;
+        TB_CUDA(cudaMalloc(&obs->brec, sizeof(int2) * n_sorted));
+        TB_CUDA(cudaMalloc(&obs->bqu, sizeof(double2) * n_sorted));
+        k_bx_gather<<<grid, kThreads, 0, st>>>(obs->xrec, obs->xqu, vout, n_sorted, nad, obs->brec,
+                                               obs->bqu);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        TB_CUDA(cudaMalloc(&starts, sizeof(int32_t) * (n_blocks + 1)));
+        k_bx_block_starts<<<(n_blocks + 1 + 127) / 128, 128, 0, st>>>(kout, n_sorted, n_blocks, starts);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        std::vector<int32_t> hs(n_blocks + 1);
+        TB_CUDA(cudaMemcpyAsync(hs.data(), starts, sizeof(int32_t) * (n_blocks + 1),
+                                cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaStreamSynchronize(st));
+        // work units: every block gets at least one (an empty block still has to be written)
+        std::vector<int4> units, single, multi;
+        std::vector<int32_t> mblocks;
+        for (int32_t b = 0; b < n_blocks; ++b) {
+            const int32_t f = hs[b], e = hs[b + 1];
+            const int32_t nu = std::max(1, (e - f + kBxUnitMax - 1) / kBxUnitMax);
+            if (nu > 1) mblocks.push_back(b);
+            for (int32_t k = 0; k < nu; ++k) {
+                // equal shares, so that no unit of a block is a sliver
+                const int32_t uf = f + (int32_t)(((int64_t)(e - f) * k) / nu);
+                const int32_t ue = f + (int32_t)(((int64_t)(e - f) * (k + 1)) / nu);
+                const int4 u = make_int4(b, uf, ue, nu > 1 ? 1 : 0);
+                units.push_back(u);
+                (nu > 1 ? multi : single).push_back(u);
+            }
+        }
+        auto upload = [&](const std::vector<int4> &v, int4 **dst) {
+            if (v.empty()) return;
+            TB_CUDA(cudaMalloc(dst, sizeof(int4) * v.size()));
+            TB_CUDA(cudaMemcpy(*dst, v.data(), sizeof(int4) * v.size(), cudaMemcpyHostToDevice));
+        };
+        upload(units, &obs->bunits);
+        upload(single, &obs->bunits_single);
+        upload(multi, &obs->bunits_multi);
+        if (!mblocks.empty()) {
+            TB_CUDA(cudaMalloc(&obs->bmulti_blocks, sizeof(int32_t) * mblocks.size()));
+            TB_CUDA(cudaMemcpy(obs->bmulti_blocks, mblocks.data(), sizeof(int32_t) * mblocks.size(),
+                               cudaMemcpyHostToDevice));
+        }
+        obs->n_brec = n_sorted;
+        obs->n_bunits = (int64_t)units.size();
+        obs->n_bunits_single = (int64_t)single.size();
+        obs->n_bunits_multi = (int64_t)multi.size();
+        obs->n_bmulti_blocks = (int64_t)mblocks.size();
+        obs->bunits_host = units;
+        obs->bchunk_unit.assign({0, obs->n_bunits});
+        cleanup();
+    } catch (...) {
+        cleanup();
+        tb_free_blocked(obs);
+        throw;
+    }
+}
+
+// pixel chunks for the multi-GPU pipeline: bounds must fall on block boundaries (or the map end)
+void tb_blocked_set_chunks(tb_obs *obs, int64_t n_chunks, const int64_t *pixel_bounds) {
+    if (obs->brec == nullptr) return;
+    std::vector<int64_t> cu(n_chunks + 1);
+    for (int64_t c = 0; c <= n_chunks; ++c) {
+        const int64_t b = pixel_bounds[c];
+        if (!(b % kBxPix == 0 || b >= obs->n_local_pix)) {
+            obs->bchunk_unit.clear(); // not block-aligned: chunked blocked calls are refused
+            return;
+        }
+        const int64_t blk = (b + kBxPix - 1) >> kBxShift;
+        // first unit whose block is >= blk
+        auto it = std::lower_bound(obs->bunits_host.begin(), obs->bunits_host.end(), blk,
+                                   [](const int4 &u, int64_t v) { return (int64_t)u.x < v; });
+        cu[c] = (int64_t)(it - obs->bunits_host.begin());
+    }
+    cu[0] = 0;
+    cu[n_chunks] = obs->n_bunits;
+    obs->bchunk_unit = cu;
+}
+
+extern "C" {
+
+int tb_bx_block_pixels(void) { return kBxPix; }
+
+int tb_obs_blocked(const tb_obs *obs) { return bx_ok(obs) ? 1 : 0; }
+
+int tb_obs_blocked_stats(const tb_obs *obs, int64_t *n_records, int64_t *n_units,
+                         int64_t *n_multi_units, int64_t *n_blocks) {
+    TB_API_BEGIN
+    TB_REQUIRE(obs != nullptr, "NULL observation");
+    if (n_records) *n_records = obs->n_brec;
+    if (n_units) *n_units = obs->n_bunits;
+    if (n_multi_units) *n_multi_units = obs->n_bunits_multi;
+    if (n_blocks) *n_blocks = obs->brec ? (obs->n_local_pix + kBxPix - 1) >> kBxShift : 0;
+    TB_API_END
+}
+
+int tb_bx_pass1(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                double *zmap, int accumulate, int64_t chunk, void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs && amplitudes && amp_flags && zmap, "NULL argument");
+    TB_REQUIRE(bx_ok(obs), "the observation has no block-ordered crossing list");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(zmap) & 15u) == 0, "zmap must be 16-byte aligned");
+    int64_t first, end;
+    chunk_units(obs, chunk, first, end);
+    if (chunk <= 0) tb_launch_prescale(obs, amplitudes, amp_flags, stream);
+    if (!accumulate && obs->n_bmulti_blocks > 0 && chunk <= 0) {
+        // the units of a multi-unit block meet in global memory: it starts from zero
+        k_bx_zero_blocks<<<(unsigned)obs->n_bmulti_blocks, kThreads, 0, (cudaStream_t)stream>>>(
+            obs->bmulti_blocks, obs->n_local_pix, zmap);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+    }
+    BxArgs a = make_args(obs, obs->bunits + first);
+    a.zmap = zmap;
+    a.accumulate = accumulate;
+    launch_bx<0>(obs, a, end - first, stream);
+    TB_API_END
+}
+
+int tb_bx_pass2(const tb_obs *obs, const double *binned, double *amplitudes_out, int64_t chunk,
+                void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs && binned && amplitudes_out, "NULL argument");
+    TB_REQUIRE(bx_ok(obs), "the observation has no block-ordered crossing list");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(binned) & 15u) == 0, "map must be 16-byte aligned");
+    int64_t first, end;
+    chunk_units(obs, chunk, first, end);
+    BxArgs a = make_args(obs, obs->bunits + first);
+    a.zmap = const_cast<double *>(binned);
+    a.out = amplitudes_out;
+    launch_bx<1>(obs, a, end - first, stream);
+    TB_API_END
+}
+
+int tb_bx_fused(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
+                const double *cov, double *zmap_scratch, double *amplitudes_out, void *stream) {
+    TB_API_BEGIN
+    tbr::require_device();
+    TB_REQUIRE(obs && amplitudes && amp_flags && cov && amplitudes_out, "NULL argument");
+    TB_REQUIRE(bx_ok(obs), "the observation has no block-ordered crossing list");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(cov) & 15u) == 0, "cov must be 16-byte aligned");
+    tb_launch_prescale(obs, amplitudes, amp_flags, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (obs->n_bunits_multi > 0) {
+        // blocks cut into several units: their units meet in global memory (zmap_scratch)
+        TB_REQUIRE(zmap_scratch != nullptr, "blocks with several units need the zmap scratch");
+        k_bx_zero_blocks<<<(unsigned)obs->n_bmulti_blocks, kThreads, 0, st>>>(
+            obs->bmulti_blocks, obs->n_local_pix, zmap_scratch);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        BxArgs m = make_args(obs, obs->bunits_multi);
+        m.zmap = zmap_scratch;
+        launch_bx<0>(obs, m, obs->n_bunits_multi, stream);
+        k_bx_cov_blocks<<<(unsigned)obs->n_bmulti_blocks, kThreads, 0, st>>>(
+            obs->bmulti_blocks, obs->n_local_pix, cov, zmap_scratch);
+        TB_CUDA(cudaGetLastError());
+        tbr::count_launch();
+        m.out = amplitudes_out;
+        launch_bx<1>(obs, m, obs->n_bunits_multi, stream);
+    }
+    BxArgs a = make_args(obs, obs->bunits_single);
+    a.cov = cov;
+    a.out = amplitudes_out;
+    launch_bx<2>(obs, a, obs->n_bunits_single, stream);
+    TB_API_END
+}
+
+} // extern "C"

@@ -15,51 +15,7 @@
 
 using namespace tbd;
 
-struct tb_obs {
-    void *blob = nullptr; // one device allocation holding every small array
-    Views V;
-    // device arrays inside blob
-    const int64_t *amp_view_off = nullptr;
-    const int64_t *amp_offsets = nullptr;
-    const int64_t *g2l = nullptr;
-    const double *fp = nullptr;      // [n_det,4]
-    const double *cal = nullptr;
-    const double *eta = nullptr;     // (1-eps)/(1+eps)
-    const double *gamma = nullptr;
-    const double *det_scale = nullptr;
-    tb_obs_desc d; // copy of the descriptor (host pointers in it are NOT kept alive)
-    int64_t n_amp_det = 0;
-    // per-interval tiles for the TMA-staged passes: [n_tiles] x {s0, off, cnt, view}
-    int64_t *tiles = nullptr;
-    int64_t n_tiles = 0;
-    // compact solver pointing (tb_obs_pack_pointing): local pixel (int32, <0 = nothing to do)
-    // and the two sample-dependent weights (Q, U) as one 16-byte record
-    int32_t *lpix = nullptr;
-    double2 *wqu = nullptr;
-    // detector-pair form of the compact pointing (tb_obs_pack_pointing): both local pixels of a
-    // pair as one 8-byte record, and the fixed 2x2 rotation-scale that maps the (Q,U) weights of
-    // detector 2p onto those of detector 2p+1 -- verified sample by sample while packing
-    int2 *lpp = nullptr;        // [n_pair][n_samp]
-    double2 *pair_rot = nullptr; // [n_pair] (A, B): (q1, u1) = (A q0 - B u0, B q0 + A u0)
-    // crossing list (see k_lhs_x): one record per run of samples that share pixel(s) and baseline
-    int4 *xrec = nullptr;       // [n_xrec] {lp0, lp1, n_samples, amp_rel}
-    double2 *xqu = nullptr;     // [n_xrec] sum over the run of the (Q,U) weights
-    int4 *xblocks = nullptr;    // [n_xblocks] {row, first record, end record, 0}
-    int64_t n_xrec = 0, n_xblocks = 0, n_xrows = 0;
-    int x_paired = 0;           // rows are detector pairs (weights shared through pair_rot)
-    // pixel-sorted copy of the crossing list for pass 1 (see k_bin_xs)
-    int4 *srec = nullptr;       // [n_srec] {local pixel, scaled-amplitude index, n0|n1<<8|row<<16, 0}
-    double2 *squ = nullptr;     // [n_srec]
-    double4 *stable = nullptr;  // [n_xrows] {cal0, cal1, A, B}
-    double *dscaled = nullptr;  // [n_det * n_amp_det] scratch: amplitude * det_scale, NaN-tagged if flagged
-    int64_t n_srec = 0;
-    int s_pass2_ok = 0;         // no unflagged off-map sample: pass 2 may run on the sorted list too
-    // pixel chunks of the sorted list (tb_obs_set_pixel_chunks): records of chunk c are
-    // [chunk_rec[c], chunk_rec[c + 1])
-    std::vector<int64_t> chunk_rec;
-    int s_uniform = 0;          // every row has the same {cal0, cal1, A, B}: kernel constants
-    double s_const[4] = {0, 0, 0, 0};
-};
+#include "tb_obs.cuh"
 
 namespace {
 
@@ -1038,29 +994,24 @@ int g_use_x = 1; // tb_set_option("crossings", 0/1)
 // that the partner detector of a pair is a constant offset away.  Pass 2 keeps the time order
 // (its scattered side is a read-only gather, its output the sequential amplitude runs).
 // =================================================================================================
-// Flagged baselines are marked in the prescaled copy with a NaN of this bit pattern (an arithmetic
-// NaN never carries this payload, so a diverged solve still propagates its own NaNs).
-constexpr unsigned long long kAmpFlagBits = 0x7FF8000000B200B2ULL;
-__device__ __forceinline__ bool amp_is_flagged(double v) {
-    return (unsigned long long)__double_as_longlong(v) == kAmpFlagBits;
-}
+// (flagged baselines carry the NaN tag kAmpFlagBits in the prescaled copy: tb_obs.cuh)
 
 // The prescaled copy is laid out by ROW of the crossing list: unpaired rows are detectors,
 // [det][baseline] doubles; paired rows hold both detectors of a polarisation pair INTERLEAVED,
 // [pair][baseline][2], so that the passes fetch both amplitudes of a crossing with ONE 16-byte
 // gather (the scattered 8-byte gathers were 79 M of the 92 M sectors k_bin_xs loads: ncu, session
-// 3).  grid = (tiles of the baselines of one detector, slots); slots = 2 x pairs when paired (the
+// 3).  grid = (slots, tiles of the baselines of one detector); slots = 2 x pairs when paired (the
 // missing partner of an odd detector count is written as "flagged").
 __global__ void __launch_bounds__(kThreads)
 k_amp_prescale(ObsDev o, int64_t n_amp_det, int paired, const double *__restrict__ amps,
                const uint8_t *__restrict__ aflags, double *__restrict__ dscaled) {
-    const int64_t det = blockIdx.y;
+    const int64_t det = blockIdx.x; // slots on grid.x (up to 2^31 - 1), baseline tiles on grid.y
     const bool real = det < o.n_det;
     const int64_t a0 = real ? __ldg(o.amp_offsets + det) : 0;
     const double scale = real ? __ldg(o.det_scale + det) : 0.0;
     const double tagged = __longlong_as_double((long long)kAmpFlagBits);
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_amp_det;
-         i += (int64_t)gridDim.x * kThreads) {
+    for (int64_t i = (int64_t)blockIdx.y * kThreads + threadIdx.x; i < n_amp_det;
+         i += (int64_t)gridDim.y * kThreads) {
         const int64_t a = a0 + i;
         const double v = (real && __ldg(aflags + a) == 0) ? __ldg(amps + a) * scale : tagged;
         const int64_t slot = paired ? ((det >> 1) * n_amp_det + i) * 2 + (det & 1)
@@ -1626,8 +1577,8 @@ void launch_prescale(const tb_obs *obs, const ObsDev &o, const double *amps, con
     int64_t gx = (nad + kThreads * 4 - 1) / (kThreads * 4);
     if (gx < 1) gx = 1;
     const int64_t slots = obs->x_paired ? 2 * obs->n_xrows : o.n_det;
-    TB_REQUIRE(slots < 65536, "too many detectors for the prescale grid");
-    dim3 grid((unsigned)gx, (unsigned)slots);
+    if (gx > 65535) gx = 65535; // (the kernel strides over the baselines)
+    dim3 grid((unsigned)slots, (unsigned)gx);
     k_amp_prescale<<<grid, kThreads, 0, (cudaStream_t)stream>>>(o, nad, obs->x_paired, amps, aflags,
                                                                 obs->dscaled);
     TB_CUDA(cudaGetLastError());
@@ -1923,6 +1874,11 @@ inline int red_grid(int64_t n) {
 
 } // namespace
 
+void tb_launch_prescale(const tb_obs *obs, const double *amps, const uint8_t *aflags, void *stream) {
+    ObsDev o = make_dev(obs, 0);
+    launch_prescale(obs, o, amps, aflags, stream);
+}
+
 extern "C" {
 
 tb_obs *tb_obs_create(const tb_obs_desc *desc) {
@@ -1954,7 +1910,12 @@ tb_obs *tb_obs_create(const tb_obs_desc *desc) {
         }
         ib[2 * nv] = total;
         for (int64_t i = 0; i < nd; ++i) ib[3 * nv + 1 + i] = d.amp_offsets[i];
-        for (int64_t i = 0; i < ns; ++i) ib[3 * nv + 1 + nd + i] = d.global2local[i];
+        int64_t n_local = 0;
+        for (int64_t i = 0; i < ns; ++i) {
+            ib[3 * nv + 1 + nd + i] = d.global2local[i];
+            if (d.global2local[i] + 1 > n_local) n_local = d.global2local[i] + 1;
+        }
+        o->n_local_pix = n_local * (int64_t)d.n_pix_submap;
         std::vector<double> db(8 * nd, 0.0);
         for (int64_t i = 0; i < nd; ++i) {
             if (d.focalplane)
@@ -2031,6 +1992,7 @@ void tb_obs_destroy(tb_obs *obs) {
     if (obs->squ) cudaFree(obs->squ);
     if (obs->stable) cudaFree(obs->stable);
     if (obs->dscaled) cudaFree(obs->dscaled);
+    tb_free_blocked(obs);
     delete obs;
 }
 
@@ -2039,6 +2001,48 @@ void tb_obs_destroy(tb_obs *obs) {
 namespace tbr {
 void sort_pairs_i32(const int32_t *keys_in, int32_t *keys_out, const int32_t *vals_in,
                     int32_t *vals_out, int64_t n, int end_bit, cudaStream_t st); // tb_sort.cu
+}
+
+// Per-row constants {cal0, cal1, A, B} of the crossing list (rows = detector pairs when paired),
+// whether they are the same for every row (then they travel as kernel arguments), and the scratch
+// for the prescaled amplitudes.  Shared by the pixel-sorted and the block-ordered passes.
+void tb_build_row_table(tb_obs *obs) {
+    const int64_t n_rows = obs->n_xrows, n_det = obs->d.n_det, nad = obs->n_amp_det;
+    if (obs->stable) cudaFree(obs->stable);
+    if (obs->dscaled) cudaFree(obs->dscaled);
+    obs->stable = nullptr;
+    obs->dscaled = nullptr;
+    std::vector<double> cal(n_det);
+    TB_CUDA(cudaMemcpy(cal.data(), obs->cal, sizeof(double) * n_det, cudaMemcpyDeviceToHost));
+    std::vector<double2> rot;
+    if (obs->x_paired) {
+        rot.resize(n_rows);
+        TB_CUDA(cudaMemcpy(rot.data(), obs->pair_rot, sizeof(double2) * n_rows,
+                           cudaMemcpyDeviceToHost));
+    }
+    std::vector<double4> tab(n_rows);
+    bool uniform = true;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t d0 = obs->x_paired ? 2 * r : r, d1 = d0 + 1;
+        bool has1 = obs->x_paired && d1 < n_det;
+        // a missing partner never contributes (n1 = 0): give it the constants of row 0 so that
+        // an odd detector count does not break uniformity
+        tab[r] = make_double4(cal[d0], has1 ? cal[d1] : (r > 0 ? tab[0].y : cal[d0]),
+                              has1 ? rot[r].x : (r > 0 ? tab[0].z : 0.0),
+                              has1 ? rot[r].y : (r > 0 ? tab[0].w : 0.0));
+        if (tab[r].x != tab[0].x || tab[r].y != tab[0].y || tab[r].z != tab[0].z ||
+            tab[r].w != tab[0].w)
+            uniform = false;
+    }
+    TB_CUDA(cudaMalloc(&obs->stable, sizeof(double4) * n_rows));
+    TB_CUDA(cudaMemcpy(obs->stable, tab.data(), sizeof(double4) * n_rows, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMalloc(&obs->dscaled,
+                       sizeof(double) * (obs->x_paired ? 2 * n_rows : n_det) * nad));
+    obs->s_uniform = uniform ? 1 : 0;
+    obs->s_const[0] = tab[0].x;
+    obs->s_const[1] = tab[0].y;
+    obs->s_const[2] = tab[0].z;
+    obs->s_const[3] = tab[0].w;
 }
 
 // Pixel-sorted copy of the crossing list for pass 1 (k_bin_xs).  Skipped (pass 1 then runs on
@@ -2090,38 +2094,6 @@ static void build_sorted(tb_obs *obs, cudaStream_t st) {
     TB_CUDA(cudaStreamSynchronize(st));
     cudaFree(kout);
     cudaFree(vout);
-    // per-row constants {cal0, cal1, A, B}
-    std::vector<double> cal(n_det);
-    TB_CUDA(cudaMemcpy(cal.data(), obs->cal, sizeof(double) * n_det, cudaMemcpyDeviceToHost));
-    std::vector<double2> rot;
-    if (obs->x_paired) {
-        rot.resize(n_rows);
-        TB_CUDA(cudaMemcpy(rot.data(), obs->pair_rot, sizeof(double2) * n_rows,
-                           cudaMemcpyDeviceToHost));
-    }
-    std::vector<double4> tab(n_rows);
-    bool uniform = true;
-    for (int64_t r = 0; r < n_rows; ++r) {
-        int64_t d0 = obs->x_paired ? 2 * r : r, d1 = d0 + 1;
-        bool has1 = obs->x_paired && d1 < n_det;
-        // a missing partner never contributes (n1 = 0): give it the constants of row 0 so that
-        // an odd detector count does not break uniformity
-        tab[r] = make_double4(cal[d0], has1 ? cal[d1] : (r > 0 ? tab[0].y : cal[d0]),
-                              has1 ? rot[r].x : (r > 0 ? tab[0].z : 0.0),
-                              has1 ? rot[r].y : (r > 0 ? tab[0].w : 0.0));
-        if (tab[r].x != tab[0].x || tab[r].y != tab[0].y || tab[r].z != tab[0].z ||
-            tab[r].w != tab[0].w)
-            uniform = false;
-    }
-    TB_CUDA(cudaMalloc(&obs->stable, sizeof(double4) * n_rows));
-    TB_CUDA(cudaMemcpy(obs->stable, tab.data(), sizeof(double4) * n_rows, cudaMemcpyHostToDevice));
-    TB_CUDA(cudaMalloc(&obs->dscaled,
-                       sizeof(double) * (obs->x_paired ? 2 * n_rows : n_det) * nad));
-    obs->s_uniform = uniform ? 1 : 0;
-    obs->s_const[0] = tab[0].x;
-    obs->s_const[1] = tab[0].y;
-    obs->s_const[2] = tab[0].z;
-    obs->s_const[3] = tab[0].w;
     obs->n_srec = n_sorted;
     obs->s_pass2_ok = hc[2] == 0 ? 1 : 0;
     obs->chunk_rec.assign({0, n_sorted});
@@ -2147,6 +2119,7 @@ static void build_crossings(tb_obs *obs, cudaStream_t st) {
     obs->n_srec = 0;
     obs->s_pass2_ok = 0;
     obs->chunk_rec.clear();
+    tb_free_blocked(obs);
     if (obs->lpix == nullptr || obs->V.total <= 0) return;
     const int paired = obs->lpp != nullptr ? 1 : 0;
     const int64_t n_det = obs->d.n_det;
@@ -2215,7 +2188,9 @@ static void build_crossings(tb_obs *obs, cudaStream_t st) {
     obs->n_xblocks = (int64_t)blocks.size();
     obs->n_xrows = n_rows;
     obs->x_paired = paired;
+    tb_build_row_table(obs);
     build_sorted(obs, st);
+    tb_build_blocked(obs, st);
 }
 
 extern "C" {
@@ -2325,6 +2300,7 @@ int tb_get_option(const char *name) {
     if (n == "sorted2") return g_use_xs2;
     if (n == "peer_ctas") return tb_peer_ctas_per_sm;
     if (n == "prefetch") return g_use_prefetch;
+    if (n == "blocked") return g_use_bx;
     if (n == "prior_chunk") return tb_prior_chunk;
     return -1;
 }
@@ -2348,6 +2324,8 @@ int tb_set_option(const char *name, int value) {
         g_use_xs2 = value;
     } else if (std::string(name) == "prefetch") {
         g_use_prefetch = value;
+    } else if (std::string(name) == "blocked") {
+        g_use_bx = value;
     } else if (std::string(name) == "prior_chunk") {
         TB_REQUIRE(value >= 0, "prior_chunk must be >= 0");
         tb_prior_chunk = value;
@@ -2392,6 +2370,7 @@ int tb_obs_set_pixel_chunks(tb_obs *obs, int64_t n_chunks, const int64_t *pixel_
     TB_REQUIRE(obs->srec != nullptr, "the observation has no pixel-sorted crossing list");
     for (int64_t c = 0; c < n_chunks; ++c)
         TB_REQUIRE(pixel_bounds[c] <= pixel_bounds[c + 1], "pixel bounds must be non-decreasing");
+    tb_blocked_set_chunks(obs, n_chunks, pixel_bounds);
     int64_t *db = nullptr, *dr = nullptr;
     const int nb = (int)n_chunks + 1;
     TB_CUDA(cudaMalloc(&db, sizeof(int64_t) * nb));

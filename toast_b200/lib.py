@@ -118,6 +118,12 @@ PROTOTYPES = {
     "tb_lhs_pass2_cov": (INT, [P, P, P, P, P]),
     "tb_cov_apply_pad": (INT, [I64, P, P, P, P]),
     "tb_lhs_pass2_pad": (INT, [P, P, P, P, P, P]),
+    "tb_bx_block_pixels": (INT, []),
+    "tb_obs_blocked": (INT, [P]),
+    "tb_obs_blocked_stats": (INT, [P, P, P, P, P]),
+    "tb_bx_pass1": (INT, [P, P, P, P, INT, I64, P]),
+    "tb_bx_pass2": (INT, [P, P, P, I64, P]),
+    "tb_bx_fused": (INT, [P, P, P, P, P, P, P]),
     "tb_rhs_project": (INT, [P, P, P, P, P, INT, P]),
     "tb_bin_signal": (INT, [P, P, P, INT, P]),
     "tb_offset_prior_create": (P, [ct.POINTER(tb_offset_prior_desc)]),

@@ -328,11 +328,12 @@ class SymmPeerMap:
             pass
 
 
-def pipeline_chunk_bounds(n_pix, world, n_chunks):
+def pipeline_chunk_bounds(n_pix, world, n_chunks, align=1):
     """Local-pixel bounds of the chunks the multi-GPU pipeline works in: every chunk but the last
-    is a multiple of 256 x world pixels (the reduction kernel's tile x one slice per rank), the
-    last one takes the remainder.  None when fewer than two chunks are possible."""
-    unit = 256 * world
+    is a multiple of 256 x world pixels (the reduction kernel's tile x one slice per rank) and of
+    ``align`` (the pixel block of the block-ordered passes), the last one takes the remainder.
+    None when fewer than two chunks are possible."""
+    unit = int(np.lcm(256 * world, max(1, int(align))))
     units = n_pix // unit
     n_chunks = max(1, min(int(n_chunks), units))
     if n_chunks < 2:
@@ -402,12 +403,15 @@ class Destriper:
         # Measured on 2 GPUs: 1.46-1.54 ms against 1.69 ms per iteration with 4 chunks, slower
         # than serial with 8-16.
         self.fuse_cov = _os.environ.get("TB_FUSE_COV", "0") == "1"
+        # one observation on one GPU: pass 1 -> covariance -> pass 2 inside one kernel
+        self.fuse_lhs = _os.environ.get("TB_FUSE_LHS", "1") != "0"
         self.pad_map = _os.environ.get("TB_PADMAP", "0") == "1"
         self._binned4 = None
         # EXPERIMENTAL: copy-engine form of the chunk reduction (needs the symmetric-memory map)
         self.reduce_ce = (_os.environ.get("TB_REDUCE", "") == "ce"
                           and isinstance(self.peer, SymmPeerMap))
         self.pipeline = False
+        self.blocked = False
         self.pipe_tune_ms = None
         self._ctas_set = None
         mode = _os.environ.get("TB_PIPE_CHUNKS", "auto")
@@ -432,15 +436,24 @@ class Destriper:
             return 0
         return min(int(self.lib.tb_obs_sorted_passes(o.handle().h)) for o in self.obs)
 
+    def _blocked(self):
+        """True when the passes of every observation run on the block-ordered crossing list
+        (shared-memory map tiles, tb_blocked.cu)."""
+        if self.regen or self.lib.tb_get_option(b"blocked") != 1:
+            return False
+        return all(bool(self.lib.tb_obs_blocked(o.handle().h)) for o in self.obs)
+
     def _setup_pipeline(self, n_chunks):
-        """Multi-GPU with both passes pixel-sorted: cut the local map into pixel chunks so that
-        pass 1 of chunk c+1 and pass 2 of chunk c-1 overlap the NVLink reduction of chunk c
-        (the reduction runs on its own high-priority stream)."""
+        """Multi-GPU with both passes in pixel (block) order: cut the local map into pixel chunks
+        so that pass 1 of chunk c+1 and pass 2 of chunk c-1 overlap the NVLink reduction of chunk
+        c (the reduction runs on its own high-priority stream)."""
         import os as _os
-        if self.peer is None or n_chunks < 2 or self._sorted_passes() != 2:
+        self.blocked = self._blocked()
+        if self.peer is None or n_chunks < 2 or not (self.blocked or self._sorted_passes() == 2):
             return
-        bounds = pipeline_chunk_bounds(self.n_local_submap * self.n_pix_submap, self.world,
-                                       n_chunks)
+        bounds = pipeline_chunk_bounds(
+            self.n_local_submap * self.n_pix_submap, self.world, n_chunks,
+            align=int(self.lib.tb_bx_block_pixels()) if self.blocked else 1)
         if bounds is None:
             return
         n_chunks = len(bounds) - 1
@@ -549,13 +562,20 @@ class Destriper:
             e1.record(stream)
             timeline.append((label, e0, e1))
 
-        timed("zero", main, lambda: (self.zmap.zero_(), amps_out.zero_()))
+        blocked = getattr(self, "blocked", False)
+        # (the block-ordered pass 1 writes every block of the map: no zero-fill)
+        timed("zero", main, lambda: (None if blocked else self.zmap.zero_(), amps_out.zero_()))
         for c in range(self.n_chunks):
             def p1(c=c):
-                for o in self.obs:
-                    L.check(self.lib.tb_lhs_pass1_chunk(o.handle().h, L.ptr(amps_in),
-                                                        L.ptr(self.amp_flags), L.ptr(self.zmap),
-                                                        c, ms))
+                for k, o in enumerate(self.obs):
+                    if blocked:
+                        L.check(self.lib.tb_bx_pass1(o.handle().h, L.ptr(amps_in),
+                                                     L.ptr(self.amp_flags), L.ptr(self.zmap),
+                                                     1 if k > 0 else 0, c, ms))
+                    else:
+                        L.check(self.lib.tb_lhs_pass1_chunk(o.handle().h, L.ptr(amps_in),
+                                                            L.ptr(self.amp_flags),
+                                                            L.ptr(self.zmap), c, ms))
             timed(f"pass1[{c}]", main, p1)
             self.ev_binned[c].record(main)
             self.comm_stream.wait_event(self.ev_binned[c])
@@ -575,8 +595,12 @@ class Destriper:
 
             def p2(c=c):
                 for o in self.obs:
-                    L.check(self.lib.tb_lhs_pass2_chunk(o.handle().h, L.ptr(self.zmap),
-                                                        L.ptr(amps_out), c, ms))
+                    if blocked:
+                        L.check(self.lib.tb_bx_pass2(o.handle().h, L.ptr(self.zmap),
+                                                     L.ptr(amps_out), c, ms))
+                    else:
+                        L.check(self.lib.tb_lhs_pass2_chunk(o.handle().h, L.ptr(self.zmap),
+                                                            L.ptr(amps_out), c, ms))
             timed(f"pass2[{c}]", main, p2)
         return amps_out
 
@@ -625,6 +649,8 @@ class Destriper:
             return self._add_prior(amps_in, amps_out)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers is not None \
             else None
+        if self._blocked():
+            return self._lhs_blocked(amps_in, amps_out, ev, timers)
         self.zmap.zero_()
         if ev:
             ev[0].record()
@@ -676,6 +702,40 @@ class Destriper:
             L.check(self.lib.tb_lhs_pass2(o.handle().h, None if reuse else L.ptr(amps_in),
                                           L.ptr(self.amp_flags), L.ptr(self.zmap),
                                           L.ptr(amps_out), self.regen, None))
+        if ev:
+            ev[3].record()
+            timers.append(ev)
+        return self._add_prior(amps_in, amps_out)
+
+    def _lhs_blocked(self, amps_in, amps_out, ev, timers):
+        """The LHS on the block-ordered crossing list.  One observation on one GPU: ONE kernel
+        (pass 1 -> covariance -> pass 2 with the map tile in shared memory); otherwise pass 1
+        writes the map (no zero-fill, no atomics), the reduction + covariance follow, and pass 2
+        reads it back tile by tile."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        fused = self.world == 1 and len(self.obs) == 1 and self.fuse_lhs
+        amps_out.zero_()
+        if ev:
+            ev[0].record()
+        if fused:
+            if ev:
+                ev[1].record()
+                ev[2].record()
+            L.check(self.lib.tb_bx_fused(self.obs[0].handle().h, L.ptr(amps_in),
+                                         L.ptr(self.amp_flags), L.ptr(self.cov), L.ptr(self.zmap),
+                                         L.ptr(amps_out), st))
+        else:
+            for k, o in enumerate(self.obs):
+                L.check(self.lib.tb_bx_pass1(o.handle().h, L.ptr(amps_in), L.ptr(self.amp_flags),
+                                             L.ptr(self.zmap), 1 if k > 0 else 0, -1, st))
+            if ev:
+                ev[1].record()
+            self.reduce_and_apply_cov()
+            if ev:
+                ev[2].record()
+            for o in self.obs:
+                L.check(self.lib.tb_bx_pass2(o.handle().h, L.ptr(self.zmap), L.ptr(amps_out), -1,
+                                             st))
         if ev:
             ev[3].record()
             timers.append(ev)
