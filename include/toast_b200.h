@@ -317,8 +317,8 @@ int tb_lhs_pass2_pad(const tb_obs *obs, const double *amplitudes, const uint8_t 
  *                amplitudes; with accumulate = 0 EVERY block of the local map is written, no
  *                zero-fill is needed.  chunk < 0: the whole map; chunk >= 0: the pixel chunk set
  *                by tb_obs_set_pixel_chunks (bounds must be multiples of the block size).
- *   tb_bx_pass2  projects the binned map for the amplitudes of the preceding tb_bx_pass1 /
- *                tb_bx_fused call and ADDS to amplitudes_out.
+ *   tb_bx_pass2  projects the binned map for the amplitudes of the preceding tb_bx_pass1 call
+ *                (whole map or one pixel chunk) and ADDS to amplitudes_out.
  *   tb_bx_fused  one observation on one GPU: pass 1 -> covariance_apply (toast_map_cov.cpp:471-528)
  *                -> pass 2 inside one kernel, the map never leaves the SM.  zmap_scratch
  *                ([n_local_pix, 3]) is only touched for blocks that had to be cut into several

@@ -64,7 +64,7 @@ def _worker(rank, world, port, out):
     try:
         from toast_b200.solver import PeerMap
 
-        n_loc, nps = 7, 3072
+        n_loc, nps = 67, 3072   # 205 824 pixels: several tiles per rank slice at every world size
         n_pix = n_loc * nps
         g = torch.Generator(device="cuda")
         g.manual_seed(100 + rank)
@@ -116,14 +116,24 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_peer_reduction_matches_nccl():
+def _need(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_peer_reduction_matches_nccl(world):
+    """tb_map_reduce_cov in its three forms (CUDA-IPC P2P, NVLS multimem on symmetric memory,
+    P2P on symmetric memory) against NCCL all-reduce + cov_apply, at every world size the
+    box offers (the reference: PixelData.sync_allreduce + covariance_apply, pixels.py:710-779,
+    covariance.py:262-306)."""
     import torch.multiprocessing as mp
 
+    _need(world)
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
     err, err_mc, err_sp = out.get(timeout=300)
@@ -133,6 +143,11 @@ def test_two_rank_peer_reduction_matches_nccl():
     assert err < 1e-14
     # -1 = the box has no NVLS multicast (reported, not a failure of the kernels)
     assert err_mc < 1e-14 and err_sp < 1e-14
+
+
+def _solve_shape(world):
+    # one detector pair per rank at least; world 2 keeps the round-1 case (3 detectors per rank)
+    return (6 if world == 2 else 2 * world), 24000, 64
 
 
 def _solve_worker(rank, world, port, out):
@@ -148,7 +163,7 @@ def _solve_worker(rank, world, port, out):
         from toast_b200 import lib as L_
         from toast_b200.solver import DeviceObservation, Destriper
 
-        n_det, n_samp, nside = 6, 24000, 64
+        n_det, n_samp, nside = _solve_shape(world)
         obs = S.make_observation("c4", n_det=n_det, n_samp=n_samp, nside=nside, eps_max=0.03)
         # the full problem (setup stages from the oracle) ...
         pb = O.build_problem(obs, O)
@@ -202,17 +217,18 @@ def _solve_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_destriper_matches_single_rank_oracle():
-    """Detector-sharded solve on 2 GPUs (fused peer reduction and NCCL) against the oracle's
-    single-process solve of the whole problem: RHS to 1e-10, residual history per the
-    reproducibility envelope."""
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_destriper_matches_single_rank_oracle(world):
+    """Detector-sharded solve on 2 / 4 / 8 GPUs (fused peer reduction and NCCL) against the
+    oracle's single-process solve of the whole problem: RHS to 1e-10, residual history per the
+    reproducibility envelope, pipelined LHS == phase-by-phase LHS."""
     import torch.multiprocessing as mp
 
+    _need(world)
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_solve_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_solve_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
     rhs_f, rhs_n, rhs_ref, hist_f, hist_n, hist_ref, pipe_err = out.get(timeout=600)
@@ -222,8 +238,9 @@ def test_two_rank_destriper_matches_single_rank_oracle():
     assert pipe_err < 1e-12, f"pipelined vs phase-by-phase LHS: {pipe_err}"
     H.assert_close_norm(rhs_f, rhs_ref, what="RHS shard (fused)")
     H.assert_close_norm(rhs_n, rhs_ref, what="RHS shard (NCCL)")
-    obs = S.make_observation("c4", n_det=6, n_samp=24000, nside=64, eps_max=0.03)
+    n_det, n_samp, nside = _solve_shape(world)
+    obs = S.make_observation("c4", n_det=n_det, n_samp=n_samp, nside=nside, eps_max=0.03)
     pb = O.build_problem(obs, O)
     env = H.pcg_envelope(pb, O.solver_rhs(pb, O, obs["signal"]), 8)
-    H.assert_history_matches(hist_f, hist_ref, env, what="2-rank fused")
-    H.assert_history_matches(hist_n, hist_ref, env, what="2-rank NCCL")
+    H.assert_history_matches(hist_f, hist_ref, env, what=f"{world}-rank fused")
+    H.assert_history_matches(hist_n, hist_ref, env, what=f"{world}-rank NCCL")

@@ -348,7 +348,7 @@ def test_pixel_chunked_passes_sum_to_the_whole():
         assert_close_norm(qh, ref, what=f"chunked blocked LHS ({n_chunks} chunks)")
         assert np.all(qh[pb.amp_flags != 0] == 0.0)
     # bounds off the block grid: the chunked block-ordered calls are refused
-    b = np.array([0, 256, n_pix], dtype=np.int64)
+    b = np.array([0, bp // 2, n_pix], dtype=np.int64)
     L.check(lib.tb_obs_set_pixel_chunks(h, 2, L.ptr(b)))
     with pytest.raises(RuntimeError):
         L.check(lib.tb_bx_pass1(h, L.ptr(a_d), L.ptr(ds.amp_flags), L.ptr(ds.zmap), 0, 0, None))

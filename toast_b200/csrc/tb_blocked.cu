@@ -41,12 +41,17 @@ int g_use_bx = 1; // tb_set_option("blocked", 0/1)
 
 namespace {
 
-constexpr int kBxShift = 11;
-constexpr int kBxPix = 1 << kBxShift;   // pixels per block: 3 x 2048 doubles = 48 KB of shared memory
-constexpr int kBxUnitMax = 16384;       // records per work unit
+#ifndef TB_BX_SHIFT
+#define TB_BX_SHIFT 8
+#endif
 #ifndef TB_BX_CTAS
 #define TB_BX_CTAS 4
 #endif
+constexpr int kBxShift = TB_BX_SHIFT;
+constexpr int kBxPix = 1 << kBxShift;   // pixels per block: 3 x kBxPix doubles of shared memory per warp
+constexpr int kBxUnitMax = 16384;       // records per work unit (one warp)
+constexpr int kBxRowBits = 32 - (kBxShift + 12); // free bits of the first record word
+static_assert(kBxRowBits >= 1, "pixel | n0 | n1 must fit one int");
 
 // ---- build ---------------------------------------------------------------------------------------
 // keys / values for the stable sort by block.  value = record index | mode << 30 (0: as recorded,
@@ -88,7 +93,7 @@ k_bx_keys(const int4 *__restrict__ xrec, int64_t n_rec, int32_t n_blocks, int32_
 
 __global__ void __launch_bounds__(kThreads)
 k_bx_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
-            const int32_t *__restrict__ vals, int64_t n_sorted, int64_t n_amp_det,
+            const int32_t *__restrict__ vals, int64_t n_sorted, int64_t n_amp_det, int row_in_rec,
             int2 *__restrict__ brec, double2 *__restrict__ bqu) {
     for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < n_sorted;
          j += (int64_t)gridDim.x * kThreads) {
@@ -99,7 +104,9 @@ k_bx_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
         const int n0 = (r.x >= 0 && mode != 2) ? n : 0;
         const int n1 = (r.y >= 0 && mode != 1 && (mode == 2 || r.x < 0 || r.y == r.x)) ? n : 0;
         const int32_t pix = (mode == 2 || r.x < 0) ? r.y : r.x;
-        brec[j] = make_int2((pix & (kBxPix - 1)) | (n0 << kBxShift) | (n1 << (kBxShift + 6)),
+        // (the row rides in the upper bits when it fits: pass 2 then needs no division)
+        brec[j] = make_int2((pix & (kBxPix - 1)) | (n0 << kBxShift) | (n1 << (kBxShift + 6)) |
+                                (row_in_rec ? (row << (kBxShift + 12)) : 0),
                             (int32_t)((int64_t)row * n_amp_det + r.w));
         bqu[j] = xqu[i];
     }
@@ -120,202 +127,281 @@ __global__ void k_bx_block_starts(const int32_t *__restrict__ keys, int64_t n, i
 }
 
 // ---- the passes ----------------------------------------------------------------------------------
+// Amplitudes travel through a per-pass scratch array laid out by ROW of the crossing list and
+// baseline, so that a record addresses it with its `slot` alone:
+//   ascaled[slot] = {a0 w0, a1 w1, w0, w1}   amplitude x detector weight and the weight itself of
+//                                            the two detectors of a pair (32 bytes = one sector;
+//                                            unpaired rows: {a w, w}); flagged baselines and the
+//                                            missing partner of an odd detector count hold zeros,
+//                                            so the passes need neither flag tests nor row lookups
+__global__ void __launch_bounds__(kThreads)
+k_bx_prescale(int paired, int n_det, int64_t nad, const int64_t *__restrict__ amp_offsets,
+              const double *__restrict__ det_scale, const double *__restrict__ amps,
+              const uint8_t *__restrict__ aflags, double *__restrict__ ascaled) {
+    const int row = blockIdx.x;
+    const int d0 = paired ? 2 * row : row, d1 = d0 + 1;
+    const bool has1 = paired && d1 < n_det;
+    const int64_t o0 = __ldg(amp_offsets + d0), o1 = has1 ? __ldg(amp_offsets + d1) : 0;
+    const double w0 = __ldg(det_scale + d0), w1 = has1 ? __ldg(det_scale + d1) : 0.0;
+    for (int64_t i = (int64_t)blockIdx.y * kThreads + threadIdx.x; i < nad;
+         i += (int64_t)gridDim.y * kThreads) {
+        const bool g0 = __ldg(aflags + o0 + i) == 0;
+        const double a0 = g0 ? __ldg(amps + o0 + i) * w0 : 0.0;
+        if (paired) {
+            const bool g1 = has1 && __ldg(aflags + o1 + i) == 0;
+            const double a1 = g1 ? __ldg(amps + o1 + i) * w1 : 0.0;
+            double2 *dst = reinterpret_cast<double2 *>(ascaled) + 2 * ((int64_t)row * nad + i);
+            dst[0] = make_double2(a0, a1);
+            dst[1] = make_double2(g0 ? w0 : 0.0, g1 ? w1 : 0.0);
+        } else {
+            reinterpret_cast<double2 *>(ascaled)[(int64_t)row * nad + i] =
+                make_double2(a0, g0 ? w0 : 0.0);
+        }
+    }
+}
+
 struct BxArgs {
     const int4 *units;        // {block, first record, end record, multi}
     const int2 *brec;
     const double2 *bqu;
-    const double *dscaled;    // prescaled amplitudes (k_amp_prescale)
+    const double *ascaled;    // k_bx_prescale
+    double *out;              // pass 2 / fused: amplitudes (REDs)
+    const int64_t *amp_offsets;
+    int32_t nad, n_det;
+    int row_in_rec;           // the record's first word carries the row in its upper bits
     double4 cst;              // {cal0, cal1, A, B} when uniform
     const double4 *table;     // per row otherwise
     double inv_nad;           // 1 / n_amp_det
-    int32_t nad;
-    const double *det_scale;
-    const int64_t *amp_offsets;
-    int n_det;
     int64_t n_pix;            // local map size
     double *zmap;             // pass 1: output;  pass 2: the binned map;  fused: unused
     const double *cov;        // fused: [n_pix, 6]
-    double *out;              // pass 2 / fused: amplitudes
     int accumulate;           // pass 1: add to zmap (REDs) even for single-unit blocks
 };
 
-struct BxRow {
-    double4 c;
-    int row;
+// Every WARP owns one pixel block at a time and keeps the block's 3 x kBxPix map values in its own
+// slice of shared memory, so the accumulation needs no atomics at all: lanes of one warp that hit
+// the same pixel in the same step (found with match.any) take turns, everything else is a plain
+// shared-memory read-modify-write.  (fp64 / fp32 atomicAdd on shared memory is a compare-and-swap
+// loop on this architecture -- ATOMS.CAST.SPIN -- and a CTA-wide tile with such atomics left the
+// kernel bound by the shared-memory pipe at 80 % utilisation: profiles/r2_ncu_blocked.txt.)  There
+// is no block-level barrier anywhere: a warp streams its unit's records with a register software
+// pipeline (records two steps ahead, amplitude gathers one step ahead).
+constexpr int kBxWarps = kThreads / 32;
+
+struct BxRec {
+    int2 r;     // {pixel | n0 << kBxShift | n1 << (kBxShift + 6), slot}
+    double2 qu; // (sum Q, sum U)
 };
+template <bool KEEP_IN_L2>
+__device__ __forceinline__ BxRec bx_load(const BxArgs &a, int i, int end, int lane) {
+    BxRec x;
+    x.r = make_int2(0, -1 - lane); // idle lanes: n0 = n1 = 0, distinct negative slots
+    x.qu = make_double2(0.0, 0.0);
+    if (i < end) {
+        x.r = KEEP_IN_L2 ? __ldg(a.brec + i) : __ldcs(a.brec + i);
+        x.qu = KEEP_IN_L2 ? __ldg(a.bqu + i) : __ldcs(a.bqu + i);
+    }
+    return x;
+}
+
+struct BxAmp {
+    double2 t; // a0 w0, a1 w1
+    double2 w; // w0, w1 (pass 2 only)
+};
+template <bool PAIRED, bool NEED_W>
+__device__ __forceinline__ BxAmp bx_gather(const BxArgs &a, int32_t slot) {
+    BxAmp g;
+    g.t = g.w = make_double2(0.0, 0.0);
+    if (slot >= 0) {
+        if (PAIRED) {
+            const double2 *p = reinterpret_cast<const double2 *>(a.ascaled) + 2 * (int64_t)slot;
+            g.t = __ldg(p);
+            if (NEED_W) g.w = __ldg(p + 1);
+        } else {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(a.ascaled) + slot);
+            g.t.x = v.x;
+            g.w.x = v.y;
+        }
+    }
+    return g;
+}
 
 template <bool UNIFORM>
-__device__ __forceinline__ BxRow bx_row(const BxArgs &a, int32_t slot) {
-    BxRow r;
-    r.row = (int)fast_div((int64_t)slot, a.inv_nad);
-    r.c = a.cst;
-    if (!UNIFORM) {
-        const double2 *tp = reinterpret_cast<const double2 *>(a.table + r.row);
-        const double2 ca = __ldg(tp), cb = __ldg(tp + 1);
-        r.c = make_double4(ca.x, ca.y, cb.x, cb.y);
-    }
-    return r;
+__device__ __forceinline__ double4 bx_consts(const BxArgs &a, int32_t slot) {
+    if (UNIFORM) return a.cst;
+    const int row = (int)fast_div((int64_t)(slot < 0 ? 0 : slot), a.inv_nad);
+    const double2 *tp = reinterpret_cast<const double2 *>(a.table + row);
+    const double2 ca = __ldg(tp), cb = __ldg(tp + 1);
+    return make_double4(ca.x, ca.y, cb.x, cb.y);
 }
 
-// amplitude x detector weight of both detectors of the record's row (0 if flagged / absent)
-template <bool PAIRED>
-__device__ __forceinline__ double2 bx_amps(const BxArgs &a, int32_t slot, int n0, int n1,
-                                           bool &ok0, bool &ok1) {
-    double2 av = make_double2(0.0, 0.0);
-    if (PAIRED) av = __ldg(reinterpret_cast<const double2 *>(a.dscaled) + slot);
-    else av.x = __ldg(a.dscaled + slot);
-    ok0 = n0 != 0 && !amp_is_flagged(av.x);
-    ok1 = PAIRED && n1 != 0 && !amp_is_flagged(av.y);
-    if (!ok0) av.x = 0.0;
-    if (!ok1) av.y = 0.0;
-    return av;
-}
-
-// pass 1 over the records [first, end) of one unit: tile += a w (n cal, sum Q, sum U)
+// pass 1 over the records [first, end) of the warp's unit: tile += a w (n cal, sum Q, sum U)
 template <bool UNIFORM, bool PAIRED, bool KEEP_IN_L2>
-__device__ __forceinline__ void bx_accumulate(const BxArgs &a, double *tile, int first, int end) {
-#pragma unroll 2
-    for (int i = first + (int)threadIdx.x; i < end; i += kThreads) {
-        const int2 r = KEEP_IN_L2 ? __ldg(a.brec + i) : __ldcs(a.brec + i);
-        const double2 qu = KEEP_IN_L2 ? __ldg(a.bqu + i) : __ldcs(a.bqu + i);
-        const int p = r.x & (kBxPix - 1);
-        const int n0 = (r.x >> kBxShift) & 63, n1 = (r.x >> (kBxShift + 6)) & 63;
-        double4 c = a.cst;
-        if (!UNIFORM) c = bx_row<false>(a, r.y).c;
-        bool ok0, ok1;
-        const double2 t = bx_amps<PAIRED>(a, r.y, n0, n1, ok0, ok1);
-        if (!(ok0 || ok1)) continue;
-        const double v0 = t.x * (c.x * (double)n0) + t.y * (c.y * (double)n1);
-        const double v1 = t.x * qu.x + t.y * (c.z * qu.x - c.w * qu.y);
-        const double v2 = t.x * qu.y + t.y * (c.w * qu.x + c.z * qu.y);
+__device__ __forceinline__ void bx_accumulate(const BxArgs &a, double *tile, int first, int end,
+                                              int lane) {
+    if (first >= end) return;
+    BxRec cur = bx_load<KEEP_IN_L2>(a, first + lane, end, lane);
+    BxRec nxt = bx_load<KEEP_IN_L2>(a, first + 32 + lane, end, lane);
+    BxAmp gc = bx_gather<PAIRED, false>(a, cur.r.y);
+    for (int base = first; base < end; base += 32) {
+        // two steps ahead: records; one step ahead: the amplitude gather
+        const BxRec nn = bx_load<KEEP_IN_L2>(a, base + 64 + lane, end, lane);
+        const BxAmp gn = bx_gather<PAIRED, false>(a, nxt.r.y);
+        const int p = cur.r.x & (kBxPix - 1);
+        const int n0 = (cur.r.x >> kBxShift) & 63, n1 = (cur.r.x >> (kBxShift + 6)) & 63;
+        const double4 c = bx_consts<UNIFORM>(a, cur.r.y);
+        const double t0 = n0 ? gc.t.x : 0.0;
+        const double t1 = (PAIRED && n1) ? gc.t.y : 0.0;
+        const bool contrib = t0 != 0.0 || t1 != 0.0;
+        const double v0 = t0 * (c.x * (double)n0) + t1 * (c.y * (double)n1);
+        const double v1 = t0 * cur.qu.x + t1 * (c.z * cur.qu.x - c.w * cur.qu.y);
+        const double v2 = t0 * cur.qu.y + t1 * (c.w * cur.qu.x + c.z * cur.qu.y);
+        // lanes of this step that hit the same pixel take turns (typically two records of one
+        // crossing cut by a baseline boundary); all others update their pixel at once
+        const unsigned same = __match_any_sync(0xffffffffu, contrib ? p : kBxPix + lane);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        const int rounds = __reduce_max_sync(0xffffffffu, rank);
         double *z = tile + 3 * p;
-        atomicAdd(z, v0);
-        atomicAdd(z + 1, v1);
-        atomicAdd(z + 2, v2);
+        for (int r = 0; r <= rounds; ++r) {
+            if (contrib && rank == r) {
+                z[0] += v0;
+                z[1] += v1;
+                z[2] += v2;
+            }
+            __syncwarp();
+        }
+        cur = nxt;
+        nxt = nn;
+        gc = gn;
     }
 }
 
-// pass 2 over the records of one unit: out[baseline] += w (n a - (n cal, sum Q, sum U) . m), one
-// RED per run of records that share the baseline (they are consecutive: (row, time) order)
+// pass 2 over the records of the warp's unit: qscaled[slot] += w (n a - (n cal, sum Q, sum U) . m),
+// one RED pair per run of records that share the baseline (consecutive in (row, time) order)
 template <bool UNIFORM, bool PAIRED>
-__device__ __forceinline__ void bx_project(const BxArgs &a, const double *tile, int first, int end) {
-    const int lane = threadIdx.x & 31;
-    for (int base = first; base < end; base += kThreads) { // uniform trip count: shuffles inside
-        const int i = base + (int)threadIdx.x;
-        int64_t key = -1 - lane; // idle lanes: distinct keys, nothing to add
+__device__ __forceinline__ void bx_project(const BxArgs &a, const double *tile, int first, int end,
+                                           int lane) {
+    if (first >= end) return;
+    BxRec cur = bx_load<false>(a, first + lane, end, lane);
+    BxRec nxt = bx_load<false>(a, first + 32 + lane, end, lane);
+    BxAmp gc = bx_gather<PAIRED, true>(a, cur.r.y);
+    for (int base = first; base < end; base += 32) {
+        const BxRec nn = bx_load<false>(a, base + 64 + lane, end, lane);
+        const BxAmp gn = bx_gather<PAIRED, true>(a, nxt.r.y);
+        const int p = cur.r.x & (kBxPix - 1);
+        const int n0 = (cur.r.x >> kBxShift) & 63, n1 = (cur.r.x >> (kBxShift + 6)) & 63;
+        const double4 c = bx_consts<UNIFORM>(a, cur.r.y);
+        const double m0 = tile[3 * p], m1 = tile[3 * p + 1], m2 = tile[3 * p + 2];
         double val0 = 0.0, val1 = 0.0;
-        int row = 0, arel = 0;
-        bool ok0 = false, ok1 = false;
-        if (i < end) {
-            const int2 r = __ldcs(a.brec + i);
-            const double2 qu = __ldcs(a.bqu + i);
-            const int p = r.x & (kBxPix - 1);
-            const int n0 = (r.x >> kBxShift) & 63, n1 = (r.x >> (kBxShift + 6)) & 63;
-            const BxRow br = bx_row<UNIFORM>(a, r.y);
-            const double4 c = br.c;
-            row = br.row;
-            arel = r.y - row * a.nad;
-            key = r.y;
-            const double2 av = bx_amps<PAIRED>(a, r.y, n0, n1, ok0, ok1);
-            const double m0 = tile[3 * p], m1 = tile[3 * p + 1], m2 = tile[3 * p + 2];
-            const int d0 = PAIRED ? 2 * row : row;
-            if (ok0) {
-                double sc = 0.0;
-                sc += (c.x * (double)n0) * m0;
-                sc += qu.x * m1;
-                sc += qu.y * m2;
-                val0 = (double)n0 * av.x - sc * __ldg(a.det_scale + d0);
-            }
-            if (PAIRED && ok1) {
-                const double q1 = c.z * qu.x - c.w * qu.y, u1 = c.w * qu.x + c.z * qu.y;
-                double sc = 0.0;
-                sc += (c.y * (double)n1) * m0;
-                sc += q1 * m1;
-                sc += u1 * m2;
-                val1 = (double)n1 * av.y - sc * __ldg(a.det_scale + d0 + 1);
-            }
+        if (n0) {
+            double sc = 0.0;
+            sc += (c.x * (double)n0) * m0;
+            sc += cur.qu.x * m1;
+            sc += cur.qu.y * m2;
+            val0 = (double)n0 * gc.t.x - sc * gc.w.x;
         }
-        const Runs rr = find_runs<8>(key, lane);
+        if (PAIRED && n1) {
+            const double q1 = c.z * cur.qu.x - c.w * cur.qu.y, u1 = c.w * cur.qu.x + c.z * cur.qu.y;
+            double sc = 0.0;
+            sc += (c.y * (double)n1) * m0;
+            sc += q1 * m1;
+            sc += u1 * m2;
+            val1 = (double)n1 * gc.t.y - sc * gc.w.y;
+        }
+        const Runs rr = find_runs32<8>(cur.r.y, lane);
         val0 = seg_sum<8>(val0, rr);
         if (PAIRED) val1 = seg_sum<8>(val1, rr);
-        if (rr.is_tail && i < end) {
+        if (rr.is_tail && cur.r.y >= 0) {
+            const int row = a.row_in_rec ? (int)((unsigned)cur.r.x >> (kBxShift + 12))
+                                         : (int)fast_div((int64_t)cur.r.y, a.inv_nad);
+            const int arel = cur.r.y - row * a.nad;
             const int d0 = PAIRED ? 2 * row : row;
             if (val0 != 0.0) atomicAdd(a.out + __ldg(a.amp_offsets + d0) + arel, val0);
             if (PAIRED && val1 != 0.0)
                 atomicAdd(a.out + __ldg(a.amp_offsets + d0 + 1) + arel, val1);
         }
+        cur = nxt;
+        nxt = nn;
+        gc = gn;
     }
 }
 
-// MODE 0: pass 1 (tile -> zmap), 1: pass 2 (binned map -> tile -> amplitudes), 2: fused
+// MODE 0: pass 1 (tile -> zmap), 1: pass 2 (binned map -> tile -> amplitudes), 2: fused.
+// One warp per work unit; grid = ceil(n_units / kBxWarps).
 template <int MODE, bool UNIFORM, bool PAIRED>
 __global__ void __launch_bounds__(kThreads, TB_BX_CTAS)
-k_bx(const BxArgs a) {
-    __shared__ __align__(16) double tile[3 * kBxPix];
-    const int4 u = __ldg(a.units + blockIdx.x);
+k_bx(const BxArgs a, int64_t n_units) {
+    __shared__ __align__(16) double tiles[kBxWarps][3 * kBxPix];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ui = (int64_t)blockIdx.x * kBxWarps + warp;
+    if (ui >= n_units) return;
+    const int4 u = __ldg(a.units + ui);
+    double *tile = tiles[warp];
+    double2 *tile2 = reinterpret_cast<double2 *>(tile);
     const int64_t g0 = (int64_t)u.x * (3 * kBxPix);          // first map double of the block
     const int64_t g_end = 3 * a.n_pix;
-    double2 *tile2 = reinterpret_cast<double2 *>(tile);
-    if (MODE == 1) {
+    if constexpr (MODE == 1) {
         const double2 *src = reinterpret_cast<const double2 *>(a.zmap + g0);
-        for (int k = threadIdx.x; k < 3 * kBxPix / 2; k += kThreads) {
+#pragma unroll 4
+        for (int k = lane; k < 3 * kBxPix / 2; k += 32) {
             const int64_t g = g0 + 2 * k;
             double2 v = make_double2(0.0, 0.0);
             if (g + 1 < g_end) v = __ldcs(src + k);
             else if (g < g_end) v.x = __ldcs(a.zmap + g);
             tile2[k] = v;
         }
+        __syncwarp();
+        bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z, lane);
     } else {
-        for (int k = threadIdx.x; k < 3 * kBxPix / 2; k += kThreads)
-            tile2[k] = make_double2(0.0, 0.0);
-    }
-    __syncthreads();
-    if (MODE == 1) {
-        bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z);
-        return;
-    }
-    bx_accumulate<UNIFORM, PAIRED, MODE == 2>(a, tile, u.y, u.z);
-    __syncthreads();
-    if (MODE == 0) {
-        if (u.w == 0 && !a.accumulate) {
-            // the only unit of its block: the tile IS the block of the map
-            double2 *dst = reinterpret_cast<double2 *>(a.zmap + g0);
-            for (int k = threadIdx.x; k < 3 * kBxPix / 2; k += kThreads) {
-                const int64_t g = g0 + 2 * k;
-                if (g + 1 < g_end) __stcs(dst + k, tile2[k]);
-                else if (g < g_end) a.zmap[g] = tile2[k].x;
+#pragma unroll 4
+        for (int k = lane; k < 3 * kBxPix / 2; k += 32) tile2[k] = make_double2(0.0, 0.0);
+        __syncwarp();
+        bx_accumulate<UNIFORM, PAIRED, MODE == 2>(a, tile, u.y, u.z, lane);
+        __syncwarp();
+        if constexpr (MODE == 0) {
+            if (u.w == 0 && !a.accumulate) {
+                // the only unit of its block: the tile IS the block of the map
+                double2 *dst = reinterpret_cast<double2 *>(a.zmap + g0);
+#pragma unroll 4
+                for (int k = lane; k < 3 * kBxPix / 2; k += 32) {
+                    const int64_t gg = g0 + 2 * k;
+                    if (gg + 1 < g_end) __stcs(dst + k, tile2[k]);
+                    else if (gg < g_end) a.zmap[gg] = tile2[k].x;
+                }
+            } else {
+                for (int k = lane; k < 3 * kBxPix; k += 32) {
+                    const double v = tile[k];
+                    if (v != 0.0 && g0 + k < g_end) atomicAdd(a.zmap + g0 + k, v);
+                }
             }
         } else {
-            for (int k = threadIdx.x; k < 3 * kBxPix; k += kThreads) {
-                const double v = tile[k];
-                if (v != 0.0 && g0 + k < g_end) atomicAdd(a.zmap + g0 + k, v);
+            // fused: m = C z in place (toast_map_cov.cpp:509-517 operation order, as k_cov_apply)
+            if (u.z > u.y) {
+                for (int p = lane; p < kBxPix; p += 32) {
+                    const int64_t gp = (int64_t)u.x * kBxPix + p;
+                    const double z0 = tile[3 * p], z1 = tile[3 * p + 1], z2 = tile[3 * p + 2];
+                    if (gp >= a.n_pix || (z0 == 0.0 && z1 == 0.0 && z2 == 0.0)) continue;
+                    const double2 *cm = reinterpret_cast<const double2 *>(a.cov + 6 * gp);
+                    const double2 ca = __ldcs(cm), cb = __ldcs(cm + 1), cc = __ldcs(cm + 2);
+                    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+                    m0 += ca.x * z0;
+                    m0 += ca.y * z1;
+                    m1 += ca.y * z0;
+                    m0 += cb.x * z2;
+                    m2 += cb.x * z0;
+                    m1 += cb.y * z1;
+                    m1 += cc.x * z2;
+                    m2 += cc.x * z1;
+                    m2 += cc.y * z2;
+                    tile[3 * p] = m0;
+                    tile[3 * p + 1] = m1;
+                    tile[3 * p + 2] = m2;
+                }
+                __syncwarp();
+                bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z, lane);
             }
         }
-        return;
     }
-    // fused: m = C z in place (toast_map_cov.cpp:509-517 operation order, as k_cov_apply)
-    for (int p = threadIdx.x; p < kBxPix; p += kThreads) {
-        const int64_t gp = (int64_t)u.x * kBxPix + p;
-        const double z0 = tile[3 * p], z1 = tile[3 * p + 1], z2 = tile[3 * p + 2];
-        if (gp >= a.n_pix || (z0 == 0.0 && z1 == 0.0 && z2 == 0.0)) continue;
-        const double2 *cm = reinterpret_cast<const double2 *>(a.cov + 6 * gp);
-        const double2 ca = __ldcs(cm), cb = __ldcs(cm + 1), cc = __ldcs(cm + 2);
-        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-        m0 += ca.x * z0;
-        m0 += ca.y * z1;
-        m1 += ca.y * z0;
-        m0 += cb.x * z2;
-        m2 += cb.x * z0;
-        m1 += cb.y * z1;
-        m1 += cc.x * z2;
-        m2 += cc.x * z1;
-        m2 += cc.y * z2;
-        tile[3 * p] = m0;
-        tile[3 * p + 1] = m1;
-        tile[3 * p + 2] = m2;
-    }
-    __syncthreads();
-    bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z);
 }
 
 // zero / covariance product on whole blocks of the global map (the multi-unit blocks of the fused
@@ -358,47 +444,64 @@ BxArgs make_args(const tb_obs *obs, const int4 *units) {
     a.units = units;
     a.brec = obs->brec;
     a.bqu = obs->bqu;
-    a.dscaled = obs->dscaled;
+    a.ascaled = obs->ascaled;
+    a.out = nullptr;
+    a.amp_offsets = obs->amp_offsets;
+    a.nad = (int32_t)obs->n_amp_det;
+    a.n_det = (int)obs->d.n_det;
+    a.row_in_rec = obs->b_row_in_rec;
     a.cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
     a.table = obs->stable;
     a.inv_nad = 1.0 / (double)obs->n_amp_det;
-    a.nad = (int32_t)obs->n_amp_det;
-    a.det_scale = obs->det_scale;
-    a.amp_offsets = obs->amp_offsets;
-    a.n_det = (int)obs->d.n_det;
     a.n_pix = obs->n_local_pix;
     a.zmap = nullptr;
     a.cov = nullptr;
-    a.out = nullptr;
     a.accumulate = 0;
     return a;
+}
+
+void row_grid(const tb_obs *obs, dim3 &grid) {
+    int64_t gy = (obs->n_amp_det + kThreads * 4 - 1) / (kThreads * 4);
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    grid = dim3((unsigned)obs->n_xrows, (unsigned)gy);
+}
+
+void launch_bx_prescale(const tb_obs *obs, const double *amps, const uint8_t *aflags, void *stream) {
+    dim3 grid;
+    row_grid(obs, grid);
+    k_bx_prescale<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        obs->x_paired, (int)obs->d.n_det, obs->n_amp_det, obs->amp_offsets, obs->det_scale, amps,
+        aflags, obs->ascaled);
+    TB_CUDA(cudaGetLastError());
+    tbr::count_launch();
 }
 
 template <int MODE>
 void launch_bx(const tb_obs *obs, const BxArgs &a, int64_t n_units, void *stream) {
     if (n_units <= 0) return;
-    TB_REQUIRE(n_units < 2147483647LL, "grid too large");
-    const unsigned g = (unsigned)n_units;
+    const int64_t nb = (n_units + kBxWarps - 1) / kBxWarps;
+    TB_REQUIRE(nb < 2147483647LL, "grid too large");
+    const unsigned g = (unsigned)nb;
     cudaStream_t st = (cudaStream_t)stream;
     static bool configured = false; // (per MODE instantiation)
     if (!configured) {
-        // 4 CTAs x 48 KB of static shared memory per SM: ask for the large carve-out
-        auto pref = [](const void *f) {
-            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 (int)cudaSharedmemCarveoutMaxShared);
+        auto prep = [&](const void *f) {
+            TB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)cudaSharedmemCarveoutMaxShared));
         };
-        pref((const void *)k_bx<MODE, true, true>);
-        pref((const void *)k_bx<MODE, true, false>);
-        pref((const void *)k_bx<MODE, false, true>);
-        pref((const void *)k_bx<MODE, false, false>);
+        prep((const void *)k_bx<MODE, true, true>);
+        prep((const void *)k_bx<MODE, true, false>);
+        prep((const void *)k_bx<MODE, false, true>);
+        prep((const void *)k_bx<MODE, false, false>);
         configured = true;
     }
     if (obs->s_uniform) {
-        if (obs->x_paired) k_bx<MODE, true, true><<<g, kThreads, 0, st>>>(a);
-        else k_bx<MODE, true, false><<<g, kThreads, 0, st>>>(a);
+        if (obs->x_paired) k_bx<MODE, true, true><<<g, kThreads, 0, st>>>(a, n_units);
+        else k_bx<MODE, true, false><<<g, kThreads, 0, st>>>(a, n_units);
     } else {
-        if (obs->x_paired) k_bx<MODE, false, true><<<g, kThreads, 0, st>>>(a);
-        else k_bx<MODE, false, false><<<g, kThreads, 0, st>>>(a);
+        if (obs->x_paired) k_bx<MODE, false, true><<<g, kThreads, 0, st>>>(a, n_units);
+        else k_bx<MODE, false, false><<<g, kThreads, 0, st>>>(a, n_units);
     }
     TB_CUDA(cudaGetLastError());
     tbr::count_launch();
@@ -426,6 +529,9 @@ void tb_free_blocked(tb_obs *obs) {
     if (obs->bunits_single) cudaFree(obs->bunits_single);
     if (obs->bunits_multi) cudaFree(obs->bunits_multi);
     if (obs->bmulti_blocks) cudaFree(obs->bmulti_blocks);
+    if (obs->ascaled) cudaFree(obs->ascaled);
+    if (obs->qscaled) cudaFree(obs->qscaled);
+    obs->ascaled = obs->qscaled = nullptr;
     obs->brec = nullptr;
     obs->bqu = nullptr;
     obs->bunits = obs->bunits_single = obs->bunits_multi = nullptr;
@@ -489,10 +595,19 @@ void tb_build_blocked(tb_obs *obs, cudaStream_t st) {
         cudaFree(kin);
         cudaFree(vin);
         kin = vin = nullptr;
-        TB_CUDA(cudaMalloc(&obs->brec, sizeof(int2) * n_sorted));
-        TB_CUDA(cudaMalloc(&obs->bqu, sizeof(double2) * n_sorted));
-        k_bx_gather<<<grid, kThreads, 0, st>>>(obs->xrec, obs->xqu, vout, n_sorted, nad, obs->brec,
-                                               obs->bqu);
+        // (two records of padding: the staged copies start / end on even record indices)
+        TB_CUDA(cudaMalloc(&obs->brec, sizeof(int2) * (n_sorted + 2)));
+        TB_CUDA(cudaMalloc(&obs->bqu, sizeof(double2) * (n_sorted + 2)));
+        TB_CUDA(cudaMemsetAsync(obs->brec + n_sorted, 0, sizeof(int2) * 2, st));
+        TB_CUDA(cudaMemsetAsync(obs->bqu + n_sorted, 0, sizeof(double2) * 2, st));
+        {
+            const size_t slots = (size_t)obs->n_xrows * (size_t)nad;
+            const size_t per = obs->x_paired ? 2 : 1;
+            TB_CUDA(cudaMalloc(&obs->ascaled, sizeof(double) * 2 * per * slots));
+        }
+        obs->b_row_in_rec = obs->n_xrows <= (1LL << kBxRowBits) ? 1 : 0;
+        k_bx_gather<<<grid, kThreads, 0, st>>>(obs->xrec, obs->xqu, vout, n_sorted, nad,
+                                               obs->b_row_in_rec, obs->brec, obs->bqu);
         TB_CUDA(cudaGetLastError());
         tbr::count_launch();
         TB_CUDA(cudaMalloc(&starts, sizeof(int32_t) * (n_blocks + 1)));
@@ -594,7 +709,7 @@ int tb_bx_pass1(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_
     TB_REQUIRE((reinterpret_cast<uintptr_t>(zmap) & 15u) == 0, "zmap must be 16-byte aligned");
     int64_t first, end;
     chunk_units(obs, chunk, first, end);
-    if (chunk <= 0) tb_launch_prescale(obs, amplitudes, amp_flags, stream);
+    if (chunk <= 0) launch_bx_prescale(obs, amplitudes, amp_flags, stream);
     if (!accumulate && obs->n_bmulti_blocks > 0 && chunk <= 0) {
         // the units of a multi-unit block meet in global memory: it starts from zero
         k_bx_zero_blocks<<<(unsigned)obs->n_bmulti_blocks, kThreads, 0, (cudaStream_t)stream>>>(
@@ -632,11 +747,13 @@ int tb_bx_fused(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_
     TB_REQUIRE(obs && amplitudes && amp_flags && cov && amplitudes_out, "NULL argument");
     TB_REQUIRE(bx_ok(obs), "the observation has no block-ordered crossing list");
     TB_REQUIRE((reinterpret_cast<uintptr_t>(cov) & 15u) == 0, "cov must be 16-byte aligned");
-    tb_launch_prescale(obs, amplitudes, amp_flags, stream);
+    launch_bx_prescale(obs, amplitudes, amp_flags, stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (obs->n_bunits_multi > 0) {
         // blocks cut into several units: their units meet in global memory (zmap_scratch)
         TB_REQUIRE(zmap_scratch != nullptr, "blocks with several units need the zmap scratch");
+        TB_REQUIRE((reinterpret_cast<uintptr_t>(zmap_scratch) & 15u) == 0,
+                   "zmap scratch must be 16-byte aligned");
         k_bx_zero_blocks<<<(unsigned)obs->n_bmulti_blocks, kThreads, 0, st>>>(
             obs->bmulti_blocks, obs->n_local_pix, zmap_scratch);
         TB_CUDA(cudaGetLastError());

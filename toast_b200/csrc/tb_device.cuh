@@ -142,6 +142,21 @@ __device__ __forceinline__ Runs find_runs(int64_t key, int lane) {
     return r;
 }
 
+// the same for 32-bit keys (one shuffle instead of two)
+template <int CAP = 32>
+__device__ __forceinline__ Runs find_runs32(int32_t key, int lane) {
+    int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    bool head = (lane == 0) || (prev != key) || ((CAP < 32) && ((lane & (CAP - 1)) == 0));
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    unsigned upto = heads & (0xffffffffu >> (31 - lane));
+    int head_lane = 31 - __clz(upto);
+    Runs r;
+    r.dist = lane - head_lane;
+    unsigned tails = (heads >> 1) | 0x80000000u;
+    r.is_tail = (tails >> lane) & 1u;
+    return r;
+}
+
 template <int CAP = 32>
 __device__ __forceinline__ double seg_sum(double v, const Runs &r) {
 #pragma unroll
