@@ -38,14 +38,18 @@ void sort_pairs_i32(const int32_t *keys_in, int32_t *keys_out, const int32_t *va
 }
 
 int g_use_bx = 1; // tb_set_option("blocked", 0/1)
+int g_bx_sort = 0; // tb_set_option("bx_sort", 0/1): fused units by decreasing size (experiment)
 
 namespace {
 
 #ifndef TB_BX_SHIFT
-#define TB_BX_SHIFT 8
+#define TB_BX_SHIFT 7
 #endif
 #ifndef TB_BX_CTAS
 #define TB_BX_CTAS 4
+#endif
+#ifndef TB_BX_PERSIST
+#define TB_BX_PERSIST 0 // persistent warps with a ticket counter measured SLOWER (profiles/r2_blocked_variants.txt)
 #endif
 constexpr int kBxShift = TB_BX_SHIFT;
 constexpr int kBxPix = 1 << kBxShift;   // pixels per block: 3 x kBxPix doubles of shared memory per warp
@@ -168,7 +172,7 @@ struct BxArgs {
     double *out;              // pass 2 / fused: amplitudes (REDs)
     const int64_t *amp_offsets;
     int32_t nad, n_det;
-    int row_in_rec;           // the record's first word carries the row in its upper bits
+    unsigned int *counters;   // {next work unit, warps that have left}: persistent-warp scheduling
     double4 cst;              // {cal0, cal1, A, B} when uniform
     const double4 *table;     // per row otherwise
     double inv_nad;           // 1 / n_amp_det
@@ -235,33 +239,33 @@ __device__ __forceinline__ double4 bx_consts(const BxArgs &a, int32_t slot) {
     return make_double4(ca.x, ca.y, cb.x, cb.y);
 }
 
-// pass 1 over the records [first, end) of the warp's unit: tile += a w (n cal, sum Q, sum U)
-template <bool UNIFORM, bool PAIRED, bool KEEP_IN_L2>
-__device__ __forceinline__ void bx_accumulate(const BxArgs &a, double *tile, int first, int end,
-                                              int lane) {
-    if (first >= end) return;
-    BxRec cur = bx_load<KEEP_IN_L2>(a, first + lane, end, lane);
-    BxRec nxt = bx_load<KEEP_IN_L2>(a, first + 32 + lane, end, lane);
-    BxAmp gc = bx_gather<PAIRED, false>(a, cur.r.y);
-    for (int base = first; base < end; base += 32) {
-        // two steps ahead: records; one step ahead: the amplitude gather
-        const BxRec nn = bx_load<KEEP_IN_L2>(a, base + 64 + lane, end, lane);
-        const BxAmp gn = bx_gather<PAIRED, false>(a, nxt.r.y);
-        const int p = cur.r.x & (kBxPix - 1);
-        const int n0 = (cur.r.x >> kBxShift) & 63, n1 = (cur.r.x >> (kBxShift + 6)) & 63;
-        const double4 c = bx_consts<UNIFORM>(a, cur.r.y);
-        const double t0 = n0 ? gc.t.x : 0.0;
-        const double t1 = (PAIRED && n1) ? gc.t.y : 0.0;
-        const bool contrib = t0 != 0.0 || t1 != 0.0;
-        const double v0 = t0 * (c.x * (double)n0) + t1 * (c.y * (double)n1);
-        const double v1 = t0 * cur.qu.x + t1 * (c.z * cur.qu.x - c.w * cur.qu.y);
-        const double v2 = t0 * cur.qu.y + t1 * (c.w * cur.qu.x + c.z * cur.qu.y);
-        // lanes of this step that hit the same pixel take turns (typically two records of one
-        // crossing cut by a baseline boundary); all others update their pixel at once
-        const unsigned same = __match_any_sync(0xffffffffu, contrib ? p : kBxPix + lane);
-        const int rank = __popc(same & ((1u << lane) - 1u));
-        const int rounds = __reduce_max_sync(0xffffffffu, rank);
-        double *z = tile + 3 * p;
+// one pass-1 step: the 32 records of `x` (amplitudes already gathered in `g`) into the tile
+template <bool UNIFORM, bool PAIRED>
+__device__ __forceinline__ void bx_acc_step(const BxArgs &a, double *tile, const BxRec &x,
+                                            const BxAmp &g, int lane) {
+    const int p = x.r.x & (kBxPix - 1);
+    const int n0 = (x.r.x >> kBxShift) & 63, n1 = (x.r.x >> (kBxShift + 6)) & 63;
+    const double4 c = bx_consts<UNIFORM>(a, x.r.y);
+    const double t0 = n0 ? g.t.x : 0.0;
+    const double t1 = (PAIRED && n1) ? g.t.y : 0.0;
+    const bool contrib = t0 != 0.0 || t1 != 0.0;
+    const double v0 = t0 * (c.x * (double)n0) + t1 * (c.y * (double)n1);
+    const double v1 = t0 * x.qu.x + t1 * (c.z * x.qu.x - c.w * x.qu.y);
+    const double v2 = t0 * x.qu.y + t1 * (c.w * x.qu.x + c.z * x.qu.y);
+    // lanes of this step that hit the same pixel take turns (typically the two records of one
+    // crossing cut by a baseline boundary); all others update their pixel at once
+    const unsigned same = __match_any_sync(0xffffffffu, contrib ? p : kBxPix + lane);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    const int rounds = __reduce_max_sync(0xffffffffu, rank);
+    double *z = tile + 3 * p;
+    if (rounds == 0) {
+        if (contrib) {
+            z[0] += v0;
+            z[1] += v1;
+            z[2] += v2;
+        }
+        __syncwarp();
+    } else {
         for (int r = 0; r <= rounds; ++r) {
             if (contrib && rank == r) {
                 z[0] += v0;
@@ -270,113 +274,154 @@ __device__ __forceinline__ void bx_accumulate(const BxArgs &a, double *tile, int
             }
             __syncwarp();
         }
-        cur = nxt;
-        nxt = nn;
-        gc = gn;
     }
 }
 
-// pass 2 over the records of the warp's unit: qscaled[slot] += w (n a - (n cal, sum Q, sum U) . m),
-// one RED pair per run of records that share the baseline (consecutive in (row, time) order)
+// pass 1 over the records [first, end) of the warp's unit: tile += a w (n cal, sum Q, sum U).
+// Software pipeline without register rotation (three record buffers, loop unrolled by three):
+// records are loaded two steps ahead, amplitudes gathered one step ahead.
+template <bool UNIFORM, bool PAIRED, bool KEEP_IN_L2>
+__device__ __forceinline__ void bx_accumulate(const BxArgs &a, double *tile, int first, int end,
+                                              int lane) {
+    if (first >= end) return;
+    BxRec A = bx_load<KEEP_IN_L2>(a, first + lane, end, lane);
+    BxRec B = bx_load<KEEP_IN_L2>(a, first + 32 + lane, end, lane);
+    BxRec C;
+    BxAmp gA = bx_gather<PAIRED, false>(a, A.r.y), gB, gC;
+    for (int base = first; base < end; base += 96) {
+        C = bx_load<KEEP_IN_L2>(a, base + 64 + lane, end, lane);
+        gB = bx_gather<PAIRED, false>(a, B.r.y);
+        bx_acc_step<UNIFORM, PAIRED>(a, tile, A, gA, lane);
+        if (base + 32 >= end) break;
+        A = bx_load<KEEP_IN_L2>(a, base + 96 + lane, end, lane);
+        gC = bx_gather<PAIRED, false>(a, C.r.y);
+        bx_acc_step<UNIFORM, PAIRED>(a, tile, B, gB, lane);
+        if (base + 64 >= end) break;
+        B = bx_load<KEEP_IN_L2>(a, base + 128 + lane, end, lane);
+        gA = bx_gather<PAIRED, false>(a, A.r.y);
+        bx_acc_step<UNIFORM, PAIRED>(a, tile, C, gC, lane);
+    }
+}
+
+// one pass-2 step: out[baseline] += w (n a - (n cal, sum Q, sum U) . m), one RED pair per run of
+// records that share the baseline (consecutive in (row, time) order)
+template <bool UNIFORM, bool PAIRED>
+__device__ __forceinline__ void bx_proj_step(const BxArgs &a, const double *tile, const BxRec &x,
+                                             const BxAmp &g, int lane) {
+    const int p = x.r.x & (kBxPix - 1);
+    const int n0 = (x.r.x >> kBxShift) & 63, n1 = (x.r.x >> (kBxShift + 6)) & 63;
+    const double4 c = bx_consts<UNIFORM>(a, x.r.y);
+    const double m0 = tile[3 * p], m1 = tile[3 * p + 1], m2 = tile[3 * p + 2];
+    double val0 = 0.0, val1 = 0.0;
+    if (n0) {
+        double sc = (c.x * (double)n0) * m0;
+        sc += x.qu.x * m1;
+        sc += x.qu.y * m2;
+        val0 = (double)n0 * g.t.x - sc * g.w.x;
+    }
+    if (PAIRED && n1) {
+        const double q1 = c.z * x.qu.x - c.w * x.qu.y, u1 = c.w * x.qu.x + c.z * x.qu.y;
+        double sc = (c.y * (double)n1) * m0;
+        sc += q1 * m1;
+        sc += u1 * m2;
+        val1 = (double)n1 * g.t.y - sc * g.w.y;
+    }
+    const Runs rr = find_runs32<8>(x.r.y, lane);
+    val0 = seg_sum<8>(val0, rr);
+    if (PAIRED) val1 = seg_sum<8>(val1, rr);
+    if (rr.is_tail && x.r.y >= 0) {
+        const int row = (int)((unsigned)x.r.x >> (kBxShift + 12)); // (rows fit: tb_build_blocked)
+        const int arel = x.r.y - row * a.nad;
+        const int d0 = PAIRED ? 2 * row : row;
+        if (val0 != 0.0) atomicAdd(a.out + __ldg(a.amp_offsets + d0) + arel, val0);
+        if (PAIRED && val1 != 0.0) atomicAdd(a.out + __ldg(a.amp_offsets + d0 + 1) + arel, val1);
+    }
+}
+
 template <bool UNIFORM, bool PAIRED>
 __device__ __forceinline__ void bx_project(const BxArgs &a, const double *tile, int first, int end,
                                            int lane) {
     if (first >= end) return;
-    BxRec cur = bx_load<false>(a, first + lane, end, lane);
-    BxRec nxt = bx_load<false>(a, first + 32 + lane, end, lane);
-    BxAmp gc = bx_gather<PAIRED, true>(a, cur.r.y);
-    for (int base = first; base < end; base += 32) {
-        const BxRec nn = bx_load<false>(a, base + 64 + lane, end, lane);
-        const BxAmp gn = bx_gather<PAIRED, true>(a, nxt.r.y);
-        const int p = cur.r.x & (kBxPix - 1);
-        const int n0 = (cur.r.x >> kBxShift) & 63, n1 = (cur.r.x >> (kBxShift + 6)) & 63;
-        const double4 c = bx_consts<UNIFORM>(a, cur.r.y);
-        const double m0 = tile[3 * p], m1 = tile[3 * p + 1], m2 = tile[3 * p + 2];
-        double val0 = 0.0, val1 = 0.0;
-        if (n0) {
-            double sc = 0.0;
-            sc += (c.x * (double)n0) * m0;
-            sc += cur.qu.x * m1;
-            sc += cur.qu.y * m2;
-            val0 = (double)n0 * gc.t.x - sc * gc.w.x;
-        }
-        if (PAIRED && n1) {
-            const double q1 = c.z * cur.qu.x - c.w * cur.qu.y, u1 = c.w * cur.qu.x + c.z * cur.qu.y;
-            double sc = 0.0;
-            sc += (c.y * (double)n1) * m0;
-            sc += q1 * m1;
-            sc += u1 * m2;
-            val1 = (double)n1 * gc.t.y - sc * gc.w.y;
-        }
-        const Runs rr = find_runs32<8>(cur.r.y, lane);
-        val0 = seg_sum<8>(val0, rr);
-        if (PAIRED) val1 = seg_sum<8>(val1, rr);
-        if (rr.is_tail && cur.r.y >= 0) {
-            const int row = a.row_in_rec ? (int)((unsigned)cur.r.x >> (kBxShift + 12))
-                                         : (int)fast_div((int64_t)cur.r.y, a.inv_nad);
-            const int arel = cur.r.y - row * a.nad;
-            const int d0 = PAIRED ? 2 * row : row;
-            if (val0 != 0.0) atomicAdd(a.out + __ldg(a.amp_offsets + d0) + arel, val0);
-            if (PAIRED && val1 != 0.0)
-                atomicAdd(a.out + __ldg(a.amp_offsets + d0 + 1) + arel, val1);
-        }
-        cur = nxt;
-        nxt = nn;
-        gc = gn;
+    BxRec A = bx_load<false>(a, first + lane, end, lane);
+    BxRec B = bx_load<false>(a, first + 32 + lane, end, lane);
+    BxRec C;
+    BxAmp gA = bx_gather<PAIRED, true>(a, A.r.y), gB, gC;
+    for (int base = first; base < end; base += 96) {
+        C = bx_load<false>(a, base + 64 + lane, end, lane);
+        gB = bx_gather<PAIRED, true>(a, B.r.y);
+        bx_proj_step<UNIFORM, PAIRED>(a, tile, A, gA, lane);
+        if (base + 32 >= end) break;
+        A = bx_load<false>(a, base + 96 + lane, end, lane);
+        gC = bx_gather<PAIRED, true>(a, C.r.y);
+        bx_proj_step<UNIFORM, PAIRED>(a, tile, B, gB, lane);
+        if (base + 64 >= end) break;
+        B = bx_load<false>(a, base + 128 + lane, end, lane);
+        gA = bx_gather<PAIRED, true>(a, A.r.y);
+        bx_proj_step<UNIFORM, PAIRED>(a, tile, C, gC, lane);
     }
 }
 
 // MODE 0: pass 1 (tile -> zmap), 1: pass 2 (binned map -> tile -> amplitudes), 2: fused.
-// One warp per work unit; grid = ceil(n_units / kBxWarps).
+// Persistent warps: every warp of the grid takes the next work unit from a global counter until
+// none is left (units differ by orders of magnitude in size); the last warp to leave resets the
+// counters for the next launch.
 template <int MODE, bool UNIFORM, bool PAIRED>
 __global__ void __launch_bounds__(kThreads, TB_BX_CTAS)
 k_bx(const BxArgs a, int64_t n_units) {
     __shared__ __align__(16) double tiles[kBxWarps][3 * kBxPix];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t ui = (int64_t)blockIdx.x * kBxWarps + warp;
-    if (ui >= n_units) return;
-    const int4 u = __ldg(a.units + ui);
     double *tile = tiles[warp];
     double2 *tile2 = reinterpret_cast<double2 *>(tile);
-    const int64_t g0 = (int64_t)u.x * (3 * kBxPix);          // first map double of the block
     const int64_t g_end = 3 * a.n_pix;
-    if constexpr (MODE == 1) {
-        const double2 *src = reinterpret_cast<const double2 *>(a.zmap + g0);
-#pragma unroll 4
-        for (int k = lane; k < 3 * kBxPix / 2; k += 32) {
-            const int64_t g = g0 + 2 * k;
-            double2 v = make_double2(0.0, 0.0);
-            if (g + 1 < g_end) v = __ldcs(src + k);
-            else if (g < g_end) v.x = __ldcs(a.zmap + g);
-            tile2[k] = v;
-        }
-        __syncwarp();
-        bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z, lane);
-    } else {
-#pragma unroll 4
-        for (int k = lane; k < 3 * kBxPix / 2; k += 32) tile2[k] = make_double2(0.0, 0.0);
-        __syncwarp();
-        bx_accumulate<UNIFORM, PAIRED, MODE == 2>(a, tile, u.y, u.z, lane);
-        __syncwarp();
-        if constexpr (MODE == 0) {
-            if (u.w == 0 && !a.accumulate) {
-                // the only unit of its block: the tile IS the block of the map
-                double2 *dst = reinterpret_cast<double2 *>(a.zmap + g0);
-#pragma unroll 4
-                for (int k = lane; k < 3 * kBxPix / 2; k += 32) {
-                    const int64_t gg = g0 + 2 * k;
-                    if (gg + 1 < g_end) __stcs(dst + k, tile2[k]);
-                    else if (gg < g_end) a.zmap[gg] = tile2[k].x;
-                }
-            } else {
-                for (int k = lane; k < 3 * kBxPix; k += 32) {
-                    const double v = tile[k];
-                    if (v != 0.0 && g0 + k < g_end) atomicAdd(a.zmap + g0 + k, v);
-                }
-            }
+    for (int64_t turn = 0;; ++turn) {
+        unsigned int ticket = 0;
+        if (TB_BX_PERSIST) {
+            if (lane == 0) ticket = atomicAdd(a.counters, 1u);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
         } else {
-            // fused: m = C z in place (toast_map_cov.cpp:509-517 operation order, as k_cov_apply)
-            if (u.z > u.y) {
+            if (turn > 0) break;
+            ticket = blockIdx.x * kBxWarps + warp;
+        }
+        if ((int64_t)ticket >= n_units) break;
+        const int4 u = __ldg(a.units + ticket);
+        const int64_t g0 = (int64_t)u.x * (3 * kBxPix);      // first map double of the block
+        if constexpr (MODE == 1) {
+            if (u.z <= u.y) continue; // nothing to project from this block
+            const double2 *src = reinterpret_cast<const double2 *>(a.zmap + g0);
+#pragma unroll 4
+            for (int k = lane; k < 3 * kBxPix / 2; k += 32) {
+                const int64_t g = g0 + 2 * k;
+                double2 v = make_double2(0.0, 0.0);
+                if (g + 1 < g_end) v = __ldcs(src + k);
+                else if (g < g_end) v.x = __ldcs(a.zmap + g);
+                tile2[k] = v;
+            }
+            __syncwarp();
+            bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z, lane);
+        } else {
+#pragma unroll 4
+            for (int k = lane; k < 3 * kBxPix / 2; k += 32) tile2[k] = make_double2(0.0, 0.0);
+            __syncwarp();
+            bx_accumulate<UNIFORM, PAIRED, MODE == 2>(a, tile, u.y, u.z, lane);
+            __syncwarp();
+            if constexpr (MODE == 0) {
+                if (u.w == 0 && !a.accumulate) {
+                    // the only unit of its block: the tile IS the block of the map
+                    double2 *dst = reinterpret_cast<double2 *>(a.zmap + g0);
+#pragma unroll 4
+                    for (int k = lane; k < 3 * kBxPix / 2; k += 32) {
+                        const int64_t gg = g0 + 2 * k;
+                        if (gg + 1 < g_end) __stcs(dst + k, tile2[k]);
+                        else if (gg < g_end) a.zmap[gg] = tile2[k].x;
+                    }
+                } else {
+                    for (int k = lane; k < 3 * kBxPix; k += 32) {
+                        const double v = tile[k];
+                        if (v != 0.0 && g0 + k < g_end) atomicAdd(a.zmap + g0 + k, v);
+                    }
+                }
+            } else if (u.z > u.y) {
+                // fused: m = C z in place (toast_map_cov.cpp:509-517 operation order)
                 for (int p = lane; p < kBxPix; p += 32) {
                     const int64_t gp = (int64_t)u.x * kBxPix + p;
                     const double z0 = tile[3 * p], z1 = tile[3 * p + 1], z2 = tile[3 * p + 2];
@@ -400,6 +445,15 @@ k_bx(const BxArgs a, int64_t n_units) {
                 __syncwarp();
                 bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z, lane);
             }
+        }
+        __syncwarp(); // the tile is reused by the warp's next unit
+    }
+    if (TB_BX_PERSIST && lane == 0) {
+        const unsigned int left = atomicAdd(a.counters + 1, 1u);
+        if (left == gridDim.x * kBxWarps - 1) { // every warp has taken its last ticket
+            a.counters[0] = 0u;
+            a.counters[1] = 0u;
+            __threadfence();
         }
     }
 }
@@ -449,7 +503,7 @@ BxArgs make_args(const tb_obs *obs, const int4 *units) {
     a.amp_offsets = obs->amp_offsets;
     a.nad = (int32_t)obs->n_amp_det;
     a.n_det = (int)obs->d.n_det;
-    a.row_in_rec = obs->b_row_in_rec;
+    a.counters = obs->bcounters;
     a.cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
     a.table = obs->stable;
     a.inv_nad = 1.0 / (double)obs->n_amp_det;
@@ -480,8 +534,9 @@ void launch_bx_prescale(const tb_obs *obs, const double *amps, const uint8_t *af
 template <int MODE>
 void launch_bx(const tb_obs *obs, const BxArgs &a, int64_t n_units, void *stream) {
     if (n_units <= 0) return;
-    const int64_t nb = (n_units + kBxWarps - 1) / kBxWarps;
-    TB_REQUIRE(nb < 2147483647LL, "grid too large");
+    int64_t nb = (n_units + kBxWarps - 1) / kBxWarps;
+    const int64_t resident = (int64_t)tbr::sm_count() * TB_BX_CTAS;
+    if (TB_BX_PERSIST && nb > resident) nb = resident; // one wave, units handed out dynamically
     const unsigned g = (unsigned)nb;
     cudaStream_t st = (cudaStream_t)stream;
     static bool configured = false; // (per MODE instantiation)
@@ -529,6 +584,8 @@ void tb_free_blocked(tb_obs *obs) {
     if (obs->bunits_single) cudaFree(obs->bunits_single);
     if (obs->bunits_multi) cudaFree(obs->bunits_multi);
     if (obs->bmulti_blocks) cudaFree(obs->bmulti_blocks);
+    if (obs->bcounters) cudaFree(obs->bcounters);
+    obs->bcounters = nullptr;
     if (obs->ascaled) cudaFree(obs->ascaled);
     if (obs->qscaled) cudaFree(obs->qscaled);
     obs->ascaled = obs->qscaled = nullptr;
@@ -551,8 +608,8 @@ void tb_build_blocked(tb_obs *obs, cudaStream_t st) {
     const int64_t n_pix = obs->n_local_pix;
     if (obs->xrec == nullptr || obs->stable == nullptr || obs->dscaled == nullptr) return;
     if (n_rec <= 0 || n_rec >= (1LL << 29) || n_det * nad >= 2147483647LL || n_pix <= 0 ||
-        n_pix >= (1LL << 31) - kBxPix)
-        return;
+        n_pix >= (1LL << 31) - kBxPix || obs->n_xrows > (1LL << kBxRowBits))
+        return; // (the records carry their row in kBxRowBits bits)
     const int32_t n_blocks = (int32_t)((n_pix + kBxPix - 1) >> kBxShift);
     const int grid = tbr::sm_count() * 8;
     unsigned int *counters = nullptr;
@@ -604,10 +661,11 @@ void tb_build_blocked(tb_obs *obs, cudaStream_t st) {
             const size_t slots = (size_t)obs->n_xrows * (size_t)nad;
             const size_t per = obs->x_paired ? 2 : 1;
             TB_CUDA(cudaMalloc(&obs->ascaled, sizeof(double) * 2 * per * slots));
+            TB_CUDA(cudaMalloc(&obs->bcounters, 2 * sizeof(unsigned int)));
+            TB_CUDA(cudaMemsetAsync(obs->bcounters, 0, 2 * sizeof(unsigned int), st));
         }
-        obs->b_row_in_rec = obs->n_xrows <= (1LL << kBxRowBits) ? 1 : 0;
-        k_bx_gather<<<grid, kThreads, 0, st>>>(obs->xrec, obs->xqu, vout, n_sorted, nad,
-                                               obs->b_row_in_rec, obs->brec, obs->bqu);
+        k_bx_gather<<<grid, kThreads, 0, st>>>(obs->xrec, obs->xqu, vout, n_sorted, nad, 1,
+                                               obs->brec, obs->bqu);
         TB_CUDA(cudaGetLastError());
         tbr::count_launch();
         TB_CUDA(cudaMalloc(&starts, sizeof(int32_t) * (n_blocks + 1)));
@@ -631,9 +689,14 @@ void tb_build_blocked(tb_obs *obs, cudaStream_t st) {
                 const int32_t ue = f + (int32_t)(((int64_t)(e - f) * (k + 1)) / nu);
                 const int4 u = make_int4(b, uf, ue, nu > 1 ? 1 : 0);
                 units.push_back(u);
-                (nu > 1 ? multi : single).push_back(u);
+                if (nu > 1) multi.push_back(u);
+                else if (ue > uf) single.push_back(u); // (the fused kernel skips empty blocks)
             }
         }
+        if (g_bx_sort)
+            std::stable_sort(single.begin(), single.end(), [](const int4 &x, const int4 &y) {
+                return (x.z - x.y) > (y.z - y.y);
+            });
         auto upload = [&](const std::vector<int4> &v, int4 **dst) {
             if (v.empty()) return;
             TB_CUDA(cudaMalloc(dst, sizeof(int4) * v.size()));

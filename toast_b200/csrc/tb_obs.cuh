@@ -57,7 +57,7 @@ struct tb_obs {
     // one block at a time and keeps its 3 x kBxPix map values in shared memory.
     double *ascaled = nullptr;  // per-pass scratch [slot]{a0 w0, a1 w1, w0, w1} (k_bx_prescale)
     double *qscaled = nullptr;  // (unused)
-    int b_row_in_rec = 0;       // records carry their row in the upper bits of the first word
+    unsigned int *bcounters = nullptr; // {next unit, warps done} of the persistent-warp kernels
     int2 *brec = nullptr;       // [n_brec] {pixel in block | n0 << kBxShift | n1 << (kBxShift+6), scaled-amplitude index}
     double2 *bqu = nullptr;     // [n_brec] (sum Q, sum U)
     int4 *bunits = nullptr;     // [n_bunits] {block, first record, end record, 1 if the block has several units}
@@ -90,3 +90,4 @@ void tb_free_blocked(tb_obs *obs);
 // unit ranges of the pixel chunks; chunked calls are refused when a bound is not block-aligned
 void tb_blocked_set_chunks(tb_obs *obs, int64_t n_chunks, const int64_t *pixel_bounds);
 extern int g_use_bx;
+extern int g_bx_sort;

@@ -2272,6 +2272,7 @@ int tb_get_option(const char *name) {
     if (n == "peer_ctas") return tb_peer_ctas_per_sm;
     if (n == "prefetch") return g_use_prefetch;
     if (n == "blocked") return g_use_bx;
+    if (n == "bx_sort") return g_bx_sort;
     if (n == "prior_chunk") return tb_prior_chunk;
     return -1;
 }
@@ -2297,6 +2298,8 @@ int tb_set_option(const char *name, int value) {
         g_use_prefetch = value;
     } else if (std::string(name) == "blocked") {
         g_use_bx = value;
+    } else if (std::string(name) == "bx_sort") {
+        g_bx_sort = value;
     } else if (std::string(name) == "prior_chunk") {
         TB_REQUIRE(value >= 0, "prior_chunk must be >= 0");
         tb_prior_chunk = value;
