@@ -322,7 +322,8 @@ int tb_lhs_pass2_pad(const tb_obs *obs, const double *amplitudes, const uint8_t 
  *   tb_bx_fused  one observation on one GPU: pass 1 -> covariance_apply (toast_map_cov.cpp:471-528)
  *                -> pass 2 inside one kernel, the map never leaves the SM.  zmap_scratch
  *                ([n_local_pix, 3]) is only touched for blocks that had to be cut into several
- *                work units (high-contention maps).  ADDS to amplitudes_out. */
+ *                work units (high-contention maps).  ADDS to amplitudes_out.  amplitudes ==
+ *                NULL: the amplitudes of the preceding tb_bx_fused / tb_bx_pass1 call. */
 int tb_bx_block_pixels(void);
 int tb_obs_blocked(const tb_obs *obs);
 int tb_obs_blocked_stats(const tb_obs *obs, int64_t *n_records, int64_t *n_units,

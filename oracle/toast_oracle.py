@@ -434,17 +434,25 @@ def template_project(pb, K, det_data, amps_out):
                                              pb.amp_flags, pb.intervals, False)
 
 
-def bin_map(pb, K, det_data, covapply):
-    """BinMap: mapmaker_binning.py:179-294 = BuildNoiseWeighted + covariance_apply."""
+def bin_map(pb, K, det_data, covapply, reverse=False):
+    """BinMap: mapmaker_binning.py:179-294 = BuildNoiseWeighted + covariance_apply.
+    ``reverse``: hand the detectors to the kernel in reverse order -- the same reference
+    arithmetic with another (equally valid) summation order; the difference between the two
+    results measures how far the reference's own output is defined (tests: order envelope)."""
     idx = np.arange(pb.n_det, dtype=np.int32)
+    det_scale = pb.det_scale
+    if reverse:
+        # (det_scale is indexed by loop position, the data arrays through idx)
+        idx = np.ascontiguousarray(idx[::-1])
+        det_scale = np.ascontiguousarray(det_scale[::-1])
     zmap = np.zeros((pb.n_local_submap, pb.n_pix_submap, 3))
     if pb.solver_flags is not None:
         K.build_noise_weighted(pb.global2local, zmap, idx, pb.pixels, idx, pb.weights, idx,
-                               det_data, idx, pb.solver_flags, pb.det_scale, pb.det_flag_mask,
+                               det_data, idx, pb.solver_flags, det_scale, pb.det_flag_mask,
                                pb.intervals, pb.shared_flags, pb.shared_flag_mask, False)
     else:
         K.build_noise_weighted(pb.global2local, zmap, idx, pb.pixels, idx, pb.weights, idx,
-                               det_data, idx, np.zeros((1, 1), dtype=np.uint8), pb.det_scale,
+                               det_data, idx, np.zeros((1, 1), dtype=np.uint8), det_scale,
                                pb.det_flag_mask, pb.intervals, pb.shared_flags,
                                pb.shared_flag_mask, False)
     covapply(pb.n_local_submap, pb.n_pix_submap, 3, pb.cov.reshape(-1), zmap.reshape(-1))
@@ -455,13 +463,13 @@ def _scan(K):
     return getattr(K, "ops_scan_map_float64", None) or K.scan_map
 
 
-def solver_lhs(pb, K, amps_in, covapply=None):
+def solver_lhs(pb, K, amps_in, covapply=None, reverse=False):
     """SolverLHS._exec with full_pointing=True: mapmaker_solve.py:342-506."""
     covapply = covapply or cov_apply_diag
     idx = np.arange(pb.n_det, dtype=np.int32)
     det_temp = np.zeros((pb.n_det, pb.n_samp))
     template_add(pb, K, amps_in, det_temp)
-    binned = bin_map(pb, K, det_temp, covapply)
+    binned = bin_map(pb, K, det_temp, covapply, reverse=reverse)
     out = np.zeros_like(amps_in)
     det_temp[:] = 0
     template_add(pb, K, amps_in, det_temp)
@@ -472,11 +480,11 @@ def solver_lhs(pb, K, amps_in, covapply=None):
     return out
 
 
-def solver_rhs(pb, K, signal, covapply=None):
+def solver_rhs(pb, K, signal, covapply=None, reverse=False):
     """SolverRHS._exec with full_pointing=True: mapmaker_solve.py:107-229."""
     covapply = covapply or cov_apply_diag
     idx = np.arange(pb.n_det, dtype=np.int32)
-    binned = bin_map(pb, K, signal, covapply)
+    binned = bin_map(pb, K, signal, covapply, reverse=reverse)
     det_temp = signal.copy()
     _scan(K)(pb.global2local, pb.n_pix_submap, binned, det_temp, idx, pb.pixels, idx,
              pb.weights, idx, pb.intervals, 1.0, False, True, False, False)

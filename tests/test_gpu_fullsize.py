@@ -101,36 +101,62 @@ def test_reference_subset_at_production_size(name, n_big, n_sub, n_iter):
                    pb.amp_flags)
     covapply = ck.cov_apply_diag
     sig = torch.from_numpy(obs["signal"]).cuda()
+    # the noise-weighted map BEFORE the covariance product is well conditioned: strict 1e-10
+    idx = np.arange(pb.n_det, dtype=np.int32)
+    zref = np.zeros((pb.n_local_submap, pb.n_pix_submap, 3))
+    ck.build_noise_weighted(pb.global2local, zref, idx, pb.pixels, idx, pb.weights, idx,
+                            obs["signal"], idx, pb.solver_flags, pb.det_scale, pb.det_flag_mask,
+                            pb.intervals, pb.shared_flags, pb.shared_flag_mask, False)
+    zgpu = torch.zeros((pb.n_local_submap, pb.n_pix_submap, 3), dtype=torch.float64, device="cuda")
+    K.build_noise_weighted(pb.global2local, zgpu, idx, dobs.pixels, idx, dobs.weights, idx, sig,
+                           idx, dobs.solver_flags, pb.det_scale, pb.det_flag_mask, pb.intervals,
+                           dobs.shared_flags, pb.shared_flag_mask)
+    assert_close_norm(zgpu.cpu().numpy(), zref, what="noise-weighted map")
+    del zgpu, zref
+    # everything behind the covariance product (condition numbers up to 1e8 at the production
+    # threshold): 1e-10, or the reference's own summation-order dependence where that is larger
+    tol = {}
     binned_ref = O.bin_map(pb, ck, obs["signal"], covapply)
-    assert_close_norm(ds.bin_signal([sig]).cpu().numpy(), binned_ref, what="binned map")
+    tol["binned"] = H.order_tolerance(binned_ref, O.bin_map(pb, ck, obs["signal"], covapply,
+                                                            reverse=True))
+    assert_close_norm(ds.bin_signal([sig]).cpu().numpy(), binned_ref, rtol=tol["binned"][0],
+                      what="binned map")
     rhs_ref = O.solver_rhs(pb, ck, obs["signal"], covapply=covapply)
-    assert_close_norm(ds.rhs([sig]).cpu().numpy(), rhs_ref, what="RHS")
+    tol["rhs"] = H.order_tolerance(rhs_ref, O.solver_rhs(pb, ck, obs["signal"], covapply=covapply,
+                                                         reverse=True))
+    assert_close_norm(ds.rhs([sig]).cpu().numpy(), rhs_ref, rtol=tol["rhs"][0], what="RHS")
     rng = np.random.default_rng(11)
     a = np.where(pb.amp_flags == 0, rng.standard_normal(pb.n_amp), 0.0)
     lhs_ref = O.solver_lhs(pb, ck, a, covapply=covapply)
+    tol["lhs"] = H.order_tolerance(lhs_ref, O.solver_lhs(pb, ck, a, covapply=covapply,
+                                                         reverse=True))
     q = torch.zeros(pb.n_amp, dtype=torch.float64, device="cuda")
     ds.lhs(torch.from_numpy(a).cuda(), q)
-    assert_close_norm(q.cpu().numpy(), lhs_ref, what="LHS")
+    assert_close_norm(q.cpu().numpy(), lhs_ref, rtol=tol["lhs"][0], what="LHS")
     if ds._blocked():   # and the separate-launch form of the same passes
         ds.fuse_lhs = False
         q2 = torch.zeros_like(q)
         ds.lhs(torch.from_numpy(a).cuda(), q2)
-        assert_close_norm(q2.cpu().numpy(), lhs_ref, what="LHS (pass 1 / covariance / pass 2)")
+        assert_close_norm(q2.cpu().numpy(), lhs_ref, rtol=tol["lhs"][0],
+                          what="LHS (pass 1 / covariance / pass 2)")
         ds.fuse_lhs = True
 
     # PCG: the reference's own iteration states, one device iteration from each
     trace = []
     amps_ref, hist_ref = O.solve(pb, ck, rhs_ref, n_iter_max=n_iter, covapply=covapply,
                                  trace=trace)
-    worst = H.restart_parity(ds, pb, trace, what=name)
+    worst = H.restart_parity(ds, pb, trace, rtol=tol["lhs"][0], what=name)
     amps3_ref = trace[3]["x"] if len(trace) > 3 else amps_ref
     amps3, _ = ds.solve(torch.from_numpy(rhs_ref).cuda(), n_iter_max=min(3, len(trace)))
-    assert_close_norm(amps3.cpu().numpy(), amps3_ref, what="amplitudes after 3 iterations")
+    assert_close_norm(amps3.cpu().numpy(), amps3_ref, rtol=8 * tol["lhs"][0],
+                      what="amplitudes after 3 iterations")
     # free-running history: where does it leave 1e-10 (reported)
     _, hist = ds.solve(torch.from_numpy(rhs_ref).cuda(), n_iter_max=n_iter)
     first, dev = H.first_iteration_over(hist, hist_ref)
-    assert dev[0] <= H.RTOL
-    report = dict(workload=name, detectors=n_sub, covariance_detectors=n_big,
+    assert dev[0] <= 8 * tol["lhs"][0]
+    report = dict(tolerances={k: dict(used=v[0], reference_order_dependence=v[1])
+                              for k, v in tol.items()},
+                  workload=name, detectors=n_sub, covariance_detectors=n_big,
                   n_samp=int(pb.n_samp), nside=int(pb.nside), unflagged_fraction=good,
                   pixels_kept_by_rcond=sc["kept"], restart_parity_worst=max(worst),
                   free_running_first_iteration_over_1e10=first,

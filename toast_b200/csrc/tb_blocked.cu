@@ -807,10 +807,14 @@ int tb_bx_fused(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_
                 const double *cov, double *zmap_scratch, double *amplitudes_out, void *stream) {
     TB_API_BEGIN
     tbr::require_device();
-    TB_REQUIRE(obs && amplitudes && amp_flags && cov && amplitudes_out, "NULL argument");
+    TB_REQUIRE(obs && cov && amplitudes_out, "NULL argument");
     TB_REQUIRE(bx_ok(obs), "the observation has no block-ordered crossing list");
     TB_REQUIRE((reinterpret_cast<uintptr_t>(cov) & 15u) == 0, "cov must be 16-byte aligned");
-    launch_bx_prescale(obs, amplitudes, amp_flags, stream);
+    // amplitudes == NULL: the amplitudes of the preceding call (their prescaled copy is reused)
+    if (amplitudes != nullptr) {
+        TB_REQUIRE(amp_flags != nullptr, "NULL argument");
+        launch_bx_prescale(obs, amplitudes, amp_flags, stream);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (obs->n_bunits_multi > 0) {
         // blocks cut into several units: their units meet in global memory (zmap_scratch)

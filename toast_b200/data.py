@@ -58,10 +58,21 @@ class Comm:
 class DetectorData:
     """observation_data.py:35-603: rows of one contiguous buffer, one row per detector."""
 
-    def __init__(self, detectors, shape, dtype):
+    def __init__(self, detectors, shape, dtype, pinned=False):
         self.detectors = list(detectors)
         self._index = {d: i for i, d in enumerate(self.detectors)}
-        self.data = np.zeros((len(self.detectors),) + tuple(shape), dtype=dtype)
+        full = (len(self.detectors),) + tuple(shape)
+        self._pinned = None
+        if pinned:
+            # page-locked host buffer (what the reference's accelerator mapping needs for
+            # asynchronous copies); numpy view of a pinned torch tensor, kept alive here
+            import torch
+
+            self._pinned = torch.zeros(full, dtype=getattr(torch, np.dtype(dtype).name),
+                                       pin_memory=True)
+            self.data = self._pinned.numpy()
+        else:
+            self.data = np.zeros(full, dtype=dtype)
         self.dtype = np.dtype(dtype)
         self.detector_shape = tuple(shape)
 
@@ -223,7 +234,7 @@ class Data:
         return list(seen)
 
 
-def observation_from_synthetic(obs, name="obs0", det_prefix="D"):
+def observation_from_synthetic(obs, name="obs0", det_prefix="D", pinned=False):
     """Wrap a ``toast_b200.synthetic.make_observation`` dict as an Observation with the
     reference's default keys (``defaults.py``): boresight_radec, flags, signal, noise_model."""
     n_det, n_samp = obs["n_det"], obs["n_samp"]
@@ -233,10 +244,10 @@ def observation_from_synthetic(obs, name="obs0", det_prefix="D"):
     ob.shared["flags"] = obs["shared_flags"]
     ob.shared["times"] = np.arange(n_samp, dtype=np.float64) / obs["rate"]
     ob.intervals["scanning"] = obs["intervals"]
-    ob.detdata["flags"] = DetectorData(dets, (n_samp,), np.uint8)
+    ob.detdata["flags"] = DetectorData(dets, (n_samp,), np.uint8, pinned=pinned)
     ob.detdata["flags"].data[:] = obs["det_flags"]
     if "signal" in obs:
-        ob.detdata["signal"] = DetectorData(dets, (n_samp,), np.float64)
+        ob.detdata["signal"] = DetectorData(dets, (n_samp,), np.float64, pinned=pinned)
         ob.detdata["signal"].data[:] = obs["signal"]
     ob["noise_model"] = NoiseModel({d: float(w) for d, w in zip(dets, obs["detweight"])})
     ob["focalplane"] = {

@@ -17,6 +17,33 @@ from ..templates.offset import Offset
 from .operator import Operator
 
 
+def _identity_rows(dd, dets):
+    idx = dd.indices(dets)
+    return len(idx) == dd.data.shape[0] and np.array_equal(idx, np.arange(len(idx)))
+
+
+def _rows_to_device(dd, dets, dev):
+    """The detdata rows of ``dets`` as a device tensor.  All rows in order (the usual case): one
+    asynchronous copy straight from the host buffer (page-locked buffers overlap with compute);
+    otherwise the selected rows are gathered on the host first."""
+    import torch
+
+    if _identity_rows(dd, dets):
+        src = dd._pinned if getattr(dd, "_pinned", None) is not None else torch.from_numpy(dd.data)
+        return src.to(dev, non_blocking=True)
+    return torch.from_numpy(np.ascontiguousarray(dd.data[dd.indices(dets)])).to(dev)
+
+
+def _rows_from_device(dd, dets, t):
+    import torch
+
+    if _identity_rows(dd, dets):
+        dst = dd._pinned if getattr(dd, "_pinned", None) is not None else torch.from_numpy(dd.data)
+        dst.copy_(t)
+    else:
+        dd.data[dd.indices(dets)] = t.cpu().numpy()
+
+
 class TemplateMatrix(Operator):
     _defaults = dict(templates=None, amplitudes=None, transpose=False, view=None,
                      det_data="signal", det_mask=1, det_flags=None, det_flag_mask=1)
@@ -87,7 +114,8 @@ class MapMaker(Operator):
                      shared_flags="flags", shared_flag_mask=1, convergence=1.0e-12, iter_min=3,
                      iter_max=100, solve_rcond_threshold=1.0e-8, map_rcond_threshold=1.0e-8,
                      binning=None, template_matrix=None, map_binning=None,
-                     regenerate_pointing=False, keep_solver_products=False, device="cuda")
+                     regenerate_pointing=False, keep_solver_products=False, device="cuda",
+                     profile_stages=False)
 
     def _exec(self, data, detectors=None, use_accel=True, **kwargs):
         import torch
@@ -97,6 +125,10 @@ class MapMaker(Operator):
         for trait in ("binning", "template_matrix"):
             if getattr(self, trait) is None:
                 raise RuntimeError(f"You must set the '{trait}' trait before calling exec()")
+        if self.map_binning is not None and self.map_binning is not self.binning:
+            # (the reference bins the final maps with a second operator, mapmaker.py:386-470)
+            raise NotImplementedError("a map_binning operator distinct from binning is not "
+                                      "supported on the B200 path")
         binning = self.binning
         pixels, weights = binning.pixel_pointing, binning.stokes_weights
         if pixels is None or weights is None:
@@ -112,6 +144,19 @@ class MapMaker(Operator):
         pixels._geometry()
         dev = torch.device(self.device)
         comm = data.comm
+        # wall-clock per stage (device synchronised at every mark) when profile_stages is set
+        import time as _time
+
+        self.stage_seconds = {}
+        _t = [_time.perf_counter()]
+
+        def mark(name):
+            if not self.profile_stages:
+                return
+            torch.cuda.synchronize(dev)
+            now = _time.perf_counter()
+            self.stage_seconds[name] = self.stage_seconds.get(name, 0.0) + now - _t[0]
+            _t[0] = now
 
         # --- template layout (host, O(n_amp)) ------------------------------------------------
         self.template_matrix.view = view if self.template_matrix.view is None else \
@@ -120,6 +165,7 @@ class MapMaker(Operator):
         self.template_matrix.det_flags = None  # solver flags are applied on the device below
         self.template_matrix.reset()
         tmpl._defer_prior = True  # built below, from the variance under the full solver flags
+        tmpl._defer_variance = True  # (and so are the amplitude flags / variance themselves)
         self.template_matrix._init_templates(data, detectors)
 
         # --- device observations, solver flags bit 0 (mapmaker_templates.py:764-810) -----------
@@ -131,13 +177,18 @@ class MapMaker(Operator):
             # samples (offset.py:136-141; the view flags are ORed into the solver flags below)
             iv = ob.intervals[tmpl._bounds_view if tmpl.use_noise_prior else view]
             sflag = ob.shared[self.shared_flags] if self.shared_flags is not None else None
-            flags = np.zeros((len(dets), ob.n_local_samples), dtype=np.uint8)
+            # solver flags are combined on the device: the detector flags travel as they are
+            # (one asynchronous copy from the -- possibly page-locked -- detdata buffer)
+            flags = torch.zeros((len(dets), ob.n_local_samples), dtype=torch.uint8, device=dev)
             if self.det_flags is not None:
                 fd = ob.detdata[self.det_flags]
-                flags |= ((fd.data[fd.indices(dets)] & self.det_flag_mask) != 0).astype(np.uint8)
+                flags |= ((_rows_to_device(fd, dets, dev) & self.det_flag_mask) != 0).to(
+                    torch.uint8)
             if sflag is not None:
-                flags |= ((sflag & self.shared_flag_mask) != 0).astype(np.uint8)[None, :]
-            flags |= tmpl._obs_view_flags[iob][None, :]
+                sf = torch.from_numpy(np.ascontiguousarray(sflag)).to(dev)
+                flags |= ((sf & self.shared_flag_mask) != 0).to(torch.uint8)[None, :]
+            flags |= torch.from_numpy(
+                np.ascontiguousarray(tmpl._obs_view_flags[iob]).astype(np.uint8)).to(dev)[None, :]
             noise = ob[binning.noise_model]
             d = DeviceObservation(
                 focalplane=np.array([fp[x]["quat"] for x in dets]),
@@ -157,10 +208,9 @@ class MapMaker(Operator):
                                      dtype=np.int64),
                 device=dev)
             dobs.append(d)
-            sd = ob.detdata[self.det_data]
-            signals.append(torch.from_numpy(
-                np.ascontiguousarray(sd.data[sd.indices(dets)])).to(dev))
+            signals.append(_rows_to_device(ob.detdata[self.det_data], dets, dev))
 
+        mark("upload + flags")
         # --- pointing expansion + pixel distribution --------------------------------------------
         hits = np.zeros(pixels._n_submap, dtype=np.uint8)
         for d in dobs:
@@ -176,6 +226,7 @@ class MapMaker(Operator):
             d.set_global2local(dist.global_submap_to_local)
         n_loc, nps = dist.n_local_submap, dist.n_pix_submap
 
+        mark("pointing expansion")
         # --- CovarianceAndHits on the device (mapmaker_utils.py:1131-1270) ----------------------
         def allreduce_dev(t):
             if comm.comm_world is not None:
@@ -197,6 +248,10 @@ class MapMaker(Operator):
             return hmap, inv, rc
 
         hmap, cov, rcond = covariance(self.solve_rcond_threshold, True)
+        # flags of the final products: the input flags only.  The solver's rcond mask (below) is
+        # NOT part of them (ops/mapmaker.py:386-470, 502-594: the final covariance and maps are
+        # made with the binning operator's own flags and map_rcond_threshold)
+        base_flags = [d.solver_flags.clone() for d in dobs]
 
         # rcond mask -> solver flags (mapmaker_templates.py:895-939 via ScanMask)
         bad = torch.zeros((n_loc, nps, 3), dtype=torch.float64, device=dev)
@@ -213,6 +268,7 @@ class MapMaker(Operator):
             del w1, tmp
         del bad
 
+        mark("covariance + rcond mask")
         # --- amplitude flags / preconditioner: n_good = F^T (good-sample indicator) -------------
         n_amp = tmpl._n_local
         n_good = torch.zeros(n_amp, dtype=torch.float64, device=dev)
@@ -241,21 +297,28 @@ class MapMaker(Operator):
         tmpl._offsetvar = offset_var
         tmpl._amp_flags = ~keep
 
+        mark("amplitude flags")
         # --- RHS, PCG ----------------------------------------------------------------------------
         if tmpl.use_noise_prior:
             tmpl._build_prior(data)  # offset.py:356-560, uploaded once
         ds = Destriper(dobs, n_loc, nps, cov, offset_var, amp_flags,
                        regen=self.regenerate_pointing, device=dev, prior=tmpl.prior())
+        mark("crossing lists + solver set-up")
         rhs = ds.rhs(signals)
+        mark("RHS")
         amps_dev, self.history = ds.solve(rhs, convergence=self.convergence,
                                           n_iter_max=self.iter_max, n_iter_min=self.iter_min)
 
+        mark("PCG")
         # --- final products -------------------------------------------------------------------------
+        for d, bf in zip(dobs, base_flags):
+            d.solver_flags.copy_(bf)   # (same buffer the native handle points at)
+        del base_flags
         if self.map_rcond_threshold != self.solve_rcond_threshold:
             _, cov_map, rcond_map = covariance(self.map_rcond_threshold, False)
             ds.cov = cov_map
         else:
-            rcond_map = rcond
+            rcond_map = rcond  # (the solve covariance was accumulated with the same flags)
         binmap = ds.bin_signal(signals).clone()
         neg = -amps_dev
         for d, sig in zip(dobs, signals):
@@ -263,6 +326,8 @@ class MapMaker(Operator):
             KC.template_offset_add_to_signal_batch(d.step_length, d.amp_offsets, d.n_amp_views,
                                                    neg, ds.amp_flags, idx, sig, d.intervals)
         destriped = ds.bin_signal(signals).clone()
+
+        mark("final binning")
 
         def to_pixdata(t, dtype, nv):
             p = PixelData(dist, dtype, n_value=nv)
@@ -281,8 +346,8 @@ class MapMaker(Operator):
         # the cleaned timestream is what the reference leaves in det_data (mapmaker.py:531-574)
         for iob, (ob, d, sig) in enumerate(zip(data.obs, dobs, signals)):
             dets = [x for x in tmpl._all_dets if x in tmpl._obs_dets[iob]]
-            sd = ob.detdata[self.det_data]
-            sd.data[sd.indices(dets)] = sig.cpu().numpy()
+            _rows_from_device(ob.detdata[self.det_data], dets, sig)
+        mark("products to host")
         if self.keep_solver_products:
             self.destriper = ds
 

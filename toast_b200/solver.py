@@ -182,6 +182,17 @@ class _CudaView:
                                          "data": (int(ptr), False), "version": 2}
 
 
+def _all_ranks_ok(ok, device, group=None):
+    """True only if ``ok`` holds on EVERY rank (MIN all-reduce of a success flag): each rank must
+    take the same decision about the reduction path, or the ranks on the fused path would spin in
+    its device-side flag barrier while the others sit in an NCCL collective."""
+    import torch.distributed as dist
+
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()) == 1)
+
+
 class PeerMap:
     """A map buffer visible to every rank of the node over NVLink (CUDA IPC) and the fused
     reduce-scatter -> covariance -> all-gather kernel on it (``tb_map_reduce_cov``).  Replaces
@@ -196,13 +207,19 @@ class PeerMap:
         self.n_pix = int(n_pix)
         nbytes = self.n_pix * 3 * 8
         self.h = self.lib.tb_peer_create(self.rank, self.world, nbytes)
-        if not self.h:
-            raise RuntimeError(L.last_error())
         buf = ct.create_string_buffer(128)
-        L.check(self.lib.tb_peer_get_handles(self.h, buf))
+        ok = bool(self.h) and self.lib.tb_peer_get_handles(self.h, buf) == 0
+        err = "" if ok else L.last_error()
+        if not _all_ranks_ok(ok, device, group):   # every rank gives up together
+            self._release()
+            raise RuntimeError(err or "peer-memory allocation failed on another rank")
         handles = [None] * self.world
         dist.all_gather_object(handles, buf.raw, group=group)
-        L.check(self.lib.tb_peer_open(self.h, b"".join(handles)))
+        ok = self.lib.tb_peer_open(self.h, b"".join(handles)) == 0
+        err = "" if ok else L.last_error()
+        if not _all_ranks_ok(ok, device, group):
+            self._release()
+            raise RuntimeError(err or "opening the peer handles failed on another rank")
         ptr = self.lib.tb_peer_map_ptr(self.h)
         self.tensor = torch.as_tensor(_CudaView(ptr, self.n_pix * 3), device=device)
         dist.barrier(group=group)
@@ -211,9 +228,14 @@ class PeerMap:
         n_pix = self.n_pix - pix_first if n_pix is None else n_pix
         L.check(self.lib.tb_map_reduce_cov_range(self.h, pix_first, n_pix, L.ptr(cov), stream))
 
+    def _release(self):
+        if getattr(self, "h", None):
+            self.lib.tb_peer_destroy(self.h)
+        self.h = None
+
     def __del__(self):
         try:
-            self.lib.tb_peer_destroy(self.h)
+            self._release()
         except Exception:
             pass
 
@@ -239,14 +261,18 @@ class SymmPeerMap:
         self.buf.zero_()
         hdl = symm_mem.rendezvous(self.buf, grp)
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-        if mc == 0:
-            raise RuntimeError("no NVLS multicast mapping for symmetric memory on this system")
         maps = (ct.c_uint64 * self.world)(*[int(p) for p in hdl.buffer_ptrs])
         flags = (ct.c_uint64 * self.world)(*[int(p) + n * 8 for p in hdl.buffer_ptrs])
         self._hdl = hdl
-        self.h = self.lib.tb_peer_attach(self.rank, self.world, n * 8, maps, flags, mc)
-        if not self.h:
-            raise RuntimeError(L.last_error())
+        self.h = self.lib.tb_peer_attach(self.rank, self.world, n * 8, maps, flags, mc) \
+            if mc != 0 else None
+        err = "" if self.h else ("no NVLS multicast mapping for symmetric memory on this system"
+                                 if mc == 0 else L.last_error())
+        if not _all_ranks_ok(bool(self.h), device, group):   # every rank gives up together
+            if self.h:
+                self.lib.tb_peer_destroy(self.h)
+                self.h = None
+            raise RuntimeError(err or "symmetric-memory set-up failed on another rank")
         self.tensor = self.buf[:n]
         self.group = group
         self.use_multimem = True
@@ -323,7 +349,8 @@ class SymmPeerMap:
 
     def __del__(self):
         try:
-            self.lib.tb_peer_destroy(self.h)
+            if getattr(self, "h", None):
+                self.lib.tb_peer_destroy(self.h)
         except Exception:
             pass
 
@@ -376,23 +403,41 @@ class Destriper:
         self.peer = None
         n_pix = self.n_local_submap * self.n_pix_submap
         import os as _os
-        if self.world > 1 and fused_reduce and _os.environ.get("TB_FUSED_REDUCE", "1") != "0":
+        # the fused reduction works in 256-pixel tiles: maps that are not a multiple of that
+        # (nside_submap < 8 gives 12 / 48 / 192 pixels per submap) take the NCCL path
+        aligned = n_pix % 256 == 0
+        if self.world > 1 and fused_reduce and aligned and \
+                _os.environ.get("TB_FUSED_REDUCE", "1") != "0":
             import warnings
 
+            # every attempt ends with an agreement over the ranks (inside the constructors and
+            # below): either all ranks use a path or none does
             if _os.environ.get("TB_MULTIMEM", "1") != "0":
+                peer, err = None, None
                 try:
-                    self.peer = SymmPeerMap(n_pix, self.device, group)
-                    self.peer.tune(self.cov)
+                    peer = SymmPeerMap(n_pix, self.device, group)
                 except Exception as exc:  # noqa: BLE001
-                    warnings.warn(f"NVLS multicast map reduction unavailable ({exc}); "
+                    err = exc
+                if _all_ranks_ok(peer is not None, self.device, group):
+                    try:
+                        peer.tune(self.cov)
+                    except Exception as exc:  # noqa: BLE001
+                        err = exc
+                    if _all_ranks_ok(err is None, self.device, group):
+                        self.peer = peer
+                if self.peer is None:
+                    warnings.warn(f"NVLS multicast map reduction unavailable ({err}); "
                                   "using P2P peer memory")
-                    self.peer = None
             if self.peer is None:
+                peer, err = None, None
                 try:
-                    self.peer = PeerMap(n_pix, self.device, group)
+                    peer = PeerMap(n_pix, self.device, group)
                 except Exception as exc:  # noqa: BLE001
-                    warnings.warn(f"peer-memory map reduction unavailable ({exc}); using NCCL")
-                    self.peer = None
+                    err = exc
+                if _all_ranks_ok(peer is not None, self.device, group):
+                    self.peer = peer
+                else:
+                    warnings.warn(f"peer-memory map reduction unavailable ({err}); using NCCL")
         if self.peer is not None:
             self.zmap = self.peer.tensor.view(self.n_local_submap, self.n_pix_submap, 3)
         else:
@@ -417,17 +462,14 @@ class Destriper:
         mode = _os.environ.get("TB_PIPE_CHUNKS", "auto")
         if mode == "auto":
             self._setup_pipeline(4)
+            if self.world > 1 and not _all_ranks_ok(self.pipeline, self.device, group):
+                self.pipeline = False
             if self.pipeline:
-                try:
-                    self._tune_pipeline()
-                except Exception as exc:  # noqa: BLE001  (e.g. graph capture refused)
-                    import warnings
-
-                    warnings.warn(f"chunk pipeline unavailable ({exc}); using the serial LHS")
-                    self.pipeline = False
-                    self._graphs = {}
+                self._tune_pipeline()
         else:
             self._setup_pipeline(int(mode))
+            if self.world > 1 and not _all_ranks_ok(self.pipeline, self.device, group):
+                self.pipeline = False
 
     # -- chunk pipeline -------------------------------------------------------------------------
     def _sorted_passes(self):
@@ -494,10 +536,24 @@ class Destriper:
         a = torch.randn(self.n_amp, generator=g, device=self.device, dtype=torch.float64)
         a[self.amp_flags != 0] = 0.0
         q = torch.zeros_like(a)
+        # capture the graph first and agree on it: a rank whose capture is refused must not
+        # leave the others waiting in the device-side barrier of a replay
+        ok = True
+        if self.use_graph:
+            try:
+                self._capture_pipelined(a, q)
+            except Exception as exc:  # noqa: BLE001
+                import warnings
+
+                warnings.warn(f"CUDA-graph capture of the chunk pipeline refused ({exc})")
+                ok = False
+            if not _all_ranks_ok(ok, self.device, self.group):
+                self.use_graph = False
+                self._graphs = {}
         times, results = [], []
         for pipelined in (True, False):
             self.pipeline = pipelined
-            self.lhs(a, q)  # warm-up (and graph capture)
+            self.lhs(a, q)  # warm-up
             dist.barrier(group=self.group)
             torch.cuda.synchronize(self.device)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -532,6 +588,11 @@ class Destriper:
         self._peer_ctas(self.pipe_ctas)
         if not self.use_graph:
             return self._enqueue_pipelined(amps_in, amps_out)
+        self._capture_pipelined(amps_in, amps_out).replay()
+        return amps_out
+
+    def _capture_pipelined(self, amps_in, amps_out):
+        self._peer_ctas(self.pipe_ctas)
         key = (amps_in.data_ptr(), amps_out.data_ptr())
         g = self._graphs.get(key)
         if g is None:
@@ -544,8 +605,7 @@ class Destriper:
                 self._enqueue_pipelined(amps_in, amps_out)
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graphs[key] = g
-        g.replay()
-        return amps_out
+        return g
 
     def _enqueue_pipelined(self, amps_in, amps_out, timeline=None):
         """``timeline``: optional list receiving (label, start event, end event) per launch
@@ -604,6 +664,13 @@ class Destriper:
             timed(f"pass2[{c}]", main, p2)
         return amps_out
 
+    def _st(self):
+        """The CUDA stream every native launch of this solver goes to: torch's CURRENT stream, so
+        that kernels and the surrounding tensor ops (zero_, copy_, NCCL collectives) stay
+        ordered under ``with torch.cuda.stream(s)`` as well.  (The deterministic reductions use
+        one scratch area per device: issue them from one stream at a time.)"""
+        return torch.cuda.current_stream(self.device).cuda_stream
+
     # -- collectives ----------------------------------------------------------------------------
     def _allreduce(self, t):
         if self.world > 1:
@@ -621,15 +688,30 @@ class Destriper:
         self._allreduce(self.zmap)
         L.check(self.lib.tb_cov_apply_diag(self.n_local_submap, self.n_pix_submap, 3,
                                            L.ptr(self.cov), L.ptr(self.zmap), L.TB_MEM_DEVICE,
-                                           None))
+                                           self._st()))
 
     def bin_amplitudes(self, amps):
         """binned = cov * allreduce(P^T N^-1 F a)   (BinMap with pre_process=TemplateMatrix)."""
         self.zmap.zero_()
         for o in self.obs:
             L.check(self.lib.tb_lhs_pass1(o.handle().h, L.ptr(amps), L.ptr(self.amp_flags),
-                                          L.ptr(self.zmap), self.regen, None))
+                                          L.ptr(self.zmap), self.regen, self._st()))
         self.reduce_and_apply_cov()
+        return self.zmap
+
+    def bin_amplitudes_raw(self, amps):
+        """This rank's raw noise-weighted map P^T N^-1 F a -- pass 1 only, no reduction, no
+        covariance (diagnostics: bench.py checks the fused reduction against NCCL on it)."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        if self._blocked():
+            for k, o in enumerate(self.obs):
+                L.check(self.lib.tb_bx_pass1(o.handle().h, L.ptr(amps), L.ptr(self.amp_flags),
+                                             L.ptr(self.zmap), 1 if k > 0 else 0, -1, st))
+            return self.zmap
+        self.zmap.zero_()
+        for o in self.obs:
+            L.check(self.lib.tb_lhs_pass1(o.handle().h, L.ptr(amps), L.ptr(self.amp_flags),
+                                          L.ptr(self.zmap), self.regen, self._st()))
         return self.zmap
 
     def bin_signal(self, signals):
@@ -637,7 +719,7 @@ class Destriper:
         self.zmap.zero_()
         for o, sig in zip(self.obs, signals):
             L.check(self.lib.tb_bin_signal(o.handle().h, L.ptr(sig), L.ptr(self.zmap), self.regen,
-                                           None))
+                                           self._st()))
         self.reduce_and_apply_cov()
         return self.zmap
 
@@ -656,7 +738,7 @@ class Destriper:
             ev[0].record()
         for o in self.obs:
             L.check(self.lib.tb_lhs_pass1(o.handle().h, L.ptr(amps_in), L.ptr(self.amp_flags),
-                                          L.ptr(self.zmap), self.regen, None))
+                                          L.ptr(self.zmap), self.regen, self._st()))
         if ev:
             ev[1].record()
         reuse = self._sorted_passes() == 2
@@ -667,7 +749,7 @@ class Destriper:
             if ev:
                 ev[2].record()
             L.check(self.lib.tb_lhs_pass2_cov(self.obs[0].handle().h, L.ptr(self.zmap),
-                                              L.ptr(self.cov), L.ptr(amps_out), None))
+                                              L.ptr(self.cov), L.ptr(amps_out), self._st()))
             if ev:
                 ev[3].record()
                 timers.append(ev)
@@ -682,13 +764,13 @@ class Destriper:
                                             dtype=torch.float64, device=self.device)
             L.check(self.lib.tb_cov_apply_pad(self.n_local_submap * self.n_pix_submap,
                                               L.ptr(self.cov), L.ptr(self.zmap),
-                                              L.ptr(self._binned4), None))
+                                              L.ptr(self._binned4), self._st()))
             amps_out.zero_()
             if ev:
                 ev[2].record()
             L.check(self.lib.tb_lhs_pass2_pad(self.obs[0].handle().h, L.ptr(amps_in),
                                               L.ptr(self.amp_flags), L.ptr(self._binned4),
-                                              L.ptr(amps_out), None))
+                                              L.ptr(amps_out), self._st()))
             if ev:
                 ev[3].record()
                 timers.append(ev)
@@ -701,7 +783,7 @@ class Destriper:
         for o in self.obs:
             L.check(self.lib.tb_lhs_pass2(o.handle().h, None if reuse else L.ptr(amps_in),
                                           L.ptr(self.amp_flags), L.ptr(self.zmap),
-                                          L.ptr(amps_out), self.regen, None))
+                                          L.ptr(amps_out), self.regen, self._st()))
         if ev:
             ev[3].record()
             timers.append(ev)
@@ -745,18 +827,18 @@ class Destriper:
         # mapmaker_solve.py:395-412 adds the prior BEFORE the projection accumulates into the same
         # vector; the sum is the same and flagged amplitudes receive nothing from either term
         if self.prior is not None:
-            self.prior.add(amps_in, self.amp_flags, amps_out)
+            self.prior.add(amps_in, self.amp_flags, amps_out, stream=self._st())
         return amps_out
 
     def precond(self, r, s):
         """s = M^-1 r: diagonal offset variance (template_offset.cpp:375-402), or the noise-prior
         preconditioner."""
         if self.prior is not None:
-            self.prior.precond(r, self.amp_flags, s)
+            self.prior.precond(r, self.amp_flags, s, stream=self._st())
         else:
             L.check(self.lib.tb_template_offset_apply_diag_precond(
                 L.ptr(self.offset_var), L.ptr(r), L.ptr(self.amp_flags), L.ptr(s), self.n_amp,
-                L.TB_MEM_DEVICE, None))
+                L.TB_MEM_DEVICE, self._st()))
 
     def rhs(self, signals):
         """SolverRHS: F^T N^-1 Z d."""
@@ -764,12 +846,12 @@ class Destriper:
         out = torch.zeros(self.n_amp, dtype=torch.float64, device=self.device)
         for o, sig in zip(self.obs, signals):
             L.check(self.lib.tb_rhs_project(o.handle().h, L.ptr(sig), L.ptr(self.amp_flags),
-                                            L.ptr(binned), L.ptr(out), self.regen, None))
+                                            L.ptr(binned), L.ptr(out), self.regen, self._st()))
         return out
 
     def dot(self, a, b, out):
         L.check(self.lib.tb_amp_dot(L.ptr(a), L.ptr(b), L.ptr(self.amp_flags), self.n_amp,
-                                    L.ptr(out), None))
+                                    L.ptr(out), self._st()))
         self._allreduce(out)
 
     # -- PCG --------------------------------------------------------------------------------------
@@ -784,12 +866,12 @@ class Destriper:
         L.check(self.lib.tb_pcg_update(L.ptr(st.delta), L.ptr(st.dq), L.ptr(st.x), L.ptr(st.r),
                                        L.ptr(st.d), L.ptr(st.q), L.ptr(st.s),
                                        L.ptr(self.offset_var), L.ptr(self.amp_flags), self.n_amp,
-                                       L.ptr(st.sums), None))
+                                       L.ptr(st.sums), self._st()))
         if self.prior is not None:
             # the fused update applied the diagonal preconditioner: redo s and s.r with the prior's
             self.precond(st.r, st.s)
             L.check(self.lib.tb_amp_dot(L.ptr(st.s), L.ptr(st.r), L.ptr(self.amp_flags),
-                                        self.n_amp, L.ptr(st.sums[1:]), None))
+                                        self.n_amp, L.ptr(st.sums[1:]), self._st()))
         self._allreduce(st.sums)
 
     def iteration(self, st):
@@ -800,7 +882,7 @@ class Destriper:
     def advance_direction(self, st):
         # delta_new = s.r = sums[1];  beta = delta_new / delta_old;  d = s + beta d
         L.check(self.lib.tb_pcg_direction(L.ptr(st.sums[1:]), L.ptr(st.delta), L.ptr(st.d),
-                                          L.ptr(st.s), self.n_amp, None))
+                                          L.ptr(st.s), self.n_amp, self._st()))
         st.delta.copy_(st.sums[1:2])
 
     def solve(self, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, x0=None):

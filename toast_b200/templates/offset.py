@@ -121,6 +121,14 @@ class Offset(Template):
         self._offsetvar = np.zeros(self._n_local)
         if self._n_local == 0:
             return
+        if getattr(self, "_defer_variance", False):
+            # MapMaker computes flags and variance itself, on the device, from the full solver
+            # flags (and then builds the prior); only the per-observation flag arrays that
+            # project_signal needs under a noise prior are prepared here
+            if self.use_noise_prior:
+                for iob, ob in enumerate(new_data.obs):
+                    self._obs_flags[iob] = self._combined_flags(ob, iob)
+            return
         n_good = np.zeros(self._n_local)
         amplen = np.zeros(self._n_local)
         detnoise = np.ones(self._n_local)
