@@ -1,11 +1,8 @@
 #!/bin/bash
-# 2 GPUs: multi-rank parity tests + bench (auto pipeline, serial, NCCL)
+# 2 GPUs: copy-engine form of the chunk reduction vs the SM kernel
 OUT=gpurun_out
-TAG=${1:-r2n2}
+TAG=${1:-r2n2b}
 mkdir -p $OUT
-nvidia-smi -L | head -8
-timeout 900 python -m pytest tests/test_gpu_peer.py -m gpu -x -q --timeout 600 > $OUT/pytest_$TAG.log 2>&1
-tail -6 $OUT/pytest_$TAG.log
 bench() {  # name, env...
   name=$1; shift
   env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
@@ -18,14 +15,14 @@ try:
     r = d["roofline"]
     print(sys.argv[2], "ms/step %.3f value %.3e p1 %.3f p2 %.3f red %.3f" % (
         d["ms_per_step"], d["value"], r["pass1_ms"], r["pass2_ms"], r["reduce_cov_ms"]),
-        "pipeline", r["pipeline"], r["pipeline_tuning_ms"], r["map_reduction"], r["map_reduction_tuning_ms"],
-        "parity", d["parity"]["map_reduce_max_rel_err"], "nvlink", d["nvlink"])
+        "pipeline", r["pipeline"], r["pipeline_tuning_ms"], "residuals", d["pcg_relative_residuals"][:2])
 except Exception as e:
     print(sys.argv[2], "FAILED", e)
     print(open(sys.argv[1].replace(".json", ".err")).read()[-2500:])
 PY
 }
-bench auto X=1
-bench serial TB_PIPE_CHUNKS=0
-bench nccl TB_FUSED_REDUCE=0
-bench oldpath TB_OPTIONS=blocked=0
+bench ce4_graph TB_REDUCE=ce TB_PIPE_CHUNKS=4 TB_GRAPH=1
+bench ce3_graph TB_REDUCE=ce TB_PIPE_CHUNKS=3 TB_GRAPH=1
+bench ce6_graph TB_REDUCE=ce TB_PIPE_CHUNKS=6 TB_GRAPH=1
+bench sm3 TB_PIPE_CHUNKS=3
+bench sm5 TB_PIPE_CHUNKS=5

@@ -1,15 +1,16 @@
 #!/bin/bash
-# 2 GPUs: multi-rank parity tests + bench (auto pipeline, serial, NCCL)
+# 8 GPUs: multi-rank parity tests at world 2/4/8 + bench
 OUT=gpurun_out
-TAG=${1:-r2n2}
+TAG=${1:-r2n8}
+N=${2:-8}
 mkdir -p $OUT
-nvidia-smi -L | head -8
+nvidia-smi -L | wc -l
 timeout 900 python -m pytest tests/test_gpu_peer.py -m gpu -x -q --timeout 600 > $OUT/pytest_$TAG.log 2>&1
 tail -6 $OUT/pytest_$TAG.log
 bench() {  # name, env...
   name=$1; shift
-  env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
-      --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 20 --warmup 3 --no-extras \
+  env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+      --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 20 --warmup 3 --no-extras \
       > $OUT/${TAG}_$name.json 2> $OUT/${TAG}_$name.err
   python - "$OUT/${TAG}_$name.json" "$name" <<'PY'
 import json, sys
@@ -27,5 +28,4 @@ PY
 }
 bench auto X=1
 bench serial TB_PIPE_CHUNKS=0
-bench nccl TB_FUSED_REDUCE=0
-bench oldpath TB_OPTIONS=blocked=0
+bench p2p TB_MULTIMEM=0
