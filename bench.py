@@ -615,6 +615,52 @@ def reduction_parity_and_rate(ds, world, lib):
                            "k_map_reduce_cov (P2P reduce-scatter + cov + all-gather)"}
 
 
+def e2e_solver_lhs(ds, st, steps, warmup, world, total_samples):
+    """SolverLHS.apply through Destriper.lhs with host-resident amplitude vectors: H2D of d,
+    both passes + the NVLink map reduction + covariance, D2H of q, every step."""
+    import torch
+
+    n = ds.n_amp
+    d_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    q_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    d_host.copy_(st.d)
+    d_dev = torch.empty(n, dtype=torch.float64, device=ds.device)
+    q_dev = torch.empty(n, dtype=torch.float64, device=ds.device)
+
+    def step():
+        d_dev.copy_(d_host, non_blocking=True)
+        ds.lhs(d_dev, q_dev)
+        q_host.copy_(q_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / max(steps, 1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=ds.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": total_samples / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+            "what": "Destriper.lhs (SolverLHS.apply, mapmaker_solve.py:342-506) with the "
+                    "amplitude vectors in pinned host memory: H2D of d, both passes + NVLink map "
+                    "reduction + covariance, D2H of q; timestream-derived data device-resident "
+                    "as in the reference's accel pipeline.  (N = 1 reports ops.MapMaker.apply "
+                    "end to end instead.)"}
+
+
 def e2e_mapmaker(workload, n_det, n_samp, n_iter, device, rank, world):
     """ops.MapMaker.apply (the reference's entry point, ops/mapmaker.py:719-787): host numpy
     buffers (pinned) in, maps / amplitudes / cleaned timestreams out.  Everything is inside the
@@ -758,6 +804,73 @@ def c2_operator_chain(device, lib, reps=5):
     return out
 
 
+def noise_prior_sub_run(device, lib, peak, reps=10):
+    """the Offset noise prior on the C4 shard (one 12-h view per detector: 128
+    segments of 43 200 baselines; 1/f PSD, banded preconditioner of width 20): tb_offset_prior_add
+    (Offset._add_prior, templates/offset/offset.py:884-960) and tb_offset_prior_precond
+    (Offset._apply_precond, :962-1010) timed alone with CUDA events, plus PCG iterations with the
+    prior in the loop."""
+    import torch
+
+    from toast_b200.templates.offset_prior import OffsetPriorBuilder, prior_frequencies
+
+    ds, dobs, signal, info = build_gpu_problem("c4", False, 1.0, 0, 1, device)
+    n_amp, nad = ds.n_amp, dobs.n_amp_det
+    step_time = S.CONFIGS["c4"]["step_time"]
+    rate = S.CONFIGS["c4"]["rate"]
+    t0 = time.perf_counter()
+    b = OffsetPriorBuilder(n_amp, precond_width=20)
+    freq = prior_frequencies(info["n_samp"] / rate, step_time, rate)
+    pf = np.logspace(-5, np.log10(rate / 2), 400)
+    var = ds.offset_var.cpu().numpy()
+    for d in range(info["n_det"]):
+        sigma2 = 1.0 / dobs.det_scale[d]
+        psd = sigma2 / rate * (1.0 + (0.05 / pf) ** 1.5)   # white level + 1/f, f_knee 50 mHz
+        b.add_detector(int(dobs.amp_offsets[d]), dobs.n_amp_views, pf, psd,
+                       float(dobs.det_scale[d]), var, freq, step_time)
+    prior = b.finish()
+    build_s = time.perf_counter() - t0
+    taps = int(np.mean(b.filt_len))
+    band = int(np.mean(b.prec_width))
+    g = torch.Generator(device=device)
+    g.manual_seed(5)
+    a = torch.randn(n_amp, generator=g, device=device, dtype=torch.float64)
+    out = torch.zeros_like(a)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_add = timed(lambda: prior.add(a, ds.amp_flags, out))
+    ms_pre = timed(lambda: prior.precond(a, ds.amp_flags, out))
+    # with the prior in the PCG
+    ds.prior = prior
+    st, sq0 = pcg_prologue(ds, signal, lib)
+    ms_iter, hist, _ = time_iterations(ds, st, sq0, 8, 3, 1, lib)
+    res = {
+        "config": f"c4 shard, {info['n_det']} segments of {nad} baselines, filter taps ~{taps}, "
+                  f"preconditioner band {band}",
+        "prior_build_host_s": round(build_s, 2),
+        "add_prior_ms": ms_add, "apply_precond_ms": ms_pre,
+        # compulsory: amplitudes in, flags, out (read + write for add); the filter / factor
+        # values are shared by a segment (add) or streamed once (banded factor: band x n_amp)
+        "add_prior_frac_of_peak": n_amp * (8 + 1 + 16) / (ms_add * 1e-3) / 1e9 / peak,
+        "apply_precond_frac_of_peak": n_amp * (8 + 1 + 8 + 8 * band) / (ms_pre * 1e-3) / 1e9 / peak,
+        "pcg_iteration_with_prior_ms": ms_iter,
+        "relative_residuals": hist[3:6],
+    }
+    del ds, dobs, signal, st, prior
+    torch.cuda.empty_cache()
+    return res
+
+
 def cpu_sample_parity(problem, device):
     """Part of the cpu_baseline leg: the GPU path on the SAME sample the reference's compiled
     kernels just ran (64 detectors, production rcond) -- pixels bit-exact, RHS / LHS relative
@@ -845,6 +958,13 @@ def main_gpu(args):
     else:
         total_samples = float(info["det_samples"])
 
+    # N > 1: the LHS through the host-facing solver call with the amplitude vectors in pinned
+    # host memory (ops.MapMaker.apply is the N = 1 end-to-end measurement; its multi-rank form
+    # is exercised by the 2-rank tests and can be selected with TB_E2E_MAPMAKER_MULTI=1)
+    e2e_lhs = None
+    if world > 1:
+        e2e_lhs = e2e_solver_lhs(ds, st, args.steps, min(args.warmup, 2), world, total_samples)
+
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -868,9 +988,12 @@ def main_gpu(args):
     del ds, dobs, st, signal
     torch.cuda.empty_cache()
 
-    # ---- end to end through the operator API -------------------------------------------------
+    # ---- end to end ---------------------------------------------------------------------------
     e2e = None
-    if not args.no_extras:
+    multi_mapmaker = os.environ.get("TB_E2E_MAPMAKER_MULTI", "0") == "1"
+    if world > 1 and not multi_mapmaker:
+        e2e = e2e_lhs
+    elif not args.no_extras:
         n_iter = max(args.steps, 1)
         r = e2e_mapmaker(args.workload, info["n_det"], info["n_samp"], n_iter, device, rank, world)
         tt = torch.tensor([r["seconds"]], dtype=torch.float64, device=device)
@@ -1000,6 +1123,11 @@ def main_gpu(args):
             others["c2_operator_chain"] = o
         except Exception as exc:
             others["c2_operator_chain"] = {"error": repr(exc)[:300]}
+        try:
+            others["noise_prior"] = noise_prior_sub_run(device, lib, peak)
+        except Exception as exc:
+            others["noise_prior"] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
         line["other_workloads"] = others
 
     if rank == 0:

@@ -295,18 +295,11 @@ int tb_lhs_pass1_chunk(const tb_obs *obs, const double *amplitudes, const uint8_
                        double *zmap, int64_t chunk, void *stream);
 int tb_lhs_pass2_chunk(const tb_obs *obs, const double *binned, double *amplitudes_out,
                        int64_t chunk, void *stream);
-/* EXPERIMENTAL (not yet validated on hardware): pass 2 for the amplitudes of the preceding
- * tb_lhs_pass1 with covariance_apply (covariance.py:262-306, toast_map_cov.cpp:471-528) folded in:
+/* Pass 2 on the pixel-sorted list for the amplitudes of the preceding tb_lhs_pass1 with
+ * covariance_apply (covariance.py:262-306, toast_map_cov.cpp:471-528) folded in:
  * zmap is the RAW noise-weighted map of pass 1, cov the [n_pix,6] pixel covariance.  One GPU. */
 int tb_lhs_pass2_cov(const tb_obs *obs, const double *zmap, const double *cov,
                      double *amplitudes_out, void *stream);
-/* EXPERIMENTAL (not yet validated on hardware): the covariance product written to a padded copy
- * of the map (binned4: [n_pix,4] doubles = I, Q, U, 0; 32-byte aligned) and the time-ordered
- * crossing-list pass 2 that gathers one 32-byte sector per crossing from it.  One GPU. */
-int tb_cov_apply_pad(int64_t n_pix, const double *cov, const double *zmap, double *binned4,
-                     void *stream);
-int tb_lhs_pass2_pad(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
-                     const double *binned4, double *amplitudes_out, void *stream);
 /* ---- block-ordered crossing list: shared-memory privatised map tiles (tb_blocked.cu) ----------
  * The same two passes as tb_lhs_pass1 / tb_lhs_pass2 (mapmaker_solve.py:342-506: template
  * add_to_signal + BuildNoiseWeighted, ops_mapmaker_utils.cpp:15-86,295-377; ScanMap + NoiseWeight

@@ -396,47 +396,29 @@ def test_off_map_samples_keep_the_time_ordered_pass2():
     assert_close_norm(out["sorted"], out["general"], what="off-map samples")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TB_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="experimental kernel written without GPU access: run with "
-                           "TB_TEST_EXPERIMENTAL=1 to validate it")
 @pytest.mark.parametrize("eps_max", [0.0, 0.03])
-def test_experimental_pass2_with_fused_covariance(eps_max):
-    """tb_lhs_pass2_cov (covariance product folded into the pixel-ordered pass 2) and the
-    prefetch variants against the shipped LHS and the oracle."""
+def test_pass2_with_fused_covariance_on_the_pixel_sorted_list(eps_max):
+    """tb_lhs_pass2_cov (covariance product folded into the pixel-ordered pass 2; the round-1
+    path, option blocked=0) against the plain pixel-sorted LHS and the oracle."""
     ck = H.checker()
     obs = S.make_observation("c4", n_det=6, n_samp=30000, eps_max=eps_max, nside=128)
     pb = O.build_problem(obs, ck, rcond_threshold=1e-5)
     rng = np.random.default_rng(7)
     a = np.where(pb.amp_flags == 0, rng.standard_normal(pb.n_amp), 0.0)
     ref = O.solver_lhs(pb, ck, a, covapply=ck.cov_apply_diag)
-    dobs, ds, _ = _device_problem(obs, pb)
-    a_d = torch.from_numpy(a).cuda()
-    q0, q1 = torch.zeros_like(a_d), torch.zeros_like(a_d)
-    ds.lhs(a_d, q0)
-    ds.fuse_cov = True
-    ds.lhs(a_d, q1)
-    assert_close_norm(q1.cpu().numpy(), ref, what="LHS (fused covariance)")
-    assert_close_norm(q1.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="fused vs shipped")
-    # covariance product into a padded map + time-ordered pass 2 gathering from it
-    ds.fuse_cov = False
-    ds.pad_map = True
-    q3 = torch.zeros_like(a_d)
-    ds.lhs(a_d, q3)
-    ds.pad_map = False
-    assert_close_norm(q3.cpu().numpy(), ref, what="LHS (padded map)")
-    assert_close_norm(q3.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="padded vs shipped")
-    # the L2-prefetch variants of both pixel-ordered passes (option "prefetch")
     lib = L.load()
-    ds.fuse_cov = False
-    for mode in (1, 2):   # 1: L2 prefetch of the later records; 2: all four iterations in flight
-        q2 = torch.zeros_like(a_d)
-        try:
-            L.check(lib.tb_set_option(b"prefetch", mode))
-            ds.lhs(a_d, q2)
-        finally:
-            lib.tb_set_option(b"prefetch", 0)
-        assert_close_norm(q2.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12,
-                          what=f"prefetch={mode} vs shipped")
+    try:
+        L.check(lib.tb_set_option(b"blocked", 0))
+        dobs, ds, _ = _device_problem(obs, pb)
+        a_d = torch.from_numpy(a).cuda()
+        q0, q1 = torch.zeros_like(a_d), torch.zeros_like(a_d)
+        ds.lhs(a_d, q0)
+        ds.fuse_cov = True
+        ds.lhs(a_d, q1)
+    finally:
+        lib.tb_set_option(b"blocked", 1)
+    assert_close_norm(q1.cpu().numpy(), ref, what="LHS (fused covariance)")
+    assert_close_norm(q1.cpu().numpy(), q0.cpu().numpy(), rtol=1e-12, what="fused vs plain")
 
 
 def test_full_size_properties_c4_shard():

@@ -48,9 +48,7 @@ namespace {
 #ifndef TB_BX_CTAS
 #define TB_BX_CTAS 4
 #endif
-#ifndef TB_BX_PERSIST
-#define TB_BX_PERSIST 0 // persistent warps with a ticket counter measured SLOWER (profiles/r2_blocked_variants.txt)
-#endif
+
 constexpr int kBxShift = TB_BX_SHIFT;
 constexpr int kBxPix = 1 << kBxShift;   // pixels per block: 3 x kBxPix doubles of shared memory per warp
 constexpr int kBxUnitMax = 16384;       // records per work unit (one warp)
@@ -172,7 +170,6 @@ struct BxArgs {
     double *out;              // pass 2 / fused: amplitudes (REDs)
     const int64_t *amp_offsets;
     int32_t nad, n_det;
-    unsigned int *counters;   // {next work unit, warps that have left}: persistent-warp scheduling
     double4 cst;              // {cal0, cal1, A, B} when uniform
     const double4 *table;     // per row otherwise
     double inv_nad;           // 1 / n_amp_det
@@ -362,9 +359,7 @@ __device__ __forceinline__ void bx_project(const BxArgs &a, const double *tile, 
 }
 
 // MODE 0: pass 1 (tile -> zmap), 1: pass 2 (binned map -> tile -> amplitudes), 2: fused.
-// Persistent warps: every warp of the grid takes the next work unit from a global counter until
-// none is left (units differ by orders of magnitude in size); the last warp to leave resets the
-// counters for the next launch.
+// One warp per work unit, eight consecutive units per CTA; grid = ceil(n_units / 8).
 template <int MODE, bool UNIFORM, bool PAIRED>
 __global__ void __launch_bounds__(kThreads, TB_BX_CTAS)
 k_bx(const BxArgs a, int64_t n_units) {
@@ -373,20 +368,16 @@ k_bx(const BxArgs a, int64_t n_units) {
     double *tile = tiles[warp];
     double2 *tile2 = reinterpret_cast<double2 *>(tile);
     const int64_t g_end = 3 * a.n_pix;
-    for (int64_t turn = 0;; ++turn) {
-        unsigned int ticket = 0;
-        if (TB_BX_PERSIST) {
-            if (lane == 0) ticket = atomicAdd(a.counters, 1u);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        } else {
-            if (turn > 0) break;
-            ticket = blockIdx.x * kBxWarps + warp;
-        }
-        if ((int64_t)ticket >= n_units) break;
+    // (persistent warps taking tickets from a global counter measured slower than this static
+    // assignment -- 0.88 vs 0.78 ms for the fused kernel on the C4 shard, profiles/README.md:
+    // concurrently running neighbours share their amplitude sectors in the L1 / L2)
+    {
+        const int64_t ticket = (int64_t)blockIdx.x * kBxWarps + warp;
+        if (ticket >= n_units) return;
         const int4 u = __ldg(a.units + ticket);
         const int64_t g0 = (int64_t)u.x * (3 * kBxPix);      // first map double of the block
         if constexpr (MODE == 1) {
-            if (u.z <= u.y) continue; // nothing to project from this block
+            if (u.z <= u.y) return; // nothing to project from this block
             const double2 *src = reinterpret_cast<const double2 *>(a.zmap + g0);
 #pragma unroll 4
             for (int k = lane; k < 3 * kBxPix / 2; k += 32) {
@@ -446,15 +437,6 @@ k_bx(const BxArgs a, int64_t n_units) {
                 bx_project<UNIFORM, PAIRED>(a, tile, u.y, u.z, lane);
             }
         }
-        __syncwarp(); // the tile is reused by the warp's next unit
-    }
-    if (TB_BX_PERSIST && lane == 0) {
-        const unsigned int left = atomicAdd(a.counters + 1, 1u);
-        if (left == gridDim.x * kBxWarps - 1) { // every warp has taken its last ticket
-            a.counters[0] = 0u;
-            a.counters[1] = 0u;
-            __threadfence();
-        }
     }
 }
 
@@ -503,7 +485,6 @@ BxArgs make_args(const tb_obs *obs, const int4 *units) {
     a.amp_offsets = obs->amp_offsets;
     a.nad = (int32_t)obs->n_amp_det;
     a.n_det = (int)obs->d.n_det;
-    a.counters = obs->bcounters;
     a.cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
     a.table = obs->stable;
     a.inv_nad = 1.0 / (double)obs->n_amp_det;
@@ -534,9 +515,8 @@ void launch_bx_prescale(const tb_obs *obs, const double *amps, const uint8_t *af
 template <int MODE>
 void launch_bx(const tb_obs *obs, const BxArgs &a, int64_t n_units, void *stream) {
     if (n_units <= 0) return;
-    int64_t nb = (n_units + kBxWarps - 1) / kBxWarps;
-    const int64_t resident = (int64_t)tbr::sm_count() * TB_BX_CTAS;
-    if (TB_BX_PERSIST && nb > resident) nb = resident; // one wave, units handed out dynamically
+    const int64_t nb = (n_units + kBxWarps - 1) / kBxWarps;
+    TB_REQUIRE(nb < 2147483647LL, "grid too large");
     const unsigned g = (unsigned)nb;
     cudaStream_t st = (cudaStream_t)stream;
     static bool configured = false; // (per MODE instantiation)
@@ -584,11 +564,8 @@ void tb_free_blocked(tb_obs *obs) {
     if (obs->bunits_single) cudaFree(obs->bunits_single);
     if (obs->bunits_multi) cudaFree(obs->bunits_multi);
     if (obs->bmulti_blocks) cudaFree(obs->bmulti_blocks);
-    if (obs->bcounters) cudaFree(obs->bcounters);
-    obs->bcounters = nullptr;
     if (obs->ascaled) cudaFree(obs->ascaled);
-    if (obs->qscaled) cudaFree(obs->qscaled);
-    obs->ascaled = obs->qscaled = nullptr;
+    obs->ascaled = nullptr;
     obs->brec = nullptr;
     obs->bqu = nullptr;
     obs->bunits = obs->bunits_single = obs->bunits_multi = nullptr;
@@ -661,8 +638,6 @@ void tb_build_blocked(tb_obs *obs, cudaStream_t st) {
             const size_t slots = (size_t)obs->n_xrows * (size_t)nad;
             const size_t per = obs->x_paired ? 2 : 1;
             TB_CUDA(cudaMalloc(&obs->ascaled, sizeof(double) * 2 * per * slots));
-            TB_CUDA(cudaMalloc(&obs->bcounters, 2 * sizeof(unsigned int)));
-            TB_CUDA(cudaMemsetAsync(obs->bcounters, 0, 2 * sizeof(unsigned int), st));
         }
         k_bx_gather<<<grid, kThreads, 0, st>>>(obs->xrec, obs->xqu, vout, n_sorted, nad, 1,
                                                obs->brec, obs->bqu);

@@ -241,12 +241,17 @@ TB_HD int32_t xy2pix(int32_t x, int32_t y) {
 TB_HD bool near_integer(double v, double tol) { return fabs(v - rint(v)) <= tol; }
 
 // phi -> tt in [0, 4)  (hpix_fmod + snap + quadrant shift, ops_pixels_healpix.cpp:44-48,132-139)
+// EXACT = false (first tier only): phi / twopi is formed as phi * (1 / twopi) -- at most one ulp
+// away from the IEEE quotient, i.e. one more ulp of phi inside a guard band that is sized for
+// eight (make_pix_ctx); a sample this could move is flagged and redone with EXACT = true.
+template <bool EXACT>
 TB_HD double phi_to_tt(double phi, bool &ambiguous) {
     const double eps = 2.220446049250313e-16;
     const double tol = 10.0 * eps;
     const double twopi = 2 * 3.14159265358979323846;
+    const double inv_twopi = 0.15915494309189534561;
     const double two_over_pi = 0.63661977236758134308;
-    double div = phi / twopi;
+    double div = EXACT ? phi / twopi : phi * inv_twopi;
     // |phi| <= pi so (int64)div == 0; the subtraction of 0.0 is kept for the sign of zero
     double phi_mod = twopi * (div - (double)((int64_t)div));
     double aphi = fabs(phi_mod);
@@ -259,12 +264,12 @@ TB_HD double phi_to_tt(double phi, bool &ambiguous) {
 // I is the integer type of the intermediate ring / face arithmetic: int32_t is exact for
 // nside <= 8192 (12 nside^2 < 2^31) and costs a third of the emulated 64-bit integer ops;
 // both instantiations perform the same arithmetic as the reference's int64 code.
-template <bool NEST, typename I>
+template <bool NEST, typename I, bool EXACT = true>
 TB_HD int64_t zphi2pix(const PixCtx &c, double phi, double z, bool &ambiguous) {
     const double twothirds = 0.66666666666666666667;
     const I nside = (I)c.nside, nm1 = (I)c.nm1, fournside = (I)c.fournside;
     double za = fabs(z);
-    double tt = phi_to_tt(phi, ambiguous);
+    double tt = phi_to_tt<EXACT>(phi, ambiguous);
     if (za <= twothirds) {
         double t1 = c.halfnside + c.dnside * tt;
         double t2 = c.tqnside * z;
@@ -370,7 +375,7 @@ TB_HD int64_t vec2pix(const PixCtx &c, double dx, double dy, double dz, int *too
     double phi = atan2(dy, dx);
     int64_t p;
     if (c.small) {
-        p = zphi2pix<NEST, int32_t>(c, phi, dz, amb);
+        p = zphi2pix<NEST, int32_t, false>(c, phi, dz, amb);
     } else {
         p = zphi2pix_wide<NEST>(c.nside, c.guard_tt, phi, dz);
         amb = (p >> 62) & 1;
@@ -396,18 +401,25 @@ TB_HD void detector_cs2alpha(double dx, double dy, double dz, double ox, double 
                              double &c2a, double &s2a) {
     double r2 = dx * dx + dy * dy;
     double cx = 1.0, sx = 0.0; // atan2(0, 0) = 0 in the reference
+    double vm_z;
     if (r2 > 0.0) {
 #ifdef __CUDA_ARCH__
         double rinv = rsqrt(r2); // 1 ulp; no division
+        // sqrt(1 - dz^2) = |(dx, dy)| = r2 * rsqrt(r2) for the unit vector vd: no second square
+        // root (and no cancellation near the poles, where the reference's 1 - dz^2 loses digits;
+        // the weights agree with it to ~1e-15 absolute, the parity bar is 1e-10)
+        vm_z = -(r2 * rinv);
 #else
         double rinv = 1.0 / sqrt(r2);
+        vm_z = -sqrt(1.0 - dz * dz);
 #endif
         cx = dx * rinv;
         sx = dy * rinv;
+    } else {
+        vm_z = -sqrt(1.0 - dz * dz);
     }
     double vm_x = dz * cx;
     double vm_y = dz * sx;
-    double vm_z = -sqrt(1.0 - dz * dz);
     double ay = (dx * (vm_y * oz - vm_z * oy) - dy * (vm_x * oz - vm_z * ox) +
                  dz * (vm_x * oy - vm_y * ox));
     double ax = (vm_x * ox + vm_y * oy + vm_z * oz);

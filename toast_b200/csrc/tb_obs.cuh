@@ -56,8 +56,6 @@ struct tb_obs {
     // PIXEL BLOCK (kBxPix consecutive local pixels), i.e. in (block, row, time) order.  A CTA owns
     // one block at a time and keeps its 3 x kBxPix map values in shared memory.
     double *ascaled = nullptr;  // per-pass scratch [slot]{a0 w0, a1 w1, w0, w1} (k_bx_prescale)
-    double *qscaled = nullptr;  // (unused)
-    unsigned int *bcounters = nullptr; // {next unit, warps done} of the persistent-warp kernels
     int2 *brec = nullptr;       // [n_brec] {pixel in block | n0 << kBxShift | n1 << (kBxShift+6), scaled-amplitude index}
     double2 *bqu = nullptr;     // [n_brec] (sum Q, sum U)
     int4 *bunits = nullptr;     // [n_bunits] {block, first record, end record, 1 if the block has several units}

@@ -196,6 +196,7 @@ k_pointing_fused(Views V, int64_t n_det, int64_t n_samp, tbm::PixCtx ctx,
                  const double *__restrict__ gamma, const double *__restrict__ cal, double U_sign,
                  double inv_nps) {
     int n_exact = 0;
+    int64_t last_sm = -1;
     TB_FOR_TILE_SAMPLES(V, n_det) {
         TB_SAMPLE_COORDS(V)
         if (!valid) continue;
@@ -212,8 +213,15 @@ k_pointing_fused(Views V, int64_t n_det, int64_t n_samp, tbm::PixCtx ctx,
             if (bad) {
                 p = -1;
             } else if (o.hsub) {
-                int64_t sm = fast_div(p, inv_nps);
-                if (o.hsub[sm] == 0) o.hsub[sm] = 1;
+                // the thread's samples mostly stay in one submap: look at the mask only when
+                // the submap changes (32-bit conversions when the pixel number allows)
+                const int64_t sm = ctx.small
+                    ? (int64_t)__double2int_rz(((double)(int)p + 0.5) * inv_nps)
+                    : fast_div(p, inv_nps);
+                if (sm != last_sm) {
+                    if (o.hsub[sm] == 0) o.hsub[sm] = 1;
+                    last_sm = sm;
+                }
             }
             st_stream(o.pixels + (int64_t)__ldg(o.pidx + det) * n_samp + s, p);
         }

@@ -1045,32 +1045,13 @@ k_xs_gather(const int4 *__restrict__ xrec, const double2 *__restrict__ xqu,
 #ifndef TB_XS_CTAS
 #define TB_XS_CTAS 8
 #endif
-// PF (EXPERIMENTAL, tb_set_option("prefetch", 1), not validated or timed on hardware yet): both
-// pixel-ordered passes are latency-bound on record load -> gather (profiles/README.md); PF = 1
-// asks the L2 for the records of the later loop iterations before the first one is processed.
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// PF = 2 (EXPERIMENTAL as well): all four loop iterations in flight at once (unroll 4) with the
-// register budget of 4 CTAs per SM instead of 8.
-template <bool UNIFORM, bool PAIRED, int PF = 0>
-__global__ void __launch_bounds__(kThreads, PF == 2 ? 4 : TB_XS_CTAS)
+template <bool UNIFORM, bool PAIRED>
+__global__ void __launch_bounds__(kThreads, TB_XS_CTAS)
 k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
          int64_t n_srec, const double *__restrict__ dscaled, double4 cst,
          const double4 *__restrict__ table, double *__restrict__ zmap) {
     const int lane = threadIdx.x & 31;
-    if (PF == 1) {
-#pragma unroll
-        for (int k = 2; k < kXPer; ++k) {
-            const int64_t j = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
-            if (j < n_srec) {
-                prefetch_l2(srec + j);
-                prefetch_l2(squ + j);
-            }
-        }
-    }
-#pragma unroll(PF == 2 ? 4 : 2)
+#pragma unroll 2
     for (int k = 0; k < kXPer; ++k) {
         const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
         int64_t key = -1;
@@ -1114,7 +1095,6 @@ k_bin_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t
 }
 
 int g_use_xs = 1; // tb_set_option("sorted", 0/1)
-int g_use_prefetch = 0; // tb_set_option("prefetch", 0/1/2): EXPERIMENTAL, see prefetch_l2
 
 // Pass 2 on the same pixel-sorted list: the binned map is read SEQUENTIALLY (every pixel once,
 // adjacent records share the load) instead of one cold 24-byte gather per crossing, and the
@@ -1124,24 +1104,14 @@ int g_use_prefetch = 0; // tb_set_option("prefetch", 0/1/2): EXPERIMENTAL, see p
 #ifndef TB_XS2_CTAS
 #define TB_XS2_CTAS 6
 #endif
-template <bool UNIFORM, bool PAIRED, int PF = 0>
-__global__ void __launch_bounds__(kThreads, PF == 2 ? 4 : TB_XS2_CTAS)
+template <bool UNIFORM, bool PAIRED>
+__global__ void __launch_bounds__(kThreads, TB_XS2_CTAS)
 k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_t rec_first,
           int64_t rec_end, const double *__restrict__ dscaled, int32_t delta, double4 cst,
           const double4 *__restrict__ table, const double *__restrict__ det_scale,
           const int64_t *__restrict__ amp_offsets, int n_det,
           const double *__restrict__ binned, double *__restrict__ out) {
-    if (PF == 1) {
-#pragma unroll
-        for (int k = 2; k < kXPer; ++k) {
-            const int64_t j = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
-            if (j < rec_end) {
-                prefetch_l2(srec + j);
-                prefetch_l2(squ + j);
-            }
-        }
-    }
-#pragma unroll(PF == 2 ? 4 : 2)
+#pragma unroll 2
     for (int k = 0; k < kXPer; ++k) {
         const int64_t i = rec_first + (int64_t)blockIdx.x * kXTile + k * kThreads + threadIdx.x;
         if (i >= rec_end) continue;
@@ -1192,8 +1162,8 @@ k_proj_xs(const int4 *__restrict__ srec, const double2 *__restrict__ squ, int64_
 
 int g_use_xs2 = 1; // tb_set_option("sorted2", 0/1)
 
-// EXPERIMENTAL -- written without GPU access at the end of round 1, NOT yet validated or timed on
-// hardware; reachable only through tb_lhs_pass2_cov (Destriper: TB_FUSE_COV=1, one GPU).
+// Reachable through tb_lhs_pass2_cov (Destriper: TB_FUSE_COV=1 with option blocked=0, one GPU;
+// validated in round 2: parity test + 1.28 -> 1.13 ms per iteration on the C4 shard).
 // Pass 2 on the sorted list with the pixel covariance folded in: `zmap` is the RAW noise-weighted
 // map of pass 1 and the 3x3 product m = C z (k_cov_apply; toast_map_cov.cpp:509-517, same
 // operation order, so m is bit-identical) is formed on the fly.  Adjacent records share the
@@ -1271,11 +1241,7 @@ k_proj_xs_cov(const int4 *__restrict__ srec, const double2 *__restrict__ squ, in
 #ifndef TB_X_CTAS
 #define TB_X_CTAS 8
 #endif
-// PAD (EXPERIMENTAL, pass 2 only, Destriper TB_PADMAP=1, not validated or timed on hardware yet):
-// `binned` holds FOUR doubles per pixel (I, Q, U, 0), 32-byte aligned, so that the cold map gather
-// of a crossing is exactly one sector instead of the 1.75 a 24-byte pixel straddles on average
-// (2.0 of the 3.3 GB this kernel reads from DRAM are those gathers: profiles/README.md).
-template <bool PASS2, bool PAD = false>
+template <bool PASS2>
 __global__ void __launch_bounds__(kThreads, TB_X_CTAS)
 k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ aflags,
         const double *__restrict__ binned, double *__restrict__ out) {
@@ -1334,18 +1300,10 @@ k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ a
                 bool have = false;
                 double v0 = n * tod0, v1 = n * tod1;
                 if (need0 && lp0 >= 0) {
-                    if (PAD) {
-                        const double2 *m = reinterpret_cast<const double2 *>(binned) + 2 * (int64_t)lp0;
-                        const double2 ma = __ldg(m), mb = __ldg(m + 1);
-                        m0 = ma.x;
-                        m1 = ma.y;
-                        m2 = mb.x;
-                    } else {
-                        const double *m = binned + 3 * (int64_t)lp0;
-                        m0 = __ldg(m);
-                        m1 = __ldg(m + 1);
-                        m2 = __ldg(m + 2);
-                    }
+                    const double *m = binned + 3 * (int64_t)lp0;
+                    m0 = __ldg(m);
+                    m1 = __ldg(m + 1);
+                    m2 = __ldg(m + 2);
                     have = true;
                     double sc = 0.0;
                     sc += (c0 * n) * m0;
@@ -1355,18 +1313,10 @@ k_lhs_x(ObsDev o, const double *__restrict__ amps, const uint8_t *__restrict__ a
                 }
                 if (need1 && lp1 >= 0) {
                     if (!(have && lp1 == lp0)) {
-                        if (PAD) {
-                            const double2 *m = reinterpret_cast<const double2 *>(binned) + 2 * (int64_t)lp1;
-                            const double2 ma = __ldg(m), mb = __ldg(m + 1);
-                            m0 = ma.x;
-                            m1 = ma.y;
-                            m2 = mb.x;
-                        } else {
-                            const double *m = binned + 3 * (int64_t)lp1;
-                            m0 = __ldg(m);
-                            m1 = __ldg(m + 1);
-                            m2 = __ldg(m + 2);
-                        }
+                        const double *m = binned + 3 * (int64_t)lp1;
+                        m0 = __ldg(m);
+                        m1 = __ldg(m + 1);
+                        m2 = __ldg(m + 2);
                     }
                     double sc = 0.0;
                     sc += (c1 * n) * m0;
@@ -1421,32 +1371,6 @@ __global__ void k_xs_lower_bound(const int4 *__restrict__ srec, int64_t n_srec,
     }
     rec[c] = lo;
 }
-
-// EXPERIMENTAL (see k_lhs_x PAD): binned4[p] = (C z[p], 0) -- k_cov_apply's arithmetic
-// (toast_map_cov.cpp:509-517 order) written to a padded copy instead of in place.
-__global__ void __launch_bounds__(kThreads)
-k_cov_apply_pad(int64_t npix, const double *__restrict__ cov, const double *__restrict__ z,
-                double *__restrict__ out4) {
-    int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (p >= npix) return;
-    const double *m = cov + p * 6;
-    const double v0 = z[3 * p], v1 = z[3 * p + 1], v2 = z[3 * p + 2];
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-    t0 += m[0] * v0;
-    t0 += m[1] * v1;
-    t1 += m[1] * v0;
-    t0 += m[2] * v2;
-    t2 += m[2] * v0;
-    t1 += m[3] * v1;
-    t1 += m[4] * v2;
-    t2 += m[4] * v1;
-    t2 += m[5] * v2;
-    double2 *o = reinterpret_cast<double2 *>(out4) + 2 * p;
-    o[0] = make_double2(t0, t1);
-    o[1] = make_double2(t2, 0.0);
-}
-
-
 
 ObsDev make_dev(const tb_obs *obs, int regen) {
     const tb_obs_desc &d = obs->d;
@@ -1561,18 +1485,6 @@ void launch_bin_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_end, 
                          void *stream) {
     int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
     double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
-    if (g_use_prefetch == 2) {
-        auto k = k_bin_xs<UNIFORM, PAIRED, 2>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
-                   obs->stable, zmap);
-        return;
-    }
-    if (g_use_prefetch) {
-        auto k = k_bin_xs<UNIFORM, PAIRED, 1>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
-                   obs->stable, zmap);
-        return;
-    }
     auto k = k_bin_xs<UNIFORM, PAIRED>;
     TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled, cst,
                obs->stable, zmap);
@@ -1594,20 +1506,6 @@ void launch_project_sorted_t(const tb_obs *obs, int64_t rec_first, int64_t rec_e
                              const double *binned, double *out, void *stream) {
     int64_t nbs = (rec_end - rec_first + kXTile - 1) / kXTile;
     double4 cst = make_double4(obs->s_const[0], obs->s_const[1], obs->s_const[2], obs->s_const[3]);
-    if (g_use_prefetch == 2) {
-        auto k = k_proj_xs<UNIFORM, PAIRED, 2>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
-                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
-                   (int)obs->d.n_det, binned, out);
-        return;
-    }
-    if (g_use_prefetch) {
-        auto k = k_proj_xs<UNIFORM, PAIRED, 1>;
-        TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
-                   (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
-                   (int)obs->d.n_det, binned, out);
-        return;
-    }
     auto k = k_proj_xs<UNIFORM, PAIRED>;
     TBS_LAUNCH(k, nbs, stream, obs->srec, obs->squ, rec_first, rec_end, obs->dscaled,
                (int32_t)obs->n_amp_det, cst, obs->stable, obs->det_scale, obs->amp_offsets,
@@ -2270,7 +2168,6 @@ int tb_get_option(const char *name) {
     if (n == "sorted") return g_use_xs;
     if (n == "sorted2") return g_use_xs2;
     if (n == "peer_ctas") return tb_peer_ctas_per_sm;
-    if (n == "prefetch") return g_use_prefetch;
     if (n == "blocked") return g_use_bx;
     if (n == "bx_sort") return g_bx_sort;
     if (n == "prior_chunk") return tb_prior_chunk;
@@ -2294,8 +2191,6 @@ int tb_set_option(const char *name, int value) {
         g_use_xs = value;
     } else if (std::string(name) == "sorted2") {
         g_use_xs2 = value;
-    } else if (std::string(name) == "prefetch") {
-        g_use_prefetch = value;
     } else if (std::string(name) == "blocked") {
         g_use_bx = value;
     } else if (std::string(name) == "bx_sort") {
@@ -2391,33 +2286,7 @@ int tb_lhs_pass2_chunk(const tb_obs *obs, const double *binned, double *amplitud
     TB_API_END
 }
 
-// EXPERIMENTAL (see k_lhs_x PAD): covariance product into a padded (4 doubles per pixel) copy of
-// the map, and the time-ordered crossing-list pass 2 gathering from it.  One GPU.
-int tb_cov_apply_pad(int64_t n_pix, const double *cov, const double *zmap, double *binned4,
-                     void *stream) {
-    TB_API_BEGIN
-    tbr::require_device();
-    TB_REQUIRE(cov && zmap && binned4 && n_pix >= 0, "bad argument");
-    TB_REQUIRE((reinterpret_cast<uintptr_t>(binned4) & 31u) == 0, "binned4 must be 32-byte aligned");
-    int64_t nb = (n_pix + kThreads - 1) / kThreads;
-    TBS_LAUNCH(k_cov_apply_pad, nb, stream, n_pix, cov, zmap, binned4);
-    TB_API_END
-}
-
-int tb_lhs_pass2_pad(const tb_obs *obs, const double *amplitudes, const uint8_t *amp_flags,
-                     const double *binned4, double *amplitudes_out, void *stream) {
-    TB_API_BEGIN
-    tbr::require_device();
-    TB_REQUIRE(obs && amplitudes && amp_flags && binned4 && amplitudes_out, "NULL argument");
-    TB_REQUIRE(g_use_compact && g_use_x && obs->xrec != nullptr,
-               "tb_lhs_pass2_pad needs the crossing list");
-    ObsDev o = make_dev(obs, 0);
-    auto k = k_lhs_x<true, true>;
-    TBS_LAUNCH(k, obs->n_xblocks, stream, o, amplitudes, amp_flags, binned4, amplitudes_out);
-    TB_API_END
-}
-
-// EXPERIMENTAL (see k_proj_xs_cov): pass 2 for the amplitudes of the preceding tb_lhs_pass1 with
+// Pass 2 (pixel-sorted list) for the amplitudes of the preceding tb_lhs_pass1 with
 // the covariance product folded in; zmap is the RAW map of pass 1 (single GPU: nothing to reduce).
 int tb_lhs_pass2_cov(const tb_obs *obs, const double *zmap, const double *cov,
                      double *amplitudes_out, void *stream) {

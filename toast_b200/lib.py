@@ -116,8 +116,6 @@ PROTOTYPES = {
     "tb_lhs_pass1_chunk": (INT, [P, P, P, P, I64, P]),
     "tb_lhs_pass2_chunk": (INT, [P, P, P, I64, P]),
     "tb_lhs_pass2_cov": (INT, [P, P, P, P, P]),
-    "tb_cov_apply_pad": (INT, [I64, P, P, P, P]),
-    "tb_lhs_pass2_pad": (INT, [P, P, P, P, P, P]),
     "tb_bx_block_pixels": (INT, []),
     "tb_obs_blocked": (INT, [P]),
     "tb_obs_blocked_stats": (INT, [P, P, P, P, P]),

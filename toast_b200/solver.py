@@ -284,39 +284,6 @@ class SymmPeerMap:
         L.check(self.lib.tb_peer_set_multimem(1 if self.use_multimem else 0))
         L.check(self.lib.tb_map_reduce_cov_range(self.h, pix_first, n_pix, L.ptr(cov), stream))
 
-    def reduce_cov_ce(self, cov_apply, pix_first=0, n_pix=None):
-        """EXPERIMENTAL (TB_REDUCE=ce; written without GPU access, not validated or timed yet):
-        the same reduction with the NVLink traffic on the COPY ENGINES instead of SMs, so that
-        it can overlap the LHS passes without competing for their L1/LSU and L2 bandwidth (the
-        SM-resident kernel runs at 45 % of its stand-alone rate when overlapped: DESIGN.md 5).
-        Runs on the current stream: barrier -> pull the peers' copies of my slice into staging
-        -> local sum + covariance (``cov_apply(pix_first, n_pix)`` on my slice) -> push the
-        finished slice into every peer's map -> barrier."""
-        n_pix = self.n_pix - pix_first if n_pix is None else n_pix
-        w, r = self.world, self.rank
-        per = ((n_pix // 256 + w - 1) // w) * 256
-        a = pix_first + min(r * per, n_pix)
-        b = pix_first + min((r + 1) * per, n_pix)
-        n = (b - a) * 3
-        if getattr(self, "_peer_tensors", None) is None:
-            total = self.n_pix * 3
-            self._peer_tensors = [self._hdl.get_buffer(q, (total,), torch.float64, 0)
-                                  for q in range(w)]
-            self._stage = torch.empty((max(w - 1, 1), ((self.n_pix // 256 + w - 1) // w) * 768),
-                                      dtype=torch.float64, device=self.tensor.device)
-        self._hdl.barrier(channel=0)   # every rank has finished pass 1 of this pixel range
-        others = [q for q in range(w) if q != r]
-        if n > 0:
-            own = self.tensor[a * 3:b * 3]
-            for k, q in enumerate(others):
-                self._stage[k, :n].copy_(self._peer_tensors[q][a * 3:b * 3], non_blocking=True)
-            for k in range(len(others)):
-                own.add_(self._stage[k, :n])
-            cov_apply(a, b - a)
-            for q in others:
-                self._peer_tensors[q][a * 3:b * 3].copy_(own, non_blocking=True)
-        self._hdl.barrier(channel=0)   # every rank's slice has landed everywhere
-
     def tune(self, cov, reps=3):
         """Measure the in-switch (multimem) and the P2P form of the kernel on this node and map
         size and keep the faster one (max over ranks, so every rank takes the same decision):
@@ -450,11 +417,6 @@ class Destriper:
         self.fuse_cov = _os.environ.get("TB_FUSE_COV", "0") == "1"
         # one observation on one GPU: pass 1 -> covariance -> pass 2 inside one kernel
         self.fuse_lhs = _os.environ.get("TB_FUSE_LHS", "1") != "0"
-        self.pad_map = _os.environ.get("TB_PADMAP", "0") == "1"
-        self._binned4 = None
-        # EXPERIMENTAL: copy-engine form of the chunk reduction (needs the symmetric-memory map)
-        self.reduce_ce = (_os.environ.get("TB_REDUCE", "") == "ce"
-                          and isinstance(self.peer, SymmPeerMap))
         self.pipeline = False
         self.blocked = False
         self.pipe_tune_ms = None
@@ -641,14 +603,8 @@ class Destriper:
             self.comm_stream.wait_event(self.ev_binned[c])
             first = int(self.chunk_bounds[c])
             count = int(self.chunk_bounds[c + 1]) - first
-            if self.reduce_ce:
-                def ce(first=first, count=count):
-                    with torch.cuda.stream(self.comm_stream):
-                        self.peer.reduce_cov_ce(self._cov_apply_range, first, count)
-                timed(f"reduce[{c}]", self.comm_stream, ce)
-            else:
-                timed(f"reduce[{c}]", self.comm_stream,
-                      lambda: self.peer.reduce_cov(self.cov, first, count, cs))
+            timed(f"reduce[{c}]", self.comm_stream,
+                  lambda: self.peer.reduce_cov(self.cov, first, count, cs))
             self.ev_reduced[c].record(self.comm_stream)
         for c in range(self.n_chunks):
             main.wait_event(self.ev_reduced[c])
@@ -743,34 +699,13 @@ class Destriper:
             ev[1].record()
         reuse = self._sorted_passes() == 2
         if self.fuse_cov and reuse and self.world == 1 and len(self.obs) == 1:
-            # EXPERIMENTAL (TB_FUSE_COV=1; not validated on hardware yet): the covariance
-            # product is formed inside pass 2, the stand-alone covariance pass disappears
+            # TB_FUSE_COV=1 (pixel-sorted path, option blocked=0): the covariance product is
+            # formed inside pass 2, the stand-alone covariance pass disappears
             amps_out.zero_()
             if ev:
                 ev[2].record()
             L.check(self.lib.tb_lhs_pass2_cov(self.obs[0].handle().h, L.ptr(self.zmap),
                                               L.ptr(self.cov), L.ptr(amps_out), self._st()))
-            if ev:
-                ev[3].record()
-                timers.append(ev)
-            return self._add_prior(amps_in, amps_out)
-        if self.pad_map and self.world == 1 and len(self.obs) == 1 and not self.regen and \
-                self.obs[0].has_compact_pointing():
-            # EXPERIMENTAL (TB_PADMAP=1; not validated on hardware yet): covariance product into
-            # a 32-byte-per-pixel copy of the map, time-ordered pass 2 gathering one sector per
-            # crossing from it
-            if self._binned4 is None:
-                self._binned4 = torch.zeros(self.n_local_submap * self.n_pix_submap * 4,
-                                            dtype=torch.float64, device=self.device)
-            L.check(self.lib.tb_cov_apply_pad(self.n_local_submap * self.n_pix_submap,
-                                              L.ptr(self.cov), L.ptr(self.zmap),
-                                              L.ptr(self._binned4), self._st()))
-            amps_out.zero_()
-            if ev:
-                ev[2].record()
-            L.check(self.lib.tb_lhs_pass2_pad(self.obs[0].handle().h, L.ptr(amps_in),
-                                              L.ptr(self.amp_flags), L.ptr(self._binned4),
-                                              L.ptr(amps_out), self._st()))
             if ev:
                 ev[3].record()
                 timers.append(ev)
