@@ -113,6 +113,36 @@ int tb_pixels_healpix(
     int64_t n_submap, int64_t n_pix_submap, int64_t nside, int nest, int64_t n_det,
     int64_t n_samp, int mem, void *stream);
 
+/* ---- f4  pixels_wcs : ops/pixels_wcs.py:39-662 (host-only in the reference: qa_to_iso +
+ * astropy / WCSLIB wcs_world2pix + around).  The projection arrives as the numbers WCSLIB's
+ * celset / linset derive from CRVAL, CDELT, CRPIX and the default LONPOLE / LATPOLE
+ * (toast_b200/ops/pixels_wcs.py builds them): projection 0 CAR, 1 CEA, 2 MER, 3 SFL, 4 TAN,
+ * 5 ZEA; euler = {lng_p, 90 - lat_p, phi_p, cos(euler[1]), sin(euler[1])}; pixel = col + row *
+ * n_col with col / row = around(world2pix, origin 0); samples that are flagged, have no image or
+ * land at or beyond n_col * n_row get -1.  hit_submaps may be NULL. */
+typedef struct tb_wcs_desc {
+    int projection;
+    int is_azimuth;               /* AZEL frame: lon = 2 pi - phi */
+    double euler[5];
+    double crpix[2], cdelt[2];
+    double cea_lambda;            /* PV2_1 of CEA, 1 otherwise */
+    int64_t n_col, n_row;
+} tb_wcs_desc;
+int tb_pixels_wcs(
+    const tb_wcs_desc *wcs,
+    const int32_t *quat_index,    /* [S] */
+    const double *quats,          /* [L] [n_quat_buf,n_samp,4] */
+    int64_t n_quat_buf,
+    const uint8_t *shared_flags,  /* [L] or NULL */
+    uint8_t shared_flag_mask,
+    const int32_t *pixel_index,   /* [S] */
+    int64_t *pixels,              /* [L] [n_pix_buf,n_samp] out */
+    int64_t n_pix_buf,
+    const tb_interval *intervals, int64_t n_view,
+    uint8_t *hit_submaps,         /* [S] [n_submap] in/out, host, or NULL */
+    int64_t n_submap, int64_t n_pix_submap, int64_t n_det, int64_t n_samp, int mem,
+    void *stream);
+
 /* ---- a3  stokes_weights_IQU / _I : ops_stokes_weights.cpp:150-392, :397-505 ------------- */
 int tb_stokes_weights_IQU(
     const int32_t *quat_index, const double *quats /* [L] */, int64_t n_quat_buf,

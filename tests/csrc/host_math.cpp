@@ -2,6 +2,7 @@
 // test-suite check the product's per-sample arithmetic (exact atan2, two-tier pixel path,
 // trig-free Stokes weights) against glibc and the oracle without a GPU.
 #include "../../toast_b200/csrc/tb_math.cuh"
+#include "../../toast_b200/csrc/tb_wcs.cuh"
 #include <cstdint>
 
 extern "C" {
@@ -192,5 +193,29 @@ void tbp_banded_partitioned_segments(int64_t n_seg, const int64_t *seg_start,
     for (int64_t s = 0; s < n_seg; ++s) tbp::pb_heads(v, s, out);
     for (int64_t s = 0; s < n_seg; ++s)
         for (int64_t j = 0; j < seg_len[s]; ++j) tbp::pb_bwd_correct(v, s, j, flags, out);
+}
+
+// tb_wcs.cuh on the host: quats [n,4] -> flat-projection pixels (and the fractional coordinates)
+void tbw_quat2pix(int64_t n, const double *quats, int proj, int is_azimuth, const double *euler,
+                  const double *crpix, const double *cdelt, double cea_lambda, int64_t n_col,
+                  int64_t n_row, int64_t *pix, double *dcol, double *drow) {
+    tbw::Wcs w;
+    w.proj = proj;
+    w.is_azimuth = is_azimuth;
+    for (int k = 0; k < 5; ++k) w.euler[k] = euler[k];
+    for (int k = 0; k < 2; ++k) {
+        w.crpix[k] = crpix[k];
+        w.cdelt[k] = cdelt[k];
+    }
+    w.cea_lambda = cea_lambda;
+    w.n_col = n_col;
+    w.n_pix = n_col * n_row;
+    for (int64_t i = 0; i < n; ++i) {
+        tbm::Quat q{quats[4 * i], quats[4 * i + 1], quats[4 * i + 2], quats[4 * i + 3]};
+        pix[i] = tbw::quat_to_wcs_pixel(w, q);
+        double lon, lat;
+        tbw::quat_to_lonlat_deg(q, is_azimuth, lon, lat);
+        if (!tbw::world2pix(w, lon, lat, dcol[i], drow[i])) dcol[i] = drow[i] = 0.0;
+    }
 }
 }

@@ -108,7 +108,7 @@ def host_math_lib():
     so = os.path.join(csrc, "libhostmath.so")
     src = os.path.join(csrc, "host_math.cpp")
     deps = [src] + [os.path.join(ROOT, "toast_b200", "csrc", h)
-                    for h in ("tb_math.cuh", "tb_prior.cuh")]
+                    for h in ("tb_math.cuh", "tb_prior.cuh", "tb_wcs.cuh")]
     if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
                                "-x", "c++", "-o", so, src, "-lm"])

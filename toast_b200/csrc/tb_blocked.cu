@@ -38,7 +38,6 @@ void sort_pairs_i32(const int32_t *keys_in, int32_t *keys_out, const int32_t *va
 }
 
 int g_use_bx = 1; // tb_set_option("blocked", 0/1)
-int g_bx_sort = 0; // tb_set_option("bx_sort", 0/1): fused units by decreasing size (experiment)
 
 namespace {
 
@@ -668,10 +667,6 @@ void tb_build_blocked(tb_obs *obs, cudaStream_t st) {
                 else if (ue > uf) single.push_back(u); // (the fused kernel skips empty blocks)
             }
         }
-        if (g_bx_sort)
-            std::stable_sort(single.begin(), single.end(), [](const int4 &x, const int4 &y) {
-                return (x.z - x.y) > (y.z - y.y);
-            });
         auto upload = [&](const std::vector<int4> &v, int4 **dst) {
             if (v.empty()) return;
             TB_CUDA(cudaMalloc(dst, sizeof(int4) * v.size()));

@@ -88,4 +88,3 @@ void tb_free_blocked(tb_obs *obs);
 // unit ranges of the pixel chunks; chunked calls are refused when a bound is not block-aligned
 void tb_blocked_set_chunks(tb_obs *obs, int64_t n_chunks, const int64_t *pixel_bounds);
 extern int g_use_bx;
-extern int g_bx_sort;

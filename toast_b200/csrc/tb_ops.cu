@@ -7,6 +7,7 @@
 //     traffic stays in L2,
 //   * once-used timestream data is read/written with streaming (evict-first) accesses.
 #include "tb_device.cuh"
+#include "tb_wcs.cuh"
 #include "tb_runtime.cuh"
 
 using namespace tbd;
@@ -135,6 +136,28 @@ k_pixels_healpix(Views V, int64_t n_det, int64_t n_samp, tbm::PixCtx ctx,
         st_stream(pixels + (int64_t)__ldg(pidx + det) * n_samp + s, p);
     }
     if (n_exact) atomicAdd(&g_exact_count, (unsigned long long)n_exact);
+}
+
+// ================================================================================================
+// f4 pixels_wcs: detector quaternions -> pixel numbers of a flat projection (tb_wcs.cuh)
+// ================================================================================================
+__global__ void __launch_bounds__(kThreads, 4)
+k_pixels_wcs(Views V, int64_t n_det, int64_t n_samp, tbw::Wcs w, const int32_t *__restrict__ qidx,
+             const double *__restrict__ quats, const uint8_t *__restrict__ flags, uint8_t mask,
+             const int32_t *__restrict__ pidx, int64_t *__restrict__ pixels,
+             uint8_t *__restrict__ hsub, double inv_nps) {
+    TB_FOR_TILE_SAMPLES(V, n_det) {
+        TB_SAMPLE_COORDS(V)
+        if (!valid) continue;
+        tbm::Quat q = ld_quat_stream(quats + ((int64_t)__ldg(qidx + det) * n_samp + s) * 4);
+        int64_t p = tbw::quat_to_wcs_pixel(w, q);
+        if (flags && ((__ldg(flags + s) & mask) != 0)) p = -1;
+        if (p >= 0 && hsub != nullptr) {
+            int64_t sm = fast_div(p, inv_nps);
+            if (hsub[sm] == 0) hsub[sm] = 1;
+        }
+        st_stream(pixels + (int64_t)__ldg(pidx + det) * n_samp + s, p);
+    }
 }
 
 // ================================================================================================
@@ -691,6 +714,48 @@ int tb_pixels_healpix(const int32_t *quat_index, const double *quats, int64_t n_
         TB_LAUNCH(k_pixels_healpix<false>, n_blocks(V, n_det), R, V, n_det, n_samp, ctx, d_qi, d_q,
                   d_fl, shared_flag_mask, d_pi, d_p, d_hs, inv);
     }
+    R.finish();
+    TB_API_END
+}
+
+int tb_pixels_wcs(const tb_wcs_desc *wcs, const int32_t *quat_index, const double *quats,
+                  int64_t n_quat_buf, const uint8_t *shared_flags, uint8_t shared_flag_mask,
+                  const int32_t *pixel_index, int64_t *pixels, int64_t n_pix_buf,
+                  const tb_interval *intervals, int64_t n_view, uint8_t *hit_submaps,
+                  int64_t n_submap, int64_t n_pix_submap, int64_t n_det, int64_t n_samp, int mem,
+                  void *stream) {
+    TB_API_BEGIN
+    tbr::Resolver R(mem, stream);
+    TB_REQUIRE(wcs != nullptr, "NULL projection");
+    TB_REQUIRE(wcs->projection >= 0 && wcs->projection <= 5, "unknown projection code");
+    TB_REQUIRE(wcs->n_col > 0 && wcs->n_row > 0, "the projection has non-positive dimensions");
+    TB_REQUIRE(wcs->cdelt[0] != 0.0 && wcs->cdelt[1] != 0.0, "CDELT must be non-zero");
+    TB_REQUIRE(hit_submaps == nullptr ||
+                   (n_pix_submap > 0 && n_submap * n_pix_submap >= wcs->n_col * wcs->n_row),
+               "hit_submaps too small for the projection");
+    check_index(quat_index, n_det, n_quat_buf, "quat");
+    check_index(pixel_index, n_det, n_pix_buf, "pixel");
+    tbw::Wcs w;
+    w.proj = wcs->projection;
+    for (int k = 0; k < 5; ++k) w.euler[k] = wcs->euler[k];
+    for (int k = 0; k < 2; ++k) {
+        w.crpix[k] = wcs->crpix[k];
+        w.cdelt[k] = wcs->cdelt[k];
+    }
+    w.cea_lambda = wcs->cea_lambda;
+    w.n_col = wcs->n_col;
+    w.n_pix = wcs->n_col * wcs->n_row;
+    w.is_azimuth = wcs->is_azimuth;
+    Views V = make_views(R, intervals, n_view, n_samp);
+    const int32_t *d_qi = R.small(quat_index, n_det);
+    const int32_t *d_pi = R.small(pixel_index, n_det);
+    uint8_t *d_hs = hit_submaps ? R.small_inout(hit_submaps, n_submap) : nullptr;
+    const double *d_q = R.in(quats, n_quat_buf * n_samp * 4);
+    const uint8_t *d_fl = R.in(shared_flags, n_samp);
+    int64_t *d_p = R.out(pixels, n_pix_buf * n_samp);
+    double inv = n_pix_submap > 0 ? 1.0 / (double)n_pix_submap : 0.0;
+    TB_LAUNCH(k_pixels_wcs, n_blocks(V, n_det), R, V, n_det, n_samp, w, d_qi, d_q, d_fl,
+              shared_flag_mask, d_pi, d_p, d_hs, inv);
     R.finish();
     TB_API_END
 }

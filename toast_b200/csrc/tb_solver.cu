@@ -2169,7 +2169,6 @@ int tb_get_option(const char *name) {
     if (n == "sorted2") return g_use_xs2;
     if (n == "peer_ctas") return tb_peer_ctas_per_sm;
     if (n == "blocked") return g_use_bx;
-    if (n == "bx_sort") return g_bx_sort;
     if (n == "prior_chunk") return tb_prior_chunk;
     return -1;
 }
@@ -2193,8 +2192,6 @@ int tb_set_option(const char *name, int value) {
         g_use_xs2 = value;
     } else if (std::string(name) == "blocked") {
         g_use_bx = value;
-    } else if (std::string(name) == "bx_sort") {
-        g_bx_sort = value;
     } else if (std::string(name) == "prior_chunk") {
         TB_REQUIRE(value >= 0, "prior_chunk must be >= 0");
         tb_prior_chunk = value;

@@ -112,6 +112,34 @@ def pixels_healpix(quat_index, quats, shared_flags, shared_flag_mask, pixel_inde
         n_samp, L.mem_of(pixels, use_accel), _stream(stream)))
 
 
+def pixels_wcs(wcs, quat_index, quats, shared_flags, shared_flag_mask, pixel_index, pixels,
+               intervals, hit_submaps, n_pix_submap, use_accel=False, stream=None):
+    """ops/pixels_wcs.py:560-620 for all detectors of an observation in one launch.  ``wcs`` is
+    a ``toast_b200.wcs.FlatWCS`` (or anything with a ``.desc()`` returning a tb_wcs_desc)."""
+    quat_index = L.host(quat_index, np.int32)
+    pixel_index = L.host(pixel_index, np.int32)
+    n_det = len(quat_index)
+    if len(pixel_index) != n_det:
+        raise RuntimeError("Object pixel_index has wrong shape")
+    _require(pixels, "pixels", "int64", 2)
+    n_samp = _shape(pixels)[1]
+    _require(quats, "quats", "float64", 3)
+    if _shape(quats)[1:] != (n_samp, 4):
+        raise RuntimeError("Object quats has wrong shape")
+    if hit_submaps is not None and (L._is_tensor(hit_submaps) or hit_submaps.dtype != np.uint8):
+        raise RuntimeError("Object hit_submaps must be a host uint8 array")
+    iv = _intervals(intervals)
+    fl = _optional(shared_flags, n_samp)
+    d = wcs.desc()
+    import ctypes as ct
+
+    L.check(L.load().tb_pixels_wcs(
+        ct.byref(d), L.ptr(quat_index), L.ptr(quats), _shape(quats)[0], L.ptr(fl),
+        shared_flag_mask, L.ptr(pixel_index), L.ptr(pixels), _shape(pixels)[0], L.ptr(iv), len(iv),
+        L.ptr(hit_submaps), 0 if hit_submaps is None else len(hit_submaps), n_pix_submap, n_det,
+        n_samp, L.mem_of(pixels, use_accel), _stream(stream)))
+
+
 def stokes_weights_IQU(quat_index, quats, weight_index, weights, hwp, intervals, epsilon, gamma,
                        cal, IAU, use_accel=False, stream=None):
     """ops_stokes_weights.cpp:150-392."""

@@ -51,6 +51,14 @@ class tb_obs_desc(ct.Structure):
     ]
 
 
+class tb_wcs_desc(ct.Structure):
+    _fields_ = [
+        ("projection", INT), ("is_azimuth", INT),
+        ("euler", F64 * 5), ("crpix", F64 * 2), ("cdelt", F64 * 2), ("cea_lambda", F64),
+        ("n_col", I64), ("n_row", I64),
+    ]
+
+
 class tb_offset_prior_desc(ct.Structure):
     _fields_ = [
         ("n_amp", I64), ("n_seg", I64),
@@ -84,6 +92,8 @@ PROTOTYPES = {
     "tb_pointing_detector": (INT, [P, P, P, P, I64, P, I64, P, U8, I64, I64, INT, P]),
     "tb_pixels_healpix": (INT, [P, P, I64, P, U8, P, P, I64, P, I64, P, I64, I64, I64, INT,
                                 I64, I64, INT, P]),
+    "tb_pixels_wcs": (INT, [ct.POINTER(tb_wcs_desc), P, P, I64, P, U8, P, P, I64, P, I64, P, I64,
+                            I64, I64, I64, INT, P]),
     "tb_stokes_weights_IQU": (INT, [P, P, I64, P, P, I64, P, P, I64, P, P, P, INT, I64, I64,
                                     INT, P]),
     "tb_stokes_weights_I": (INT, [P, P, I64, P, I64, P, I64, I64, INT, P]),

@@ -19,3 +19,4 @@ from .mapmaker_utils import (  # noqa: F401
     ScanMask,
 )
 from .mapmaker import MapMaker, TemplateMatrix  # noqa: F401
+from .pixels_wcs import PixelsWCS  # noqa: F401
