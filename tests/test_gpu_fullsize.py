@@ -25,6 +25,7 @@ from toast_b200.solver import DeviceObservation, Destriper
 
 pytestmark = pytest.mark.gpu
 
+RCOND = 1.0e-8   # production solve_rcond_threshold (ops/mapmaker.py)
 # (workload, detectors that build the covariance, detectors the reference runs, PCG iterations)
 CASES = [("c4", 128, 4, 12), ("c3", 256, 4, 12), ("c5", 256, 4, 12)]
 
@@ -62,7 +63,7 @@ def _shard_covariance(name, n_big, n_sub):
     K.cov_accum(g2l, n_loc, nps, 3, None, inv, idx, dobs.pixels, idx, dobs.weights, idx, flags,
                 big["detweight"], 1, big["intervals"], None, 0)
     rc = torch.zeros(n_loc * nps, dtype=torch.float64, device=dev)
-    K.cov_invert(n_loc * nps, 3, inv, rc, 1.0e-8)   # production solve_rcond_threshold
+    K.cov_invert(n_loc * nps, 3, inv, rc, RCOND)
     small = S.make_observation(name, n_det=n_sub)
     small["det_flags"] = np.ascontiguousarray(big["det_flags"][:n_sub])
     assert np.array_equal(small["shared_flags"], big["shared_flags"])
@@ -118,18 +119,18 @@ def test_reference_subset_at_production_size(name, n_big, n_sub, n_iter):
     tol = {}
     binned_ref = O.bin_map(pb, ck, obs["signal"], covapply)
     tol["binned"] = H.order_tolerance(binned_ref, O.bin_map(pb, ck, obs["signal"], covapply,
-                                                            reverse=True))
+                                                            reverse=True), rcond=RCOND)
     assert_close_norm(ds.bin_signal([sig]).cpu().numpy(), binned_ref, rtol=tol["binned"][0],
                       what="binned map")
     rhs_ref = O.solver_rhs(pb, ck, obs["signal"], covapply=covapply)
     tol["rhs"] = H.order_tolerance(rhs_ref, O.solver_rhs(pb, ck, obs["signal"], covapply=covapply,
-                                                         reverse=True))
+                                                         reverse=True), rcond=RCOND)
     assert_close_norm(ds.rhs([sig]).cpu().numpy(), rhs_ref, rtol=tol["rhs"][0], what="RHS")
     rng = np.random.default_rng(11)
     a = np.where(pb.amp_flags == 0, rng.standard_normal(pb.n_amp), 0.0)
     lhs_ref = O.solver_lhs(pb, ck, a, covapply=covapply)
     tol["lhs"] = H.order_tolerance(lhs_ref, O.solver_lhs(pb, ck, a, covapply=covapply,
-                                                         reverse=True))
+                                                         reverse=True), rcond=RCOND)
     q = torch.zeros(pb.n_amp, dtype=torch.float64, device="cuda")
     ds.lhs(torch.from_numpy(a).cuda(), q)
     assert_close_norm(q.cpu().numpy(), lhs_ref, rtol=tol["lhs"][0], what="LHS")

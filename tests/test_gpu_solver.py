@@ -175,7 +175,8 @@ def test_pcg_restart_parity_every_iteration(name, n_det, n_samp, nside, rcond):
     # 1e-10, or the reference's own summation-order dependence at this rcond if that is larger
     d0 = trace[0]["d"]
     tol, self_diff = H.order_tolerance(
-        trace[0]["q"], O.solver_lhs(pb, ck, d0, covapply=ck.cov_apply_diag, reverse=True))
+        trace[0]["q"], O.solver_lhs(pb, ck, d0, covapply=ck.cov_apply_diag, reverse=True),
+        rcond=rcond)
     worst = H.restart_parity(ds, pb, trace, rtol=tol, what=name)
     _, hist = ds.solve(torch.from_numpy(rhs_ref).cuda(), n_iter_max=20)
     first, dev = H.first_iteration_over(hist, hist_ref)

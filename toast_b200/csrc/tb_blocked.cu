@@ -11,21 +11,28 @@
 // The crossing list (tb_solver.cu: k_xbuild) already collapses every run of samples that share
 // (pixel, baseline) into one record; both passes are linear in the record's (n, sum Q, sum U).
 //
-// Here the records are stably sorted by PIXEL BLOCK (kBxPix consecutive local pixels), which
-// leaves them in (block, row, time) order:
-//   * the map side is private to the CTA: the 3 x kBxPix doubles of a block live in shared memory
-//     (48 KB), pass 1 accumulates with shared-memory atomics and flushes the finished tile with
-//     coalesced 16-byte stores -- no zero-fill, no global atomics when the block is one work unit
-//     (blocks with very many records are cut into units of kBxUnitMax records whose tiles are
-//     flushed with fp64 REDs: the high-contention case, one RED per touched pixel and unit instead
-//     of three per record);
+// Here the records are stably sorted by PIXEL BLOCK (kBxPix = 128 consecutive local pixels), which
+// leaves them in (block, row, time) order, and every WARP owns one block at a time:
+//   * the map side is private to the warp: the 3 x 128 doubles of its block live in the warp's
+//     3 KB slice of shared memory.  Pass 1 accumulates into it with PLAIN read-modify-writes --
+//     lanes of one step that hit the same pixel (found with match.any) take turns -- and flushes
+//     the finished tile with coalesced 16-byte stores: no zero-fill of the map, no atomics at all
+//     when the block is one work unit.  (Blocks with more than kBxUnitMax records -- the
+//     high-contention maps of ground patches -- are cut into units whose tiles are flushed with
+//     fp64 REDs: one RED per touched pixel value and unit instead of three per record.)
+//     fp64 atomicAdd on shared memory is a compare-and-swap loop on this architecture
+//     (ATOMS.CAST.SPIN); a CTA-wide tile updated with it left the kernel bound by the shared-
+//     memory pipe at 80 % utilisation (profiles/r2_ncu_blocked.txt), which is why the tile is
+//     warp-private;
 //   * the amplitude side keeps its time locality: consecutive records of a detector's track
-//     through the block share the baseline, so the 16-byte amplitude gather of a warp touches a
-//     handful of sectors and pass 2 issues one RED per baseline run (segmented warp sum) instead
-//     of one per record.
+//     through the block share the baseline, so the 16 / 32-byte amplitude gather of a warp touches
+//     a handful of sectors (5.5 M sectors for 39.6 M records on the C4 shard) and pass 2 issues
+//     one RED per baseline run (segmented warp sum) instead of one per record;
+//   * there is no block-level barrier: a warp streams its unit's records with a register software
+//     pipeline (records two steps ahead, amplitude gathers one step ahead).
 // On one GPU with one observation nothing has to leave the SM between the passes: the fused
-// kernel accumulates the tile, applies the 3x3 pixel covariance in shared memory and projects the
-// same records (second read served by the L2) -- the map never touches HBM.
+// kernel (k_bx<2>) accumulates the tile, applies the 3x3 pixel covariance in shared memory and
+// projects the same records (second read served by the L2) -- the map never touches HBM.
 #include <algorithm>
 
 #include "tb_obs.cuh"
