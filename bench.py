@@ -967,7 +967,7 @@ def main_gpu(args):
     # host memory (ops.MapMaker.apply is the N = 1 end-to-end measurement; its multi-rank form
     # is exercised by the 2-rank tests and can be selected with TB_E2E_MAPMAKER_MULTI=1)
     e2e_lhs = None
-    if world > 1:
+    if world > 1 or os.environ.get("TB_E2E_LHS", "0") == "1":
         e2e_lhs = e2e_solver_lhs(ds, st, args.steps, min(args.warmup, 2), world, total_samples)
 
     peaks = {}
@@ -1103,6 +1103,7 @@ def main_gpu(args):
                                                 "h2d_bytes_per_step": None,
                                                 "d2h_bytes_per_step": None,
                                                 "skipped": "--no-extras"},
+            "e2e_solver_lhs": e2e_lhs if (world == 1 and e2e_lhs is not None) else None,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "pcg_relative_residuals": history[args.warmup:args.warmup + 5],
