@@ -205,13 +205,10 @@ def test_offset_template_with_noise_prior(precond_width, det_flags, name, n_samp
     assert_close_norm(pre.local, ref_pre, rtol=1e-12, what="Offset.apply_precond")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TB_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="experimental kernels written without GPU access: run with "
-                           "TB_TEST_EXPERIMENTAL=1 to validate them")
-@pytest.mark.parametrize("chunk", [8, 64, 256])
-def test_experimental_partitioned_banded_solve(chunk):
-    """The six-launch partitioned form of the banded preconditioner (option prior_chunk; its
-    per-thread code is checked on the host in tests/test_offset_prior.py) against the oracle."""
+@pytest.mark.parametrize("chunk", [0, 8, 64, 256])
+def test_partitioned_banded_solve(chunk):
+    """The six-launch partitioned form of the banded preconditioner (option prior_chunk, default
+    256; 0 = one thread per segment) against the oracle."""
     from toast_b200 import lib as L
 
     lib = L.load()
@@ -220,7 +217,7 @@ def test_experimental_partitioned_banded_solve(chunk):
         L.check(lib.tb_set_option(b"prior_chunk", chunk))
         prior = build_product(case, cut=(2,)).finish()
     finally:
-        lib.tb_set_option(b"prior_chunk", 0)
+        lib.tb_set_option(b"prior_chunk", 256)
     n, per = case["n_amp"], case["per"]
     rng = np.random.default_rng(8)
     a_in = rng.standard_normal(n)
@@ -232,3 +229,24 @@ def test_experimental_partitioned_banded_solve(chunk):
     prior.precond(a_in, flags, pre)
     assert_close_norm(pre, ref, rtol=1e-12, what=f"partitioned precond (chunk {chunk})")
     assert np.all(pre[flags != 0] == 0.0)
+
+
+def test_partitioned_banded_solve_on_a_12_hour_view():
+    """The C4 shape: one view of 43 200 baselines per detector (169 chunks of 256)."""
+    case = make_case(20, n_amp_views=(43200,), n_det=2)
+    prior = build_product(case).finish()
+    n = case["n_amp"]
+    rng = np.random.default_rng(12)
+    a_in = rng.standard_normal(n)
+    flags = (rng.random(n) < 0.05).astype(np.uint8)
+    ref = np.zeros(n)
+    OP.apply_precond(case["prior"], a_in, flags, ref)
+    a_d, f_d = torch.from_numpy(a_in).cuda(), torch.from_numpy(flags).cuda()
+    p_d = torch.full((n,), 7.0, dtype=torch.float64, device="cuda")
+    prior.precond(a_d, f_d, p_d)
+    assert_close_norm(p_d.cpu().numpy(), ref, rtol=1e-12, what="partitioned precond, 43200")
+    ref_add = np.zeros(n)
+    OP.add_prior(case["prior"], a_in, flags, ref_add)
+    o_d = torch.zeros(n, dtype=torch.float64, device="cuda")
+    prior.add(a_d, f_d, o_d)
+    assert_close_norm(o_d.cpu().numpy(), ref_add, rtol=1e-12, what="add_prior, 43200")

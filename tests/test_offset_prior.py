@@ -344,7 +344,8 @@ def test_template_mirror_host_logic_matches_reference_initialize(tag, name, prio
 
 
 @pytest.mark.parametrize("n,w,m", [(800, 20, 64), (800, 20, 19), (431, 4, 50), (60, 20, 32),
-                                   (37, 20, 19), (5000, 20, 256), (300, 1, 16)])
+                                   (37, 20, 19), (5000, 20, 256), (300, 1, 16),
+                                   (43200, 20, 256)])
 def test_partitioned_banded_solve_matches_the_sequential_one(n, w, m):
     """The chunk-parallel form of cho_solve_banded (tb_prior.cuh: fwd/bwd_chunk, fwd/bwd_response,
     chunk_correct; device wiring is the next step) against scipy, for chunk sizes down to the

@@ -32,16 +32,20 @@ struct tb_offset_prior {
     int64_t n_blocks = 0;
     const double *filters = nullptr, *precond = nullptr;
     int precond_mode = 0;
-    // partitioned banded solve (EXPERIMENTAL, tb_set_option("prior_chunk", m) before create)
+    // partitioned banded solve (tb_set_option("prior_chunk", m) before create; 0 = off)
     bool has_part = false;
     void *part_blob = nullptr;
     tbp::PartView part;
 };
 
 // chunk length of the partitioned banded solve for priors created from now on; 0 = one thread
-// per segment (the validated form).  EXPERIMENTAL: the per-thread code is checked on the host
-// (tests/test_offset_prior.py), the launches have not run on hardware yet.
-int tb_prior_chunk = 0;
+// per segment.  One thread per segment is the wrong shape for long segments (one 12-hour view =
+// 43 200 baselines per detector: 402 ms per application on the C4 shard, profiles/README.md);
+// the partitioned form (local solves per chunk, a (w-1)-wide boundary recurrence, a correction
+// with precomputed homogeneous responses) is the default.  Both forms are held to scipy's
+// cho_solve_banded on the host (tests/test_offset_prior.py) and on the device
+// (tests/test_gpu_prior.py).
+int tb_prior_chunk = 256;
 
 namespace {
 
