@@ -208,7 +208,7 @@ def test_offset_template_with_noise_prior(precond_width, det_flags, name, n_samp
 @pytest.mark.parametrize("chunk", [0, 8, 64, 256])
 def test_partitioned_banded_solve(chunk):
     """The six-launch partitioned form of the banded preconditioner (option prior_chunk, default
-    256; 0 = one thread per segment) against the oracle."""
+    1024; 0 = one thread per segment) against the oracle."""
     from toast_b200 import lib as L
 
     lib = L.load()
@@ -217,7 +217,7 @@ def test_partitioned_banded_solve(chunk):
         L.check(lib.tb_set_option(b"prior_chunk", chunk))
         prior = build_product(case, cut=(2,)).finish()
     finally:
-        lib.tb_set_option(b"prior_chunk", 256)
+        lib.tb_set_option(b"prior_chunk", 1024)   # the default
     n, per = case["n_amp"], case["per"]
     rng = np.random.default_rng(8)
     a_in = rng.standard_normal(n)
@@ -232,7 +232,7 @@ def test_partitioned_banded_solve(chunk):
 
 
 def test_partitioned_banded_solve_on_a_12_hour_view():
-    """The C4 shape: one view of 43 200 baselines per detector (169 chunks of 256)."""
+    """The C4 shape: one view of 43 200 baselines per detector (43 chunks of 1024)."""
     case = make_case(20, n_amp_views=(43200,), n_det=2)
     prior = build_product(case).finish()
     n = case["n_amp"]

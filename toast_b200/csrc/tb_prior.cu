@@ -41,11 +41,11 @@ struct tb_offset_prior {
 // chunk length of the partitioned banded solve for priors created from now on; 0 = one thread
 // per segment.  One thread per segment is the wrong shape for long segments (one 12-hour view =
 // 43 200 baselines per detector: 402 ms per application on the C4 shard, profiles/README.md);
-// the partitioned form (local solves per chunk, a (w-1)-wide boundary recurrence, a correction
+// the partitioned form with 1024-baseline chunks (12 ms; 256: 20 ms, 4096: 38 ms; local solves per chunk, a (w-1)-wide boundary recurrence, a correction
 // with precomputed homogeneous responses) is the default.  Both forms are held to scipy's
 // cho_solve_banded on the host (tests/test_offset_prior.py) and on the device
 // (tests/test_gpu_prior.py).
-int tb_prior_chunk = 256;
+int tb_prior_chunk = 1024;
 
 namespace {
 
