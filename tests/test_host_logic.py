@@ -88,6 +88,24 @@ def test_pixel_distribution_and_amplitudes():
     np.testing.assert_array_equal(m["x"].local, 3.0 * np.arange(6))
 
 
+def test_finished_maps_land_in_the_pixeldata_buffer():
+    """MapMaker's products: one copy from the (device) tensor straight into PixelData.data,
+    whatever the tensor's shape (flat hit / rcond maps, [n_loc, n_pix_submap, nnz] maps)."""
+    import torch
+
+    from toast_b200.ops.mapmaker import _pixdata_from_device
+
+    dist = PixelDistribution(12 * 64 * 64, 16, [3, 7, 8])
+    hits = torch.arange(3 * 3072, dtype=torch.int64)
+    p = _pixdata_from_device(dist, hits, np.int64, 1)
+    assert p.data.shape == (3, 3072, 1) and p.data.dtype == np.int64
+    np.testing.assert_array_equal(p.raw, hits.numpy())
+    cov = torch.randn((3, 3072, 6), dtype=torch.float64)
+    p = _pixdata_from_device(dist, cov, np.float64, 6)
+    np.testing.assert_array_equal(p.data, cov.numpy())
+    assert p.raw.base is not None and p.distribution is dist
+
+
 def test_argument_validation_happens_before_the_device():
     obs = S.make_observation("c1", n_det=4, n_samp=600)
     idx = np.arange(4, dtype=np.int32)

@@ -34,6 +34,16 @@ def _rows_to_device(dd, dets, dev):
     return torch.from_numpy(np.ascontiguousarray(dd.data[dd.indices(dets)])).to(dev)
 
 
+def _pixdata_from_device(dist, t, dtype, n_value):
+    """A finished device map as a PixelData: ONE device -> host copy straight into the product's
+    own buffer (no intermediate host tensor, no zero-fill of pages that are overwritten anyway)."""
+    import torch
+
+    p = PixelData(dist, dtype, n_value=n_value, zero=False)
+    torch.from_numpy(p.data).copy_(t.reshape(p.data.shape))
+    return p
+
+
 def _rows_from_device(dd, dets, t):
     import torch
 
@@ -330,9 +340,7 @@ class MapMaker(Operator):
         mark("final binning")
 
         def to_pixdata(t, dtype, nv):
-            p = PixelData(dist, dtype, n_value=nv)
-            p.data[:] = t.reshape(n_loc, nps, nv).cpu().numpy()
-            return p
+            return _pixdata_from_device(dist, t, dtype, nv)
 
         data[f"{self.name}_hits"] = to_pixdata(hmap, np.int64, 1)
         data[f"{self.name}_cov"] = to_pixdata(ds.cov, np.float64, 6)

@@ -37,11 +37,13 @@ class PixelDistribution:
 
 
 class PixelData:
-    def __init__(self, dist, dtype=np.float64, n_value=1, units=None):
+    def __init__(self, dist, dtype=np.float64, n_value=1, units=None, zero=True):
         self.distribution = dist
         self.n_value = int(n_value)
         self.dtype = np.dtype(dtype)
-        self.data = np.zeros((dist.n_local_submap, dist.n_pix_submap, self.n_value), dtype=dtype)
+        # zero=False: the caller overwrites every value (a device -> host copy of a finished map)
+        alloc = np.zeros if zero else np.empty
+        self.data = alloc((dist.n_local_submap, dist.n_pix_submap, self.n_value), dtype=dtype)
         self.raw = self.data.reshape(-1)
         self.units = units
 

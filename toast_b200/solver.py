@@ -639,7 +639,7 @@ class Destriper:
         there is more than one rank."""
         if self.peer is not None:
             self._peer_ctas(12)
-            self.peer.reduce_cov(self.cov)
+            self.peer.reduce_cov(self.cov, stream=self._st())
             return
         self._allreduce(self.zmap)
         L.check(self.lib.tb_cov_apply_diag(self.n_local_submap, self.n_pix_submap, 3,
