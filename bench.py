@@ -476,6 +476,7 @@ def time_iterations(ds, st, sqsum_init, steps, warmup, world, lib):
         ev_sums.synchronize()
         history.append(float(host_sums[0]) / sqsum_init)  # host convergence test
 
+    ds.prepare_lhs(st.d, st.q)  # (N > 1: the pipeline's CUDA graph, captured on all ranks together)
     ds.lhs_and_dot(st)  # the LHS of the first iteration (prologue of the pipelined loop)
     for _ in range(warmup):
         step()
@@ -638,6 +639,7 @@ def e2e_solver_lhs(ds, st, steps, warmup, world, total_samples):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    ds.prepare_lhs(d_dev, q_dev)
     for _ in range(warmup):
         step()
     barrier()

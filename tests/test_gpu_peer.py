@@ -230,6 +230,7 @@ def _solve_worker(rank, world, port, out):
                 a = torch.randn(ds.n_amp, generator=g, device="cuda", dtype=torch.float64)
                 a[ds.amp_flags != 0] = 0.0
                 q_pipe, q_ser = torch.zeros_like(a), torch.zeros_like(a)
+                ds.prepare_lhs(a, q_pipe)   # every rank captures before any rank replays
                 for _ in range(3):
                     ds.lhs(a, q_pipe)
                 ds.pipeline = False

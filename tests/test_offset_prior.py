@@ -345,7 +345,8 @@ def test_template_mirror_host_logic_matches_reference_initialize(tag, name, prio
 
 @pytest.mark.parametrize("n,w,m", [(800, 20, 64), (800, 20, 19), (431, 4, 50), (60, 20, 32),
                                    (37, 20, 19), (5000, 20, 256), (300, 1, 16),
-                                   (43200, 20, 256)])
+                                   (43200, 20, 256), (43200, 20, 1024), (5000, 20, 1024),
+                                   (1024, 20, 1024), (1025, 20, 1024)])
 def test_partitioned_banded_solve_matches_the_sequential_one(n, w, m):
     """The chunk-parallel form of cho_solve_banded (tb_prior.cuh: fwd/bwd_chunk, fwd/bwd_response,
     chunk_correct; device wiring is the next step) against scipy, for chunk sizes down to the
@@ -371,13 +372,14 @@ def test_partitioned_banded_solve_matches_the_sequential_one(n, w, m):
     H.assert_close_norm(x, ref, rtol=1e-12, what=f"partitioned solve n={n} w={w} m={m}")
 
 
-@pytest.mark.parametrize("chunk", [8, 19, 64, 1000])
+@pytest.mark.parametrize("chunk", [8, 19, 64, 1000, 1024])
 def test_partitioned_segments_match_the_reference_preconditioner(chunk):
     """The per-thread functions of the partitioned solve (pb_* in tb_prior.cuh), run over all
     segments in the order of the six launches, against Offset._apply_precond on the banded
     cases: different widths, views shorter than the band, a cut detector, flagged amplitudes."""
     hm = H.host_math_lib()
-    for pw, views in ((20, (120, 37, 700, 5)), (4, (50, 3, 1, 64))):
+    # (the third case straddles the default chunk length: 1024 / 1025 / several chunks of 1024)
+    for pw, views in ((20, (120, 37, 700, 5)), (4, (50, 3, 1, 64)), (20, (1024, 1025, 3000))):
         case = make_case(pw, n_amp_views=views, n_det=3)
         b = build_product(case, cut=(1,))
         n = case["n_amp"]

@@ -553,6 +553,27 @@ class Destriper:
         self._capture_pipelined(amps_in, amps_out).replay()
         return amps_out
 
+    def prepare_lhs(self, amps_in, amps_out):
+        """Multi-GPU pipelined form only: capture the CUDA graph of ``lhs(amps_in, amps_out)`` on
+        EVERY rank before any rank replays it.  A lazily captured graph is captured while faster
+        ranks may already be replaying theirs -- their reduction kernels then spin in the
+        device-side barrier until this rank's capture (a device synchronisation, a garbage
+        collection and an allocator flush inside torch.cuda.graph) is over; capturing together
+        removes that window.  Call it symmetrically on all ranks (solve() does)."""
+        if not (self.pipeline and self.world > 1 and getattr(self, "use_graph", False)):
+            return
+        ok = True
+        try:
+            self._capture_pipelined(amps_in, amps_out)
+        except Exception as exc:  # noqa: BLE001
+            import warnings
+
+            warnings.warn(f"CUDA-graph capture of the chunk pipeline refused ({exc})")
+            ok = False
+        if not _all_ranks_ok(ok, self.device, self.group):
+            self.use_graph = False
+            self._graphs = {}
+
     def _capture_pipelined(self, amps_in, amps_out):
         self._peer_ctas(self.pipe_ctas)
         key = (amps_in.data_ptr(), amps_out.data_ptr())
@@ -832,6 +853,8 @@ class Destriper:
         st = _PCGState(n, dev)
         if x0 is not None:
             st.x.copy_(x0)
+        self.prepare_lhs(st.x, st.q)   # (multi-GPU pipeline: both graphs captured up front,
+        self.prepare_lhs(st.d, st.q)   #  on all ranks together)
         self.lhs(st.x, st.q)
         st.r.copy_(rhs)
         st.r.sub_(st.q)
