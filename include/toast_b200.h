@@ -334,8 +334,8 @@ int tb_lhs_pass2_cov(const tb_obs *obs, const double *zmap, const double *cov,
  * The same two passes as tb_lhs_pass1 / tb_lhs_pass2 (mapmaker_solve.py:342-506: template
  * add_to_signal + BuildNoiseWeighted, ops_mapmaker_utils.cpp:15-86,295-377; ScanMap + NoiseWeight
  * + project_signal, ops_scan_map.cpp:16-78, template_offset.cpp:243-327) on the crossing records
- * sorted by pixel BLOCK (tb_bx_block_pixels() consecutive local pixels): a CTA keeps the block's
- * map values in shared memory.
+ * sorted by pixel BLOCK (tb_bx_block_pixels() consecutive local pixels): every WARP keeps the map
+ * values of the block it works on in its own slice of shared memory (no atomics on the tile).
  *   tb_bx_pass1  writes (accumulate = 0) or adds to (accumulate = 1) the noise-weighted map of the
  *                amplitudes; with accumulate = 0 EVERY block of the local map is written, no
  *                zero-fill is needed.  chunk < 0: the whole map; chunk >= 0: the pixel chunk set
