@@ -106,6 +106,58 @@ def test_finished_maps_land_in_the_pixeldata_buffer():
     assert p.raw.base is not None and p.distribution is dist
 
 
+def test_amplitude_flags_and_variance_helpers_match_the_numpy_form():
+    """MapMaker forms the Offset amplitude flags / preconditioner (offset.py:283-344) with torch
+    element-wise ops on the device; the same functions on CPU tensors must give the bits of the
+    numpy form in templates/offset.py, and the layout fill must equal the per-detector loop."""
+    import torch
+
+    from toast_b200.ops.mapmaker import _amp_flags_and_variance, _fill_amp_layout
+
+    rng = np.random.default_rng(3)
+    nad, n_det = 37, 5
+    n = nad * n_det + 25
+    lens = np.minimum(50, 1830 - 50 * np.arange(nad)).astype(np.float64)
+    scale = rng.uniform(0.5, 2.0, n_det)
+    scale[3] = 0.0                                   # a detector with zero weight is cut
+    for offs in (7 + nad * np.arange(n_det), np.array([40, 0, 120, 80, 160]) + 3):
+        amplen, detnoise = np.zeros(n), np.ones(n)
+        for k, o in enumerate(offs):
+            amplen[o:o + nad] = lens
+            detnoise[o:o + nad] = scale[k]
+        a_t, d_t = torch.zeros(n, dtype=torch.float64), torch.ones(n, dtype=torch.float64)
+        _fill_amp_layout(a_t, d_t, offs, nad, lens, scale)
+        np.testing.assert_array_equal(a_t.numpy(), amplen)
+        np.testing.assert_array_equal(d_t.numpy(), detnoise)
+        ng = np.floor(rng.uniform(0.0, 1.0, n) * amplen)
+        ng[::7] = 0.0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            keep = (np.where(amplen > 0, ng / amplen, 0.0) > 0.5) & (detnoise > 0)
+            var = np.where(keep, 1.0 / (detnoise * ng), 0.0)
+        flagged, var_t = _amp_flags_and_variance(torch.from_numpy(ng), a_t, d_t, 0.5)
+        np.testing.assert_array_equal(flagged.numpy(), ~keep)
+        np.testing.assert_array_equal(var_t.numpy(), var)
+        assert keep.any() and (~keep).any() and np.all(np.isfinite(var_t.numpy()))
+
+
+def test_median_spacing_on_a_torch_device_equals_numpy():
+    """The sample spacing behind the Offset step length (utils.py:655-685): the torch form used
+    for long time vectors gives numpy's value, for odd and even counts and jittered stamps."""
+    import torch
+
+    from toast_b200.templates.offset import median_spacing
+
+    rng = np.random.default_rng(9)
+    cpu = torch.device("cpu")
+    for n in ((1 << 18) + 1, (1 << 18) + 2, (1 << 18) + 7):
+        t = np.arange(n, dtype=np.float64) / 37.0
+        for tt in (t, t + rng.normal(0.0, 1e-4, n), np.cumsum(rng.uniform(0.01, 0.03, n))):
+            ref = float(np.median(np.diff(tt)))
+            assert median_spacing(tt, cpu) == ref
+            assert median_spacing(tt) == ref
+    assert median_spacing(np.arange(100.0) / 10.0, cpu) == float(np.median(np.diff(np.arange(100.0) / 10.0)))
+
+
 def test_argument_validation_happens_before_the_device():
     obs = S.make_observation("c1", n_det=4, n_samp=600)
     idx = np.arange(4, dtype=np.int32)

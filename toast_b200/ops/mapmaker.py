@@ -34,6 +34,46 @@ def _rows_to_device(dd, dets, dev):
     return torch.from_numpy(np.ascontiguousarray(dd.data[dd.indices(dets)])).to(dev)
 
 
+def _amp_flags_and_variance(n_good, amplen, detnoise, good_fraction):
+    """Amplitude flags and the diagonal preconditioner of the Offset template
+    (``offset.py:283-344``): an amplitude is kept when more than ``good_fraction`` of its samples
+    are good and its detector weight is positive; ``offset_var = 1 / (detweight * n_good)``.
+    Plain IEEE element-wise arithmetic on torch tensors of any device (the same bits as the numpy
+    form in ``templates/offset.py``).  Returns (flagged [bool], offset_var [f64])."""
+    import torch
+
+    zero = torch.zeros_like(n_good)
+    frac = torch.where(amplen > 0, n_good / amplen, zero)
+    keep = (frac > good_fraction) & (detnoise > 0)
+    offset_var = torch.where(keep, 1.0 / (detnoise * n_good), zero)
+    return ~keep, offset_var
+
+
+def _fill_amp_layout(amplen, detnoise, amp_offsets, n_amp_det, lens, det_scale):
+    """Per-amplitude baseline length and detector weight for the detectors of one observation:
+    ``amplen[o_k : o_k + n_amp_det] = lens``, ``detnoise[...] = det_scale[k]`` for every detector
+    k (in place; tensors of any device)."""
+    import torch
+
+    offs = np.asarray(amp_offsets, dtype=np.int64)
+    n_det = len(offs)
+    if n_det == 0 or n_amp_det == 0:
+        return
+    lens_t = torch.as_tensor(np.ascontiguousarray(lens, dtype=np.float64)).to(amplen.device)
+    w_t = torch.as_tensor(np.ascontiguousarray(det_scale, dtype=np.float64)).to(amplen.device)
+    if np.all(np.diff(offs) == n_amp_det):
+        # detector-major and contiguous (one observation, or the detectors of this observation
+        # next to each other): two strided assignments
+        o0 = int(offs[0])
+        amplen[o0:o0 + n_det * n_amp_det].view(n_det, n_amp_det)[:] = lens_t[None, :]
+        detnoise[o0:o0 + n_det * n_amp_det].view(n_det, n_amp_det)[:] = w_t[:, None]
+        return
+    for k, o in enumerate(offs):
+        o = int(o)
+        amplen[o:o + n_amp_det] = lens_t
+        detnoise[o:o + n_amp_det] = w_t[k]
+
+
 def _pixdata_from_device(dist, t, dtype, n_value):
     """A finished device map as a PixelData: ONE device -> host copy straight into the product's
     own buffer (no intermediate host tensor, no zero-fill of pages that are overwritten anyway)."""
@@ -176,10 +216,13 @@ class MapMaker(Operator):
         self.template_matrix.reset()
         tmpl._defer_prior = True  # built below, from the variance under the full solver flags
         tmpl._defer_variance = True  # (and so are the amplitude flags / variance themselves)
+        tmpl._device = dev           # (long time vectors: the sample rate's median on the device)
         self.template_matrix._init_templates(data, detectors)
 
         # --- device observations, solver flags bit 0 (mapmaker_templates.py:764-810) -----------
         dobs, signals = [], []
+        main_stream = torch.cuda.current_stream(dev)
+        upload = torch.cuda.Stream(device=dev)
         for iob, ob in enumerate(data.obs):
             dets = [d for d in tmpl._all_dets if d in tmpl._obs_dets[iob]]
             fp = ob[dp.focalplane_key]
@@ -218,7 +261,13 @@ class MapMaker(Operator):
                                      dtype=np.int64),
                 device=dev)
             dobs.append(d)
-            signals.append(_rows_to_device(ob.detdata[self.det_data], dets, dev))
+            # the timestreams are not needed before the RHS: their upload (the largest transfer)
+            # runs on its own stream, underneath the pointing expansion, the covariance and the
+            # construction of the crossing lists
+            with torch.cuda.stream(upload):
+                sig = _rows_to_device(ob.detdata[self.det_data], dets, dev)
+            sig.record_stream(main_stream)
+            signals.append(sig)
 
         mark("upload + flags")
         # --- pointing expansion + pixel distribution --------------------------------------------
@@ -283,8 +332,8 @@ class MapMaker(Operator):
         n_amp = tmpl._n_local
         n_good = torch.zeros(n_amp, dtype=torch.float64, device=dev)
         zero_flags = torch.zeros(n_amp, dtype=torch.uint8, device=dev)
-        amplen = np.zeros(n_amp)
-        detnoise = np.ones(n_amp)
+        amplen = torch.zeros(n_amp, dtype=torch.float64, device=dev)
+        detnoise = torch.ones(n_amp, dtype=torch.float64, device=dev)
         for d in dobs:
             idx = np.arange(d.n_det, dtype=np.int32)
             ones = torch.ones((d.n_det, d.n_samp), dtype=torch.float64, device=dev)
@@ -296,16 +345,14 @@ class MapMaker(Operator):
                 np.minimum(d.step_length,
                            int(v["last"] - v["first"]) - d.step_length * np.arange(na))
                 for v, na in zip(d.intervals, d.n_amp_views)])
-            for k, o in enumerate(d.amp_offsets):
-                amplen[o:o + d.n_amp_det] = lens
-                detnoise[o:o + d.n_amp_det] = d.det_scale[k]
-        ng = n_good.cpu().numpy()
-        with np.errstate(divide="ignore", invalid="ignore"):
-            keep = (np.where(amplen > 0, ng / amplen, 0.0) > tmpl.good_fraction) & (detnoise > 0)
-            offset_var = np.where(keep, 1.0 / (detnoise * ng), 0.0)
-        amp_flags = (~keep).astype(np.uint8)
-        tmpl._offsetvar = offset_var
-        tmpl._amp_flags = ~keep
+            _fill_amp_layout(amplen, detnoise, d.amp_offsets, d.n_amp_det, lens, d.det_scale)
+        # (element-wise on the device: the vectors hold millions of baselines)
+        flagged, offset_var = _amp_flags_and_variance(n_good, amplen, detnoise,
+                                                      float(tmpl.good_fraction))
+        amp_flags = flagged.to(torch.uint8)
+        tmpl._offsetvar = offset_var.cpu().numpy()
+        tmpl._amp_flags = flagged.cpu().numpy()
+        del amplen, detnoise, n_good
 
         mark("amplitude flags")
         # --- RHS, PCG ----------------------------------------------------------------------------
@@ -313,6 +360,7 @@ class MapMaker(Operator):
             tmpl._build_prior(data)  # offset.py:356-560, uploaded once
         ds = Destriper(dobs, n_loc, nps, cov, offset_var, amp_flags,
                        regen=self.regenerate_pointing, device=dev, prior=tmpl.prior())
+        main_stream.wait_stream(upload)   # the timestreams have arrived
         mark("crossing lists + solver set-up")
         rhs = ds.rhs(signals)
         mark("RHS")

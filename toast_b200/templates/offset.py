@@ -16,6 +16,25 @@ from .amplitudes import Amplitudes
 from .offset_prior import OffsetPriorBuilder, prior_frequencies
 
 
+def median_spacing(t, device=None):
+    """``np.median(np.diff(times))`` -- the sample spacing the reference derives the rate from
+    (``offset.py:167`` -> ``utils.py:655-685`` ``rate_from_times``).  With ``device`` given and a long vector the difference and the sort
+    run there with torch (12 hours at 50 Hz cost a tenth of a second in numpy's partition); the
+    value is the same: IEEE differences, the middle element of the sorted differences or the
+    mean of the two middle ones."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    n = len(t) - 1
+    if device is None or n < (1 << 18):
+        return float(np.median(np.diff(t)))
+    import torch
+
+    tt = torch.from_numpy(t).to(device)
+    s = torch.sort(tt[1:] - tt[:-1]).values
+    if n % 2 == 1:
+        return float(s[n // 2])
+    return (float(s[n // 2 - 1]) + float(s[n // 2])) / 2.0
+
+
 class Template:
     """templates/template.py:24-263 (the parts Offset uses)."""
 
@@ -79,7 +98,7 @@ class Offset(Template):
         all_dets = {}
         for iob, ob in enumerate(new_data.obs):
             t = ob.shared[self.times]
-            rate = 1.0 / np.median(np.diff(t)) if len(t) > 1 else 1.0
+            rate = 1.0 / median_spacing(t, getattr(self, "_device", None)) if len(t) > 1 else 1.0
             self._obs_rate[iob] = rate
             step = self._step_length(self.step_time, rate)
             views = []
