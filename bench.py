@@ -557,7 +557,10 @@ def committed_traffic(kernel, workload, world):
     e = t.get("kernels", {}).get(f"{kernel}|{workload}|n{world}")
     if e is None:
         return None, "no capture of this kernel / workload / world size"
-    return float(e["dram_bytes"]), e.get("report")
+    note = e.get("report")
+    if e.get("ncu"):   # what the same capture says binds the kernel
+        note = {"report": note, "ncu": e["ncu"]}
+    return float(e["dram_bytes"]), note
 
 
 def reduction_parity_and_rate(ds, world, lib):

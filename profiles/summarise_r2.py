@@ -59,6 +59,9 @@ REPORTS = [
 ]
 
 
+CAPTURE = None
+
+
 def ncu_rows(rep):
     path = os.path.join(SRC, rep + ".ncu-rep")
     if not os.path.exists(path):
@@ -105,6 +108,22 @@ def ncu_summary():
                 rd = float(row[hdr.index("dram__bytes_read.sum")]) * unit[hu["dram__bytes_read.sum"]]
                 wr = float(row[hdr.index("dram__bytes_write.sum")]) * unit[hu["dram__bytes_write.sum"]]
                 traffic = rd + wr
+                pick = {"time_us": "gpu__time_duration.sum",
+                        "dram_pct_of_peak": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                        "l1_lsu_wavefronts_pct_of_peak":
+                            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                        "of_which_shared_memory_pct":
+                            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                        "l2_throughput_pct_of_peak":
+                            "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+                        "l2_hit_rate_pct": "lts__t_sector_hit_rate.pct",
+                        "issue_slots_busy_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                        "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
+                        "registers_per_thread": "launch__registers_per_thread"}
+                global CAPTURE
+                CAPTURE = {k: round(float(row[hdr.index(v)].replace(",", "")), 2)
+                           for k, v in pick.items() if v in hdr}
+                CAPTURE["bound_by"] = "L1/LSU data pipe (shared-memory tile updates + gathers)"
         lines.append("")
     open(os.path.join(OUT, "r2_ncu_blocked.txt"), "w").write("\n".join(lines) + "\n")
     return traffic
@@ -179,6 +198,7 @@ if __name__ == "__main__":
                                "toast_b200/csrc/tb_obs.cuh"],
                    "kernels": {"k_bx<2>|c4|n1": {
                        "dram_bytes": traffic,
+                       "ncu": CAPTURE,
                        "report": "profiles/r2_ncu_blocked.txt (prof_r2final_fused: ncu --set full "
                                  "--clock-control none, C4 shard, one B200)"}}},
                   open(os.path.join(OUT, "ncu_traffic.json"), "w"), indent=1)
