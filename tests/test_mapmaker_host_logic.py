@@ -1,0 +1,77 @@
+"""ops.MapMaker's HOST LOGIC in the CPU suite: the operator runs with device="cpu" against the
+stand-ins of tests/fake_device.py (the oracle does the per-sample compute), and its products must
+be what the oracle's own restatement of the reference stages gives -- the same assertions as
+tests/test_gpu_ops.py::test_mapmaker_end_to_end makes on the GPU with the real kernels.  What
+this covers is everything between the kernels: solver flags, the pixel distribution, the rcond
+mask, amplitude flags and variances, the stage order, the products and where they land."""
+
+import numpy as np
+import pytest
+
+import fake_device
+import helpers as H
+from helpers import O, S, assert_close_norm
+from toast_b200 import ops
+from toast_b200.data import Data, observation_from_synthetic
+from toast_b200.templates import Offset
+
+
+@pytest.mark.parametrize("name,n_det,n_samp,nside", [("c1", 4, 6000, 64), ("c2", 6, 12000, 64)])
+def test_mapmaker_host_logic_with_oracle_compute(monkeypatch, name, n_det, n_samp, nside):
+    fake_device.install(monkeypatch)
+    obs = S.make_observation(name, n_det=n_det, n_samp=n_samp, nside=nside, eps_max=0.03)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    pb = O.build_problem(obs, O, rcond_threshold=1.0e-3)
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                         stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model")
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+    mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning, template_matrix=tmat,
+                          solve_rcond_threshold=1.0e-3, map_rcond_threshold=1.0e-3, iter_max=8,
+                          convergence=1.0e-30, device="cpu")
+    signal0 = obs["signal"].copy()
+    mapper.apply(data)
+
+    # pixel distribution and the products of CovarianceAndHits
+    dist = data["pixel_dist"]
+    np.testing.assert_array_equal(dist.global_submap_to_local, pb.global2local)
+    hits_ref = np.zeros(pb.n_local_submap * pb.n_pix_submap, dtype=np.int64)
+    sf0 = ((obs["det_flags"] & 1) != 0) | ((obs["shared_flags"] & 1) != 0)[None, :]
+    for d in range(n_det):
+        for iv in pb.intervals:
+            a, b = int(iv["first"]), int(iv["last"])
+            sm, lp = O.global_to_local(pb.pixels[d, a:b], pb.n_pix_submap, pb.global2local)
+            lp[sf0[d, a:b]] = -1
+            O.cov_accum_diag_hits(pb.n_local_submap, pb.n_pix_submap, 3, sm, lp, hits_ref)
+    np.testing.assert_array_equal(data["mm_hits"].raw, hits_ref)
+    assert data["mm_hits"].data.dtype == np.int64
+    np.testing.assert_array_equal(data["mm_cov"].data, pb.cov)
+    np.testing.assert_array_equal(data["mm_rcond"].raw, pb.rcond)
+
+    # amplitude flags / variance formed by the operator == the oracle's restatement
+    # (offset.py:283-344) under the full solver flags, bit for bit
+    np.testing.assert_array_equal(tmpl._amp_flags, pb.amp_flags != 0)
+    np.testing.assert_array_equal(tmpl._offsetvar, pb.offset_var)
+    np.testing.assert_array_equal(data["amplitudes"]["baselines"].local_flags != 0,
+                                  pb.amp_flags != 0)
+
+    # raw binned map, PCG history, amplitudes, destriped map, cleaned timestream
+    covapply = O.cov_apply_diag
+    np.testing.assert_array_equal(data["mm_binmap"].data, O.bin_map(pb, O, signal0, covapply))
+    rhs_ref = O.solver_rhs(pb, O, signal0, covapply)
+    amps_ref, hist_ref = O.solve(pb, O, rhs_ref, convergence=1e-30, n_iter_max=8,
+                                 covapply=covapply)
+    assert mapper.history == hist_ref
+    amps = data["amplitudes"]["baselines"].local
+    np.testing.assert_array_equal(amps, amps_ref)
+    clean = signal0.copy()
+    O.template_add(pb, O, -amps, clean)
+    np.testing.assert_array_equal(data.obs[0].detdata["signal"].data, clean)
+    assert_close_norm(data["mm_map"].data, O.bin_map(pb, O, clean, covapply), rtol=1e-15,
+                      what="destriped map")
