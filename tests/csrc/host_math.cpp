@@ -39,6 +39,11 @@ void tbm_zphi2pix(int64_t n, const double *z, const double *phi, int64_t nside, 
     }
 }
 
+// the per-pixel 3x3 eigen-inverse of k_cov_invert3 over a whole map
+void tbm_cov_invert3(int64_t npix, double *cov, double *rcond, double threshold) {
+    for (int64_t p = 0; p < npix; ++p) rcond[p] = tbm::cov_invert3(cov + 6 * p, threshold);
+}
+
 void tbm_stokes_iqu(int64_t n, const double *quats, double cal, double eps, double U_sign,
                     double gamma, const double *hwp, double *w) {
     double eta = (1.0 - eps) / (1.0 + eps);

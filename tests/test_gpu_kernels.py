@@ -456,8 +456,10 @@ def test_covariance_kernels(K, ck):
     K.cov_invert(n_loc * nps, 3, cov, rc, 1e-3)
     assert (rc_ref > 0).sum() > 100
     np.testing.assert_array_equal(rc > 0, rc_ref > 0)
-    assert np.allclose(rc, rc_ref, rtol=1e-9, atol=1e-14)
-    assert np.allclose(cov, cov_ref, rtol=1e-9, atol=1e-9 * np.abs(cov_ref).max())
+    # (the kernel's per-pixel code agrees with this restatement to 1e-13 at this threshold when
+    # it runs on the host: tests/test_host_math.py)
+    assert np.allclose(rc, rc_ref, rtol=1e-10, atol=1e-14)
+    assert_close_norm(cov, cov_ref, what="inverse of the pixel covariance")
 
     # cov_apply
     v_ref = np.random.default_rng(4).standard_normal(n_loc * nps * 3)

@@ -460,4 +460,68 @@ TB_HD void stokes_iqu(const Quat &q, double cal, double eta, double U_sign, doub
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Pixel covariance: symmetric 3x3 eigen-decomposition by cyclic Jacobi rotations, then the
+// reference's inverse = V diag(1/lambda) V^T and rcond = lambda_min / lambda_max
+// (toast_map_cov.cpp:246-396 does the same through LAPACK dsyev + dgemm).  `m` holds the upper
+// triangle row-major (6 values) and is replaced by the inverse, or by zeros when rcond is below
+// the threshold; returns the rcond that is stored (0 for a rejected pixel).
+// ------------------------------------------------------------------------------------------
+TB_HD double cov_invert3(double *m, double threshold) {
+    double a[3][3] = {{m[0], m[1], m[2]}, {m[1], m[3], m[4]}, {m[2], m[4], m[5]}};
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double offn = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        double dn = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+        if (offn <= 1.0e-300 || offn <= 1.0e-18 * dn) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int i = (pq == 2) ? 1 : 0;
+            const int j = (pq == 0) ? 1 : 2;
+            double apq = a[i][j];
+            if (apq == 0.0) continue;
+            double theta = (a[j][j] - a[i][i]) / (2.0 * apq);
+            double t = ((theta >= 0.0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            double c = 1.0 / sqrt(t * t + 1.0);
+            double sn = t * c;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { // A <- A J
+                double aki = a[k][i], akj = a[k][j];
+                a[k][i] = c * aki - sn * akj;
+                a[k][j] = sn * aki + c * akj;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { // A <- J^T A
+                double aik = a[i][k], ajk = a[j][k];
+                a[i][k] = c * aik - sn * ajk;
+                a[j][k] = sn * aik + c * ajk;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double vki = v[k][i], vkj = v[k][j];
+                v[k][i] = c * vki - sn * vkj;
+                v[k][j] = sn * vki + c * vkj;
+            }
+        }
+    }
+    double e0 = a[0][0], e1 = a[1][1], e2 = a[2][2];
+    double emin = fmin(e0, fmin(e1, e2));
+    double emax = fmax(e0, fmax(e1, e2));
+    double rc = (emax > 0.0) ? (emin / emax) : 0.0;
+    bool ok = rc >= threshold;
+    if (ok) {
+        double i0 = 1.0 / e0, i1 = 1.0 / e1, i2 = 1.0 / e2;
+        int o = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c2 = r; c2 < 3; ++c2)
+                m[o++] = v[r][0] * i0 * v[c2][0] + v[r][1] * i1 * v[c2][1] + v[r][2] * i2 * v[c2][2];
+    } else {
+#pragma unroll
+        for (int o = 0; o < 6; ++o) m[o] = 0.0;
+    }
+    return ok ? rc : 0.0;
+}
+
 } // namespace tbm
