@@ -112,6 +112,16 @@ def _worker(rank, world, port, out):
         dist.barrier()
         if rank == 0:
             out.put((err, err_mc, err_sp))
+    except BaseException:
+        # a rank that fails leaves its peers in a collective or in the device-side barrier, and
+        # tearing the process group down can then block for ever: report and leave at once (the
+        # parent sees the exit code and stops the other ranks, _collect)
+        import sys
+        import traceback
+
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
     finally:
         dist.destroy_process_group()
 
@@ -244,6 +254,16 @@ def _solve_worker(rank, world, port, out):
             out.put((res[True][0], res[False][0], rhs_ref[asl], res[True][1], res[False][1],
                      hist_ref, res["pipe_err"]))
         dist.barrier()
+    except BaseException:
+        # a rank that fails leaves its peers in a collective or in the device-side barrier, and
+        # tearing the process group down can then block for ever: report and leave at once (the
+        # parent sees the exit code and stops the other ranks, _collect)
+        import sys
+        import traceback
+
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
     finally:
         dist.destroy_process_group()
 
