@@ -934,6 +934,11 @@ def main_gpu(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # a rank stuck in a collective or in a device-side barrier would otherwise sit there until
+        # the caller's limit: say where and leave (the run normally takes about a minute)
+        import faulthandler
+
+        faulthandler.dump_traceback_later(600, exit=True)
         torch.distributed.init_process_group("nccl", device_id=device)
     lib = L.load()
 
@@ -1165,6 +1170,7 @@ def main_gpu(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+        faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":
