@@ -867,6 +867,8 @@ def noise_prior_sub_run(device, lib, peak, reps=10):
         "config": f"c4 shard, {info['n_det']} segments of {nad} baselines, filter taps ~{taps}, "
                   f"preconditioner band {band}",
         "prior_build_host_s": round(build_s, 2),
+        "banded_solve": (f"partitioned, chunks of {lib.tb_get_option(b'prior_chunk')} baselines"
+                         if lib.tb_get_option(b"prior_chunk") > 0 else "one thread per segment"),
         "add_prior_ms": ms_add, "apply_precond_ms": ms_pre,
         # compulsory: amplitudes in, flags, out (read + write for add); the filter / factor
         # values are shared by a segment (add) or streamed once (banded factor: band x n_amp)
