@@ -395,7 +395,7 @@ TB_HD int64_t vec2pix(const PixCtx &c, double dx, double dy, double dz, int *too
 // alpha = atan2(vd.(vm x vo), vm.vo) and then cos/sin(2 alpha).  (cos, sin)(ang_xy) is
 // (vd.x, vd.y)/hypot and (cos, sin)(2 alpha) is a rational function of (alpha_x, alpha_y), so
 // no transcendental call is needed: the result differs from the libm chain by ~1e-15 absolute
-// (tests/test_oracle_math.py), five orders inside the 1e-10 parity bar.
+// (tests/test_host_math.py), five orders inside the 1e-10 parity bar.
 // ------------------------------------------------------------------------------------------
 TB_HD void detector_cs2alpha(double dx, double dy, double dz, double ox, double oy, double oz,
                              double &c2a, double &s2a) {

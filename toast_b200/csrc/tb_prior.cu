@@ -14,9 +14,10 @@
 //
 // Parallelisation: the convolution is one thread per output amplitude (tiles of 256 amplitudes
 // of one segment per CTA; taps are broadcast loads, the input window is L1-resident).  The banded
-// solve is a length-n recurrence per segment: one thread per segment, which is the right shape
-// for ground scans (thousands of short segments per detector set) and the slow one for a single
-// 12-hour satellite view -- a chunk-parallel (partitioned) solve is the next step there.
+// solve is a length-n recurrence per segment: one thread per segment (k_prior_banded) is the
+// right shape for ground scans (thousands of short segments per detector set) and the wrong one
+// for a single 12-hour satellite view, which the partitioned form (k_pb_*, below) cuts into
+// chunks that are solved in parallel.
 #include "tb_prior.cuh"
 #include "tb_runtime.cuh"
 

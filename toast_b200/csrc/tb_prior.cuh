@@ -50,10 +50,10 @@ TBP_HD void banded_cho_solve(const double *ab, int64_t w, int64_t n, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Partitioned form of the same solve (k_pb_* in tb_prior.cu, tb_set_option("prior_chunk", m),
-// default off: EXPERIMENTAL, not yet run on hardware).  The code below is checked on the host
-// against scipy and the reference's preconditioner (tests/test_offset_prior.py, looped in the
-// order of the six launches).  A segment is cut
+// Partitioned form of the same solve (k_pb_* in tb_prior.cu; tb_set_option("prior_chunk", m),
+// default m = 1024, 0 = one thread per segment).  The code below is checked on the host against
+// scipy and the reference's preconditioner (tests/test_offset_prior.py, looped in the order of
+// the six launches) and on the device (tests/test_gpu_prior.py).  A segment is cut
 // into chunks of m >= w - 1 rows.  Forward substitution of chunk [s, e) only needs the w - 1
 // values before s, so
 //     y[s:e] = u + Gf t,   u = the chunk solved with zeros before it (chunks in parallel),
