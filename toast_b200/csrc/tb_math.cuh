@@ -300,6 +300,11 @@ TB_HD int64_t zphi2pix(const PixCtx &c, double phi, double z, bool &ambiguous) {
             return (int64_t)((I)c.ncap + ((ir - 1) * fournside + ip));
         }
     } else {
+        // (za can exceed 1 by an ulp at the exact south pole -- dz = 1 - 2 (x^2 + y^2) with the sum
+        // rounded up: the root is then NaN and so are vp / vm.  Their integer conversions give
+        // INT_MIN on x86 (the reference) and 0 on the device; both end at the same pixel -- NEST
+        // only uses the low bits, which are zero either way, and RING wraps to ir = 1 -- which
+        // tests/test_host_math.py pins with the quaternion (s, s, 0, 0).)
         double rtz = sqrt(3.0 * (1.0 - za));
         if (near_integer(tt, c.guard_tt)) ambiguous = true;
         double t1 = c.dnside * rtz;
