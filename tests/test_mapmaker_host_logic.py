@@ -75,3 +75,51 @@ def test_mapmaker_host_logic_with_oracle_compute(monkeypatch, name, n_det, n_sam
     np.testing.assert_array_equal(data.obs[0].detdata["signal"].data, clean)
     assert_close_norm(data["mm_map"].data, O.bin_map(pb, O, clean, covapply), rtol=1e-15,
                       what="destriped map")
+
+
+def test_final_products_use_the_map_threshold_and_the_input_flags(monkeypatch):
+    """ops/mapmaker.py:386-470, 502-594: the final covariance and maps are made with the binning
+    flags (input flags, bad pointing, view) and map_rcond_threshold -- NOT with the solver's
+    rcond mask.  With a looser map threshold the products must keep the pixels the solve masked."""
+    fake_device.install(monkeypatch)
+    obs = S.make_observation("c2", n_det=6, n_samp=12000, nside=64, eps_max=0.03)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    solve_thr, map_thr = 1.0e-2, 1.0e-6
+    pb_solve = O.build_problem(obs, O, rcond_threshold=solve_thr)
+    pb_map = O.build_problem(obs, O, rcond_threshold=map_thr)
+    assert (pb_map.rcond > 0).sum() > (pb_solve.rcond > 0).sum()   # the thresholds differ in effect
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                         stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model")
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+    mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning, template_matrix=tmat,
+                          solve_rcond_threshold=solve_thr, map_rcond_threshold=map_thr,
+                          iter_max=5, convergence=1.0e-30, device="cpu")
+    signal0 = obs["signal"].copy()
+    mapper.apply(data)
+    # the solve saw the strict mask ...
+    np.testing.assert_array_equal(tmpl._amp_flags, pb_solve.amp_flags != 0)
+    rhs_ref = O.solver_rhs(pb_solve, O, signal0)
+    _, hist_ref = O.solve(pb_solve, O, rhs_ref, convergence=1e-30, n_iter_max=5)
+    assert mapper.history == hist_ref
+    # ... the products the loose one, on the input flags
+    np.testing.assert_array_equal(data["mm_cov"].data, pb_map.cov)
+    np.testing.assert_array_equal(data["mm_rcond"].raw, pb_map.rcond)
+    in_view = np.zeros(pb_map.n_samp, dtype=bool)
+    for iv in pb_map.intervals:
+        in_view[iv["first"]:iv["last"]] = True
+    base = (((obs["det_flags"] & 1) != 0) | ((obs["shared_flags"] & 1) != 0)[None, :]
+            | ~in_view[None, :] | (pb_map.pixels < 0)).astype(np.uint8)
+    pbx = O.Problem(**pb_map.__dict__)
+    pbx.solver_flags = base
+    np.testing.assert_array_equal(data["mm_binmap"].data,
+                                  O.bin_map(pbx, O, signal0, O.cov_apply_diag))
+    kept_only_by_map = (pb_map.rcond > 0) & (pb_solve.rcond == 0)
+    hit = data["mm_binmap"].data.reshape(-1, 3)[kept_only_by_map]
+    assert np.any(hit != 0.0)
