@@ -132,9 +132,49 @@ class FakeDeviceObservation:
         self.global2local = np.ascontiguousarray(g2l, dtype=np.int64)
 
 
+def _world():
+    import torch.distributed as dist
+
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _covapply(nsub, subsize, nnz, mat, vec):
+    """The reduction of the path and the step after it (pixels.py:710-779 + covariance.py:
+    262-306): sum the noise-weighted map over the ranks (gloo, in place), then apply C."""
+    if _world() > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(torch.from_numpy(vec))
+    O.cov_apply_diag(nsub, subsize, nnz, mat, vec)
+
+
+@contextlib.contextmanager
+def _global_dots():
+    """Amplitude dot products summed over the ranks (templates/amplitudes.py:560-571) inside the
+    oracle's PCG."""
+    if _world() == 1:
+        yield
+        return
+    import torch.distributed as dist
+
+    local = O.amp_dot
+
+    def dot(a, b, aflags):
+        v = torch.tensor([float(local(a, b, aflags))], dtype=torch.float64)
+        dist.all_reduce(v)
+        return np.float64(v[0].item())
+
+    O.amp_dot = dot
+    try:
+        yield
+    finally:
+        O.amp_dot = local
+
+
 class FakeDestriper:
     """solver.Destriper's interface towards ops.MapMaker (one observation), computed by the
-    oracle's restatement of SolverRHS / solve() / BinMap."""
+    oracle's restatement of SolverRHS / solve() / BinMap.  Under torch.distributed (gloo) the map
+    and the dot products are summed over the ranks where the device solver does it."""
 
     def __init__(self, observations, n_local_submap, n_pix_submap, cov, offset_var, amp_flags,
                  regen=False, device="cpu", prior=None, **unused):
@@ -159,15 +199,17 @@ class FakeDestriper:
             cov=_np(self.cov).reshape(self.n_local_submap, self.n_pix_submap, 6))
 
     def rhs(self, signals):
-        return torch.from_numpy(O.solver_rhs(self._pb(), O, _np(signals[0])))
+        return torch.from_numpy(O.solver_rhs(self._pb(), O, _np(signals[0]), _covapply))
 
     def solve(self, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, x0=None):
-        amps, hist = O.solve(self._pb(), O, _np(rhs), convergence=convergence,
-                             n_iter_max=n_iter_max, n_iter_min=n_iter_min)
+        with _global_dots():
+            amps, hist = O.solve(self._pb(), O, _np(rhs), convergence=convergence,
+                                 n_iter_max=n_iter_max, n_iter_min=n_iter_min,
+                                 covapply=_covapply)
         return torch.from_numpy(amps), hist
 
     def bin_signal(self, signals):
-        z = O.bin_map(self._pb(), O, _np(signals[0]), O.cov_apply_diag)
+        z = O.bin_map(self._pb(), O, _np(signals[0]), _covapply)
         return torch.from_numpy(z)
 
 
