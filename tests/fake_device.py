@@ -236,3 +236,23 @@ def install(monkeypatch):
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
     monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+
+
+def install_operator_kernels(monkeypatch):
+    """Route the per-operator kernels (the ``_libtoast`` names the operator mirror calls with
+    ``use_accel=False``: host buffers in, host buffers out) to the oracle, which has the
+    reference's positional signatures, so that the operators' own logic -- views, detector rows,
+    flags, ``ensure()`` / skip, the pixel distribution, Pipeline staging -- runs in the CPU suite."""
+    import toast_b200._libtoast as KP
+    import toast_b200.kernels as KCm
+
+    for name in ("pointing_detector", "pixels_healpix", "stokes_weights_IQU", "stokes_weights_I",
+                 "noise_weight", "build_noise_weighted", "template_offset_add_to_signal",
+                 "template_offset_project_signal", "template_offset_apply_diag_precond",
+                 "cov_apply_diag"):
+        monkeypatch.setattr(KP, name, getattr(O, name))
+    for dt in ("float64", "float32", "int64", "int32"):
+        monkeypatch.setattr(KP, f"ops_scan_map_{dt}", O.scan_map)
+    monkeypatch.setattr(KP, "accel_present", lambda arr, name: False)
+    monkeypatch.setattr(KCm, "template_offset_project_signal_batch",
+                        _KC.template_offset_project_signal_batch)

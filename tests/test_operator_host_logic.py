@@ -1,0 +1,120 @@
+"""The operator mirror's HOST LOGIC in the CPU suite (views, detector rows, flags, `ensure()` /
+skip, pixel distribution, Pipeline): the `_libtoast` kernels the operators call are routed to the
+oracle (tests/fake_device.py::install_operator_kernels -- it has the reference's signatures), the
+expectations are formed by calling the oracle directly on the raw arrays, as the GPU tests do with
+the real kernels (tests/test_gpu_ops.py)."""
+
+import numpy as np
+
+import fake_device
+from helpers import O, S, assert_close_norm
+from toast_b200 import ops
+from toast_b200.data import Data, observation_from_synthetic
+from toast_b200.templates import Offset
+
+
+def _data(name, n_det, n_samp, nside=64):
+    obs = S.make_observation(name, n_det=n_det, n_samp=n_samp, nside=nside, eps_max=0.03)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    return obs, data
+
+
+def test_operator_chain_host_logic(monkeypatch):
+    fake_device.install_operator_kernels(monkeypatch)
+    n_det = 4
+    obs, data = _data("c2", n_det, 12000)
+    ob = data.obs[0]
+    pb = O.build_problem(obs, O)
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    ops.Pipeline(operators=[pix, wts]).apply(data, use_accel=False)
+    np.testing.assert_array_equal(ob.detdata["pixels"].data, pb.pixels)
+    np.testing.assert_array_equal(ob.detdata["weights"].data, pb.weights)
+    dist = data["pixel_dist"]
+    np.testing.assert_array_equal(dist.local_submaps, pb.local_submaps)
+    np.testing.assert_array_equal(dist.global_submap_to_local, pb.global2local)
+    # `exists => skip` (pixels_healpix.py:215-243)
+    ob.detdata["pixels"].data[0, :10] = -5
+    pix.apply(data)
+    assert np.all(ob.detdata["pixels"].data[0, :10] == -5)
+    ob.detdata["pixels"].data[:] = pb.pixels
+
+    idx = np.arange(n_det, dtype=np.int32)
+    build = ops.BuildNoiseWeighted(pixel_dist="pixel_dist", zmap="zmap", view="scanning",
+                                   det_flags="flags", det_flag_mask=1, shared_flags="flags",
+                                   shared_flag_mask=1)
+    ops.Pipeline(operators=[build]).apply(data, use_accel=False)
+    z_ref = np.zeros((pb.n_local_submap, pb.n_pix_submap, 3))
+    O.build_noise_weighted(pb.global2local, z_ref, idx, pb.pixels, idx, pb.weights, idx,
+                           obs["signal"], idx, obs["det_flags"], pb.det_scale, 1, pb.intervals,
+                           obs["shared_flags"], 1, False)
+    np.testing.assert_array_equal(data["zmap"].data, z_ref)
+
+    before = ob.detdata["signal"].data.copy()
+    scan = ops.ScanMap(pixels="pixels", weights="weights", map_key="zmap", view="scanning",
+                       subtract=True)
+    ops.Pipeline(operators=[scan]).apply(data, use_accel=False)
+    d_ref = obs["signal"].copy()
+    O.scan_map(pb.global2local, pb.n_pix_submap, z_ref, d_ref, idx, pb.pixels, idx, pb.weights,
+               idx, pb.intervals, 1.0, False, True, False, False)
+    np.testing.assert_array_equal(ob.detdata["signal"].data, d_ref)
+    scan.subtract = False
+    scan.apply(data)
+    assert_close_norm(ob.detdata["signal"].data, before, rtol=1e-12, what="scan round trip")
+    ob.detdata["signal"].data[:] = before
+
+    ops.NoiseWeight(noise_model="noise_model", view="scanning").apply(data)
+    d_ref = obs["signal"].copy()
+    O.noise_weight(d_ref, idx, pb.intervals, pb.det_scale, False)
+    np.testing.assert_array_equal(ob.detdata["signal"].data, d_ref)
+
+
+def test_template_matrix_offset_host_logic(monkeypatch):
+    """tests/template_offset.py:26-92 through TemplateMatrix / templates.Offset: layout, flags,
+    variance, project(add(1)) = samples per step."""
+    fake_device.install_operator_kernels(monkeypatch)
+    obs, data = _data("c2", 4, 12000)
+    ob = data.obs[0]
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model", det_flags="flags", det_flag_mask=1)
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amps", view="scanning",
+                              det_data="signal", det_flags="flags", det_flag_mask=1)
+    tmat.transpose = True
+    tmat.apply(data)
+    amps = data["amps"]["baselines"]
+    nav, det_start, n_amp = O.offset_layout(4, obs["intervals"], obs["step_length"])
+    assert amps.n_local == n_amp
+    ref = np.zeros(n_amp)
+    aflags = amps.local_flags.copy()
+    for d in range(4):
+        O.template_offset_project_signal(d, obs["signal"], d, obs["det_flags"], 1,
+                                         obs["step_length"], int(det_start[d]), nav, ref, aflags,
+                                         obs["intervals"])
+    np.testing.assert_array_equal(amps.local, ref)
+    sf = (obs["det_flags"] & 1).astype(np.uint8)
+    var_ref, fl_ref = O.offset_variance(4, obs["n_samp"], obs["intervals"], obs["step_length"],
+                                        nav, obs["detweight"], sf, 1)
+    np.testing.assert_array_equal(aflags, fl_ref)
+    np.testing.assert_array_equal(tmpl._offsetvar, var_ref)
+    ob.detdata["signal"].data[:] = 0
+    amps.local[:] = 1.0
+    amps.local_flags[:] = 0
+    tmat.transpose = False
+    tmat.apply(data)
+    out = amps.duplicate()
+    out.reset()
+    data["amps2"] = type(data["amps"])()
+    data["amps2"]["baselines"] = out
+    tmpl.det_flags = None
+    tmat2 = ops.TemplateMatrix(templates=[tmpl], amplitudes="amps2", view="scanning",
+                               det_data="signal", transpose=True)
+    tmat2._initialized = True
+    tmat2.apply(data)
+    lens = np.concatenate([
+        np.minimum(obs["step_length"],
+                   int(v["last"] - v["first"]) - obs["step_length"] * np.arange(na))
+        for v, na in zip(obs["intervals"], nav)])
+    np.testing.assert_array_equal(out.local, np.tile(lens, 4).astype(np.float64))
