@@ -229,3 +229,70 @@ def test_gpu_operator_pixel_centre_kat():
         dist = data["pixel_dist"]
         assert dist.n_pix == DIMS[0] * DIMS[1] and dist.n_local_submap == 10
         assert dist.wcs_shape == (DIMS[1], DIMS[0])
+
+
+def _host_pixels_wcs(wcs, quat_index, quats, shared_flags, shared_flag_mask, pixel_index, pixels,
+                     intervals, hit_submaps, n_pix_submap, use_accel=False, stream=None):
+    """kernels.pixels_wcs with the device code run on the host (tb_wcs.cuh through
+    tests/csrc/host_math.cpp): per detector and view, as tb_pixels_wcs lays the work out."""
+    lib = H.host_math_lib()
+    d = wcs.desc()
+    euler = np.array(list(d.euler), dtype=np.float64)
+    crpix = np.array(list(d.crpix), dtype=np.float64)
+    cdelt = np.array(list(d.cdelt), dtype=np.float64)
+    q, p = np.asarray(quats), np.asarray(pixels)
+    for qi, pi in zip(quat_index, pixel_index):
+        for iv in intervals:
+            a, b = int(iv["first"]), int(iv["last"])
+            n = b - a
+            qq = np.ascontiguousarray(q[qi, a:b])
+            out = np.zeros(n, dtype=np.int64)
+            dc, dr = np.zeros(n), np.zeros(n)
+            lib.tbw_quat2pix(ct.c_int64(n), qq.ctypes.data_as(ct.c_void_p), ct.c_int(d.projection),
+                             ct.c_int(d.is_azimuth), euler.ctypes.data_as(ct.c_void_p),
+                             crpix.ctypes.data_as(ct.c_void_p), cdelt.ctypes.data_as(ct.c_void_p),
+                             ct.c_double(d.cea_lambda), ct.c_int64(d.n_col), ct.c_int64(d.n_row),
+                             out.ctypes.data_as(ct.c_void_p), dc.ctypes.data_as(ct.c_void_p),
+                             dr.ctypes.data_as(ct.c_void_p))
+            if shared_flags is not None and len(shared_flags) == q.shape[1]:
+                out[(np.asarray(shared_flags)[a:b] & shared_flag_mask) != 0] = -1
+            p[pi, a:b] = out
+            if hit_submaps is not None:
+                hit_submaps[out[out >= 0] // n_pix_submap] = 1
+
+
+def test_operator_pixel_centre_kat_on_the_host(monkeypatch):
+    """The reference's own test of PixelsWCS (tests/ops_pointing_wcs.py:165-215) through the
+    operator mirror with the kernel's code run on the host: a boresight aimed at every pixel
+    centre hits every pixel of the projection exactly once, for all six projections; the
+    operator's views, flags, pixel distribution and submaps as on the device."""
+    import fake_device
+    from toast_b200 import ops
+    from toast_b200.data import Data, observation_from_synthetic
+    import toast_b200.ops.pixels_wcs as PW
+
+    fake_device.install_operator_kernels(monkeypatch)      # pointing_detector -> oracle
+    monkeypatch.setattr(PW.K, "pixels_wcs", _host_pixels_wcs)
+    for proj in OW.PROJECTIONS:
+        wo, shape = OW.create_wcs(proj, center_deg=(130.0, -40.0), res_deg=(0.02, 0.02), dims=DIMS)
+        bore, expect = _pixel_centre_quats(wo)
+        n_samp = len(bore)
+        obs = S.make_observation("c1", n_det=2, n_samp=n_samp, with_signal=False, flags=False)
+        obs["boresight"] = np.ascontiguousarray(bore)
+        obs["focalplane"] = np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (2, 1))   # on the boresight
+        obs["intervals"] = S.make_intervals([(0, n_samp)])
+        data = Data()
+        data.obs.append(observation_from_synthetic(obs))
+        dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+        pix = ops.PixelsWCS(detector_pointing=dp, projection=proj, auto_bounds=False,
+                            center=(130.0, -40.0), resolution=(0.02, 0.02), dimensions=DIMS,
+                            submaps=10, create_dist="pixel_dist")
+        pix.apply(data)
+        assert pix.wcs_shape == (DIMS[1], DIMS[0])
+        p = data.obs[0].detdata["pixels"].data
+        for d in range(2):
+            np.testing.assert_array_equal(p[d], expect)
+            assert np.array_equal(np.bincount(p[d], minlength=n_samp), np.ones(n_samp, dtype=int))
+        dist = data["pixel_dist"]
+        assert dist.n_pix == DIMS[0] * DIMS[1] and dist.n_local_submap == 10
+        assert dist.wcs_shape == (DIMS[1], DIMS[0])
