@@ -35,12 +35,17 @@ class _KC:
                   pixels, weight_index, weights, flag_index, det_flags, det_scale, det_flag_mask,
                   intervals, shared_flags, shared_flag_mask, use_accel=False, stream=None):
         g2l = np.asarray(global2local, dtype=np.int64)
-        px, wt, fl = _np(pixels), _np(weights), _np(det_flags)
-        for k, (pi, wi, fi) in enumerate(zip(pixel_index, weight_index, flag_index)):
+        px = _np(pixels)
+        wt = None if weights is None else _np(weights)
+        fl = None if det_flags is None else _np(det_flags)
+        for k, pi in enumerate(pixel_index):
+            wi = None if weight_index is None else weight_index[k]
             for iv in intervals:
                 a, b = int(iv["first"]), int(iv["last"])
                 sm, lp = O.global_to_local(px[pi, a:b], n_pix_submap, g2l)
-                bad = (fl[fi, a:b] & det_flag_mask) != 0
+                bad = np.zeros(b - a, dtype=bool)
+                if fl is not None:
+                    bad |= (fl[flag_index[k], a:b] & det_flag_mask) != 0
                 if shared_flags is not None:
                     bad |= (_np(shared_flags)[a:b] & shared_flag_mask) != 0
                 lp[bad] = -1
@@ -254,5 +259,5 @@ def install_operator_kernels(monkeypatch):
     for dt in ("float64", "float32", "int64", "int32"):
         monkeypatch.setattr(KP, f"ops_scan_map_{dt}", O.scan_map)
     monkeypatch.setattr(KP, "accel_present", lambda arr, name: False)
-    monkeypatch.setattr(KCm, "template_offset_project_signal_batch",
-                        _KC.template_offset_project_signal_batch)
+    for name in ("template_offset_project_signal_batch", "cov_accum", "cov_invert"):
+        monkeypatch.setattr(KCm, name, getattr(_KC, name))

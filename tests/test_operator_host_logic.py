@@ -118,3 +118,90 @@ def test_template_matrix_offset_host_logic(monkeypatch):
                    int(v["last"] - v["first"]) - obs["step_length"] * np.arange(na))
         for v, na in zip(obs["intervals"], nav)])
     np.testing.assert_array_equal(out.local, np.tile(lens, 4).astype(np.float64))
+
+
+def test_covariance_operators_and_binmap_host_logic(monkeypatch):
+    """CovarianceAndHits / BuildHitMap / BuildInverseCovariance / BinMap / covariance_rcond
+    (mapmaker_utils.py:114-515, 1131-1270; mapmaker_binning.py:27-294; covariance.py:20-306):
+    the operators' glue around the accumulation, inversion and apply kernels."""
+    from toast_b200.covariance import covariance_rcond
+
+    fake_device.install_operator_kernels(monkeypatch)
+    n_det = 6
+    obs, data = _data("c2", n_det, 12000)
+    pb = O.build_problem(obs, O, rcond_threshold=1.0e-3)
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    ops.Pipeline(operators=[pix, wts]).apply(data)
+
+    cah = ops.CovarianceAndHits(pixel_dist="pixel_dist", view="scanning", hits="hits",
+                                inverse_covariance="invcov", covariance="cov", rcond="rcond",
+                                rcond_threshold=1.0e-3)
+    cah.apply(data)
+    # the oracle's build_problem accumulates with the same flags (input flags, bad pointing)
+    np.testing.assert_array_equal(data["invcov"].raw, pb.invcov)
+    np.testing.assert_array_equal(data["cov"].data, pb.cov)
+    np.testing.assert_array_equal(data["rcond"].raw, pb.rcond)
+    assert data["hits"].data.dtype == np.int64 and data["hits"].raw.sum() > 0
+    np.testing.assert_array_equal(covariance_rcond(data["invcov"], 1.0e-3).raw, pb.rcond)
+
+    ops.BuildHitMap(pixel_dist="pixel_dist", view="scanning", hits="hits2").apply(data)
+    np.testing.assert_array_equal(data["hits2"].raw, data["hits"].raw)
+    ops.BuildInverseCovariance(pixel_dist="pixel_dist", view="scanning",
+                               inverse_covariance="invcov2").apply(data)
+    np.testing.assert_array_equal(data["invcov2"].raw, pb.invcov)
+
+    # BinMap = pointing (already there: skipped) + BuildNoiseWeighted + covariance_apply
+    binner = ops.BinMap(name="bin", pixel_dist="pixel_dist", covariance="cov", binned="binned",
+                        pixel_pointing=pix, stokes_weights=wts, noise_model="noise_model",
+                        full_pointing=True)
+    binner.apply(data)
+    idx = np.arange(n_det, dtype=np.int32)
+    z_ref = np.zeros((pb.n_local_submap, pb.n_pix_submap, 3))
+    O.build_noise_weighted(pb.global2local, z_ref, idx, pb.pixels, idx, pb.weights, idx,
+                           obs["signal"], idx, obs["det_flags"], pb.det_scale, 1, pb.intervals,
+                           obs["shared_flags"], 1, False)
+    O.cov_apply_diag(pb.n_local_submap, pb.n_pix_submap, 3, pb.cov.reshape(-1), z_ref.reshape(-1))
+    np.testing.assert_array_equal(data["binned"].data, z_ref)
+    assert "bin_zmap" not in data
+    # one detector at a time (full_pointing=False) sums the same map
+    binner2 = ops.BinMap(name="bin1", pixel_dist="pixel_dist", covariance="cov", binned="binned1",
+                         pixel_pointing=pix, stokes_weights=wts, noise_model="noise_model",
+                         full_pointing=False, noiseweighted="zkeep")
+    binner2.apply(data)
+    assert_close_norm(data["binned1"].data, z_ref, rtol=1e-13, what="BinMap, single detectors")
+    assert "zkeep" in data
+
+
+def test_scan_mask_host_logic(monkeypatch):
+    """ops/scan_map/scan_map.py:216-357."""
+    from toast_b200.pixels import PixelData
+
+    fake_device.install_operator_kernels(monkeypatch)
+    obs, data = _data("c2", 4, 12000)
+    ob = data.obs[0]
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    pix.apply(data)
+    dist = data["pixel_dist"]
+    mask = PixelData(dist, np.uint8, n_value=1)
+    rng = np.random.default_rng(8)
+    mask.data[:] = rng.integers(0, 4, mask.data.shape).astype(np.uint8)
+    data["mask"] = mask
+    before = ob.detdata["flags"].data.copy()
+    ops.ScanMask(det_flags="flags", det_flags_value=4, pixels="pixels", mask_key="mask",
+                 mask_bits=2, view="scanning").apply(data)
+    expect = before.copy()
+    p = ob.detdata["pixels"].data
+    for iv in obs["intervals"]:
+        a, b = int(iv["first"]), int(iv["last"])
+        sm, lp = dist.global_pixel_to_submap(p[:, a:b])
+        ok = sm >= 0
+        hit = np.zeros(sm.shape, dtype=bool)
+        hit[ok] = (mask.data[sm[ok], lp[ok], 0] & 2) != 0
+        expect[:, a:b] |= np.where(hit, 4, 0).astype(np.uint8)
+    np.testing.assert_array_equal(ob.detdata["flags"].data, expect)
+    assert (expect != before).any()
