@@ -205,3 +205,74 @@ def test_scan_mask_host_logic(monkeypatch):
         expect[:, a:b] |= np.where(hit, 4, 0).astype(np.uint8)
     np.testing.assert_array_equal(ob.detdata["flags"].data, expect)
     assert (expect != before).any()
+
+
+def test_pipeline_staging_follows_requires_and_provides(monkeypatch):
+    """pipeline.py:208-303 with use_accel=True: everything the operators require is created on
+    the device and filled before the first operator runs, outputs are created by `ensure(...,
+    accel=True)`, what the pipeline provides is copied back at the end, what it staged itself is
+    dropped, and a buffer somebody else had staged stays where it was.  The device table is a
+    recording stand-in (the kernels work on the host arrays)."""
+    import toast_b200._libtoast as KP
+
+    fake_device.install_operator_kernels(monkeypatch)
+    table, log = {}, []
+    key = lambda arr: arr.__array_interface__["data"][0]
+
+    def create(arr, name):
+        assert key(arr) not in table, f"{name}: created twice"
+        table[key(arr)] = name
+        log.append(("create", name))
+
+    def need(arr, name, what):
+        assert key(arr) in table, f"{what} of '{name}', which is not on the device"
+        log.append((what, name))
+
+    monkeypatch.setattr(KP, "accel_present", lambda arr, name: key(arr) in table)
+    monkeypatch.setattr(KP, "accel_create", create)
+    monkeypatch.setattr(KP, "accel_update_device", lambda a, n: need(a, n, "update_device"))
+    monkeypatch.setattr(KP, "accel_update_host", lambda a, n: need(a, n, "update_host"))
+    monkeypatch.setattr(KP, "accel_reset", lambda a, n: need(a, n, "reset"))
+
+    def delete(arr, name):
+        need(arr, name, "delete")
+        del table[key(arr)]
+
+    monkeypatch.setattr(KP, "accel_delete", delete)
+
+    n_det = 4
+    obs, data = _data("c2", n_det, 6000)
+    ob = data.obs[0]
+    pb = O.build_problem(obs, O)
+    ob.detdata["signal"].accel_create("signal")          # staged by "somebody else"
+    ob.detdata["signal"].accel_update_device("signal")
+    del log[:]
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    ops.Pipeline(operators=[pix, wts]).apply(data, use_accel=True)
+    build = ops.BuildNoiseWeighted(pixel_dist="pixel_dist", zmap="zmap", view="scanning",
+                                   det_flags="flags", det_flag_mask=1, shared_flags="flags",
+                                   shared_flag_mask=1)
+    ops.Pipeline(operators=[build]).apply(data, use_accel=True)
+
+    # results as without the device table
+    np.testing.assert_array_equal(ob.detdata["pixels"].data, pb.pixels)
+    np.testing.assert_array_equal(ob.detdata["weights"].data, pb.weights)
+    idx = np.arange(n_det, dtype=np.int32)
+    z_ref = np.zeros((pb.n_local_submap, pb.n_pix_submap, 3))
+    O.build_noise_weighted(pb.global2local, z_ref, idx, pb.pixels, idx, pb.weights, idx,
+                           obs["signal"], idx, obs["det_flags"], pb.det_scale, 1, pb.intervals,
+                           obs["shared_flags"], 1, False)
+    np.testing.assert_array_equal(data["zmap"].data, z_ref)
+
+    names = lambda what: [n for w, n in log if w == what]
+    # inputs were staged before use, outputs came back, the pipelines cleaned up after themselves
+    assert "boresight_radec" in names("create") and "boresight_radec" in names("update_device")
+    for out in ("pixels", "weights", "zmap"):
+        assert out in names("create") and out in names("update_host"), out
+    assert "signal" not in names("create") and "signal" not in names("delete")
+    assert sorted(table.values()) == ["signal"]          # only the pre-staged buffer is left
+    first_exec = min(i for i, (w, n) in enumerate(log) if (w, n) == ("create", "pixels"))
+    assert log.index(("update_device", "boresight_radec")) < first_exec
