@@ -296,3 +296,52 @@ def test_operator_pixel_centre_kat_on_the_host(monkeypatch):
         dist = data["pixel_dist"]
         assert dist.n_pix == DIMS[0] * DIMS[1] and dist.n_local_submap == 10
         assert dist.wcs_shape == (DIMS[1], DIMS[0])
+
+
+@pytest.mark.parametrize("proj", ["CAR", "TAN"])
+def test_operator_auto_bounds_cover_the_scan(monkeypatch, proj):
+    """pixels_wcs.py:436-489 (auto_bounds, the operator's default): the projection is sized from
+    the boresight track plus the field of view, so every unflagged detector sample of the scan
+    lands inside the image; the bounds contain the detectors' own lon / lat range."""
+    import fake_device
+    from toast_b200 import ops
+    from toast_b200.data import Data, observation_from_synthetic
+    import toast_b200.ops.pixels_wcs as PW
+
+    fake_device.install_operator_kernels(monkeypatch)
+    monkeypatch.setattr(PW.K, "pixels_wcs", _host_pixels_wcs)
+    obs = S.make_observation("c2", n_det=6, n_samp=20000, with_signal=False)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsWCS(detector_pointing=dp, projection=proj, field_of_view=11.0,
+                        resolution=(0.05, 0.05), submaps=8, create_dist="pixel_dist")
+    assert pix.auto_bounds
+    pix.apply(data)
+    assert not pix.auto_bounds and len(pix.bounds) == 4
+    lon_min, lon_max, lat_min, lat_max = pix.bounds
+    assert lon_max - lon_min > 10.0 and lat_max - lat_min > 10.0      # track + field of view
+    ob = data.obs[0]
+    p = ob.detdata["pixels"].data
+    good = np.zeros(obs["n_samp"], dtype=bool)
+    for iv in obs["intervals"]:
+        good[int(iv["first"]):int(iv["last"])] = True
+    good &= (obs["shared_flags"] & 1) == 0
+    assert good.sum() > 1000
+    assert np.all(p[:, good] >= 0), "an unflagged sample fell outside the auto-sized image"
+    flagged_in_view = np.zeros(obs["n_samp"], dtype=bool)
+    for iv in obs["intervals"]:
+        flagged_in_view[int(iv["first"]):int(iv["last"])] = True
+    flagged_in_view &= (obs["shared_flags"] & 1) != 0
+    assert np.all(p[:, flagged_in_view] == -1)
+    n_row, n_col = pix.wcs_shape
+    assert p.max() < n_row * n_col
+    # the detectors' own directions lie inside the bounds
+    quats = ob.detdata[dp.quats].data
+    lon, lat = OW.quat_to_lonlat_deg(quats[:, good].reshape(-1, 4))
+    lon = np.where(lon < lon_min - 180.0, lon + 360.0, lon)
+    lon = np.where(lon > lon_max + 180.0, lon - 360.0, lon)
+    assert lon.min() >= lon_min - 1e-9 and lon.max() <= lon_max + 1e-9
+    assert lat.min() >= lat_min - 1e-9 and lat.max() <= lat_max + 1e-9
+    dist = data["pixel_dist"]
+    assert dist.n_pix == n_row * n_col and 1 <= dist.n_local_submap <= 8
