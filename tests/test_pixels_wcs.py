@@ -345,3 +345,15 @@ def test_operator_auto_bounds_cover_the_scan(monkeypatch, proj):
     assert lat.min() >= lat_min - 1e-9 and lat.max() <= lat_max + 1e-9
     dist = data["pixel_dist"]
     assert dist.n_pix == n_row * n_col and 1 <= dist.n_local_submap <= 8
+
+
+def test_scan_range_refuses_a_track_through_the_pole():
+    """pointing_utils.py:121-130: same refusal, same message, as the reference."""
+    from toast_b200.ops.pixels_wcs import scan_range_lonlat_deg
+
+    lat = np.radians(np.linspace(80.0, 88.0, 50))
+    bore = H.iso_quat(np.pi / 2 - lat, np.zeros(50), np.zeros(50))
+    with pytest.raises(RuntimeError, match="includes the zenith"):
+        scan_range_lonlat_deg(bore, None, 0, 6.0, False)
+    lo, hi, la0, la1 = scan_range_lonlat_deg(bore, None, 0, 2.0, False)   # 88 + 1 < 90: fine
+    assert la1 <= 89.0 + 1e-9 and la0 >= 79.0 - 1e-9

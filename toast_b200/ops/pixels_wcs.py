@@ -39,6 +39,15 @@ def scan_range_lonlat_deg(boresight, flags, flag_mask, fov_deg, is_azimuth):
     if flags is not None:
         bore = bore[(np.asarray(flags) & flag_mask) == 0]
     radius = 0.5 * np.radians(fov_deg)
+    # pointing_utils.py:121-130: the top of the focalplane must stay below the pole
+    nb = bore / np.sqrt(np.sum(bore * bore, axis=-1, keepdims=True))
+    el_max = float(np.max(np.arcsin(np.clip(1 - 2 * (nb[:, 0] ** 2 + nb[:, 1] ** 2), -1, 1))))
+    if el_max + radius > np.pi / 2:
+        raise RuntimeError(
+            "The scan range includes the zenith."
+            f" Max boresight elevation is {np.degrees(el_max)} deg"
+            f" and focalplane radius is {np.degrees(radius)} deg."
+            " Scan range facility cannot handle this case.")
     lon_all, lat_all = [], []
     thetarot = q_rotation(YAXIS, radius)
     for phi in np.linspace(0, 2 * np.pi, 64, endpoint=False):
