@@ -257,3 +257,76 @@ def test_pipeline_chunk_bounds():
     assert pipeline_chunk_bounds(10 * 3072, 2, 1) is None   # a single chunk requested
     b = pipeline_chunk_bounds(2 * 3072, 4, 100)             # more chunks wanted than units
     assert len(b) - 1 == (2 * 3072) // 1024
+
+
+def test_product_amplitudes_drive_the_reference_solve():
+    """templates.Amplitudes / AmplitudesMap as a drop-in for the reference's own PCG driver: the
+    `solve()` of ops/mapmaker_solve.py:524-755 is lifted from the reference source (as
+    tests/golden/make_golden_solve.py does) and run on the PRODUCT's amplitude classes --
+    duplicate, reset, +=, -=, *=, masked dot -- with the oracle as the LHS operator; amplitudes
+    and residual history must be the oracle's restatement bit for bit.  (Needs /root/reference:
+    runs in the build container only.)"""
+    import ast
+    import os
+    import sys
+
+    ref_src = "/root/reference/src/toast/ops/mapmaker_solve.py"
+    if not os.path.exists(ref_src):
+        pytest.skip("the reference source is not available on this machine")
+    sys.path.insert(0, os.path.join(H.ROOT, "tests", "golden"))
+    import make_golden_solve as G
+    from helpers import O
+    from toast_b200.templates.amplitudes import Amplitudes, AmplitudesMap
+
+    dots = []
+
+    class Recording(AmplitudesMap):
+        def dot(self, other):
+            v = super().dot(other)
+            dots.append((other is self, v))
+            return v
+
+        def duplicate(self):
+            out = Recording()
+            for k, v in self.items():
+                out[k] = v.duplicate()
+            return out
+
+    tree = ast.parse(open(ref_src).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "solve")
+    fn.decorator_list = []
+    ns = {"np": np, "Logger": G._Logger, "Timer": G._Timer, "AmplitudesMap": Recording}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), ref_src, "exec"), ns)
+    solve = ns["solve"]
+
+    obs = S.make_observation("c1", n_det=4, n_samp=6000, nside=32, eps_max=0.03)
+    pb = O.build_problem(obs, O)
+    rhs = O.solver_rhs(pb, O, obs["signal"])
+
+    class TemplateMatrix:
+        amplitudes = None
+
+        @staticmethod
+        def apply_precond(a_in, a_out):
+            O.template_offset_apply_diag_precond(pb.offset_var, a_in["baselines"].local,
+                                                 a_in["baselines"].local_flags,
+                                                 a_out["baselines"].local, False)
+
+    class LhsOp:
+        name, out, template_matrix = "lhs", None, TemplateMatrix
+
+        @staticmethod
+        def apply(data, detectors=None):
+            a = data[TemplateMatrix.amplitudes]["baselines"].local
+            data[LhsOp.out]["baselines"].local[:] = O.solver_lhs(pb, O, a)
+
+    start = Amplitudes(None, pb.n_amp, pb.n_amp)
+    start.local[:] = rhs
+    start.local_flags[:] = pb.amp_flags
+    data = G._Data()
+    data["rhs"] = Recording(baselines=start)
+    solve(data, None, LhsOp, "rhs", "result", convergence=1e-12, n_iter_max=12, n_iter_min=3)
+    hist = [v / dots[0][1] for self_dot, v in dots[2:] if self_dot]
+    amps_ref, hist_ref = O.solve(pb, O, rhs, convergence=1e-12, n_iter_max=12, n_iter_min=3)
+    assert hist == hist_ref
+    np.testing.assert_array_equal(data["result"]["baselines"].local, amps_ref)
