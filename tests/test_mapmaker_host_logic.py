@@ -123,3 +123,46 @@ def test_final_products_use_the_map_threshold_and_the_input_flags(monkeypatch):
     kept_only_by_map = (pb_map.rcond > 0) & (pb_solve.rcond == 0)
     hit = data["mm_binmap"].data.reshape(-1, 3)[kept_only_by_map]
     assert np.any(hit != 0.0)
+
+
+def test_a_cut_detector_is_left_out_and_left_alone(monkeypatch):
+    """Per-detector cut flags (det_mask): MapMaker solves and maps with the remaining detector
+    rows only (gathered from / scattered back to the detdata buffer), the cut detector's
+    timestream stays as it was, and the result is the oracle's for the problem without it."""
+    fake_device.install(monkeypatch)
+    n_det, cut = 6, 2
+    obs = S.make_observation("c2", n_det=n_det, n_samp=12000, nside=64, eps_max=0.03)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    ob = data.obs[0]
+    ob.det_flags[ob.local_detectors[cut]] = 1
+    keep = [d for d in range(n_det) if d != cut]
+    sub = dict(obs)
+    sub["n_det"] = len(keep)
+    for key in ("focalplane", "epsilon", "gamma", "cal", "detweight", "sigma", "det_flags",
+                "signal"):
+        sub[key] = np.ascontiguousarray(obs[key][keep])
+    pb = O.build_problem(sub, O, rcond_threshold=1.0e-3)
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                         stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model")
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+    mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning, template_matrix=tmat,
+                          solve_rcond_threshold=1.0e-3, map_rcond_threshold=1.0e-3, iter_max=5,
+                          convergence=1.0e-30, device="cpu")
+    mapper.apply(data)
+    np.testing.assert_array_equal(data["mm_cov"].data, pb.cov)
+    rhs_ref = O.solver_rhs(pb, O, sub["signal"])
+    amps_ref, hist_ref = O.solve(pb, O, rhs_ref, convergence=1e-30, n_iter_max=5)
+    assert mapper.history == hist_ref
+    np.testing.assert_array_equal(data["amplitudes"]["baselines"].local, amps_ref)
+    clean = sub["signal"].copy()
+    O.template_add(pb, O, -amps_ref, clean)
+    got = ob.detdata["signal"].data
+    np.testing.assert_array_equal(got[keep], clean)
+    np.testing.assert_array_equal(got[cut], obs["signal"][cut])       # untouched
