@@ -177,13 +177,16 @@ def _global_dots():
 
 
 class FakeDestriper:
-    """solver.Destriper's interface towards ops.MapMaker (one observation), computed by the
-    oracle's restatement of SolverRHS / solve() / BinMap.  Under torch.distributed (gloo) the map
-    and the dot products are summed over the ranks where the device solver does it."""
+    """solver.Destriper's interface towards ops.MapMaker, computed with the oracle's kernels in
+    the order of SolverRHS / SolverLHS / solve() / BinMap (mapmaker_solve.py:107-229, 342-506,
+    524-755; mapmaker_binning.py:179-294) over ONE OR SEVERAL observations: every observation
+    bins into the same map, the map is reduced and multiplied by the covariance once, every
+    observation then scans it.  Under torch.distributed (gloo) the map and the dot products are
+    summed over the ranks where the device solver does it."""
 
     def __init__(self, observations, n_local_submap, n_pix_submap, cov, offset_var, amp_flags,
                  regen=False, device="cpu", prior=None, **unused):
-        assert len(observations) == 1 and prior is None
+        assert prior is None
         self.obs = list(observations)
         self.n_local_submap, self.n_pix_submap = int(n_local_submap), int(n_pix_submap)
         self.cov = cov if isinstance(cov, torch.Tensor) else torch.from_numpy(np.asarray(cov))
@@ -191,8 +194,7 @@ class FakeDestriper:
         self.amp_flags = torch.as_tensor(_np(amp_flags)).to(torch.uint8)
         self.n_amp = int(self.offset_var.numel())
 
-    def _pb(self):
-        d = self.obs[0]
+    def _pb(self, d):
         return O.Problem(
             n_det=d.n_det, n_samp=d.n_samp, step_length=d.step_length, det_start=d.amp_offsets,
             n_amp_views=d.n_amp_views, n_amp=self.n_amp, amp_flags=_np(self.amp_flags),
@@ -203,19 +205,56 @@ class FakeDestriper:
             n_local_submap=self.n_local_submap, n_pix_submap=self.n_pix_submap,
             cov=_np(self.cov).reshape(self.n_local_submap, self.n_pix_submap, 6))
 
+    def _bin(self, pbs, timestreams):
+        z = np.zeros((self.n_local_submap, self.n_pix_submap, 3))
+        for pb, tod in zip(pbs, timestreams):
+            idx = np.arange(pb.n_det, dtype=np.int32)
+            O.build_noise_weighted(pb.global2local, z, idx, pb.pixels, idx, pb.weights, idx, tod,
+                                   idx, pb.solver_flags, pb.det_scale, pb.det_flag_mask,
+                                   pb.intervals, pb.shared_flags, pb.shared_flag_mask, False)
+        _covapply(self.n_local_submap, self.n_pix_submap, 3, pbs[0].cov.reshape(-1),
+                  z.reshape(-1))
+        return z
+
+    @staticmethod
+    def _scan_weight_project(pb, binned, tod, out):
+        idx = np.arange(pb.n_det, dtype=np.int32)
+        O.scan_map(pb.global2local, pb.n_pix_submap, binned, tod, idx, pb.pixels, idx,
+                   pb.weights, idx, pb.intervals, 1.0, False, True, False, False)
+        O.noise_weight(tod, idx, pb.intervals, pb.det_scale, False)
+        O.template_project(pb, O, tod, out)
+
+    def _lhs(self, pbs, amps):
+        def from_template():
+            tods = [np.zeros((pb.n_det, pb.n_samp)) for pb in pbs]
+            for pb, tod in zip(pbs, tods):
+                O.template_add(pb, O, amps, tod)
+            return tods
+
+        binned = self._bin(pbs, from_template())
+        out = np.zeros_like(amps)
+        for pb, tod in zip(pbs, from_template()):
+            self._scan_weight_project(pb, binned, tod, out)
+        return out
+
     def rhs(self, signals):
-        return torch.from_numpy(O.solver_rhs(self._pb(), O, _np(signals[0]), _covapply))
+        pbs = [self._pb(d) for d in self.obs]
+        binned = self._bin(pbs, [_np(s) for s in signals])
+        out = np.zeros(self.n_amp)
+        for pb, sig in zip(pbs, signals):
+            self._scan_weight_project(pb, binned, _np(sig).copy(), out)
+        return torch.from_numpy(out)
 
     def solve(self, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, x0=None):
+        pbs = [self._pb(d) for d in self.obs]
         with _global_dots():
-            amps, hist = O.solve(self._pb(), O, _np(rhs), convergence=convergence,
-                                 n_iter_max=n_iter_max, n_iter_min=n_iter_min,
-                                 covapply=_covapply)
+            amps, hist = O._solve(pbs[0], O, _np(rhs), convergence, n_iter_max, n_iter_min,
+                                  _covapply, lambda pb, K, a, c=None: self._lhs(pbs, a))
         return torch.from_numpy(amps), hist
 
     def bin_signal(self, signals):
-        z = O.bin_map(self._pb(), O, _np(signals[0]), _covapply)
-        return torch.from_numpy(z)
+        pbs = [self._pb(d) for d in self.obs]
+        return torch.from_numpy(self._bin(pbs, [_np(s) for s in signals]))
 
 
 class _Stream:

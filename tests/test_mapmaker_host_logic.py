@@ -166,3 +166,70 @@ def test_a_cut_detector_is_left_out_and_left_alone(monkeypatch):
     got = ob.detdata["signal"].data
     np.testing.assert_array_equal(got[keep], clean)
     np.testing.assert_array_equal(got[cut], obs["signal"][cut])       # untouched
+
+
+def _split_observation(obs, cut):
+    """The synthetic observation cut into two at sample ``cut`` (which lies between two views):
+    the same detectors, the same baselines in the same detector-major order."""
+    def part(a, b, ranges):
+        o = dict(obs)
+        o["n_samp"] = b - a
+        o["boresight"] = np.ascontiguousarray(obs["boresight"][a:b])
+        o["shared_flags"] = np.ascontiguousarray(obs["shared_flags"][a:b])
+        o["det_flags"] = np.ascontiguousarray(obs["det_flags"][:, a:b])
+        o["signal"] = np.ascontiguousarray(obs["signal"][:, a:b])
+        o["intervals"] = S.make_intervals([(f - a, l - a) for f, l in ranges])
+        return o
+
+    iv = [(int(v["first"]), int(v["last"])) for v in obs["intervals"]]
+    first = [r for r in iv if r[1] <= cut]
+    second = [r for r in iv if r[0] >= cut]
+    assert len(first) + len(second) == len(iv) and first and second
+    return part(0, cut, first), part(cut, obs["n_samp"], second)
+
+
+def test_two_observations_equal_the_one_they_were_cut_from(monkeypatch):
+    """Several observations in one MapMaker call (the usual TOAST job): every observation bins
+    into the same map and owns its slice of every detector's amplitudes
+    (templates/offset/offset.py:166-253).  One observation cut in two between views is the SAME
+    destriping problem -- same baselines, same amplitude order -- so hits, covariance, maps,
+    amplitudes and cleaned timestreams must agree with the uncut run (sums re-associated)."""
+    fake_device.install(monkeypatch)
+    obs = S.make_observation("c2", n_det=4, n_samp=12000, nside=64, eps_max=0.03)
+
+    def run(parts):
+        data = Data()
+        for k, o in enumerate(parts):
+            data.obs.append(observation_from_synthetic(o, name=f"obs{k}"))
+        dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+        pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                                create_dist="pixel_dist")
+        wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+        binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                             stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+        tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                      noise_model="noise_model")
+        tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+        mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning,
+                              template_matrix=tmat, solve_rcond_threshold=1.0e-3,
+                              map_rcond_threshold=1.0e-3, iter_max=6, iter_min=6,
+                              convergence=1.0e-30, device="cpu")
+        mapper.apply(data)
+        return data, mapper, tmpl
+
+    one, m1, t1 = run([obs])
+    two, m2, t2 = run(_split_observation(obs, 4500))
+    assert t2._n_local == t1._n_local
+    np.testing.assert_array_equal(two["pixel_dist"].global_submap_to_local,
+                                  one["pixel_dist"].global_submap_to_local)
+    np.testing.assert_array_equal(two["mm_hits"].raw, one["mm_hits"].raw)
+    np.testing.assert_array_equal(t2._amp_flags, t1._amp_flags)
+    np.testing.assert_array_equal(t2._offsetvar, t1._offsetvar)
+    assert_close_norm(two["mm_cov"].data, one["mm_cov"].data, rtol=1e-12, what="covariance")
+    assert_close_norm(two["mm_binmap"].data, one["mm_binmap"].data, rtol=1e-12, what="binned map")
+    np.testing.assert_allclose(m2.history, m1.history, rtol=1e-10)
+    assert_close_norm(two["amplitudes"]["baselines"].local, one["amplitudes"]["baselines"].local,
+                      what="amplitudes")
+    assert_close_norm(two["mm_map"].data, one["mm_map"].data, what="destriped map")
+    cleaned = np.hstack([ob.detdata["signal"].data for ob in two.obs])
+    assert_close_norm(cleaned, one.obs[0].detdata["signal"].data, what="cleaned timestreams")
