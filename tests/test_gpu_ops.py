@@ -195,64 +195,6 @@ def test_mapmaker_end_to_end(name, n_det, n_samp, nside, regen):
     assert_close_norm(data.obs[0].detdata["signal"].data, clean, what="cleaned TOD")
 
 
-def test_covariance_operators_and_binmap():
-    """CovarianceAndHits / BuildHitMap / BuildInverseCovariance / BinMap / covariance_rcond
-    (mapmaker_utils.py:114-515, 1131-1270; mapmaker_binning.py:27-294; covariance.py:20-306)
-    through the operator mirror on host buffers (the CPU suite runs the same operator code with
-    the oracle behind the kernels: tests/test_operator_host_logic.py)."""
-    from toast_b200.covariance import covariance_rcond
-
-    ck = H.checker()
-    n_det = 6
-    obs, data = _data("c2", n_det, 24000, 64)
-    pb = O.build_problem(obs, ck, rcond_threshold=1.0e-3)
-    dp, pix, wts = _pointing_ops(obs)
-    ops.Pipeline(operators=[pix, wts]).apply(data)
-    ops.CovarianceAndHits(pixel_dist="pixel_dist", view="scanning", hits="hits",
-                          inverse_covariance="invcov", covariance="cov", rcond="rcond",
-                          rcond_threshold=1.0e-3).apply(data)
-    hits_ref = np.zeros(pb.n_local_submap * pb.n_pix_submap, dtype=np.int64)
-    sf0 = ((obs["det_flags"] & 1) != 0) | ((obs["shared_flags"] & 1) != 0)[None, :]
-    for d in range(n_det):
-        for iv in pb.intervals:
-            a, b = int(iv["first"]), int(iv["last"])
-            sm, lp = O.global_to_local(pb.pixels[d, a:b], pb.n_pix_submap, pb.global2local)
-            lp[sf0[d, a:b]] = -1
-            O.cov_accum_diag_hits(pb.n_local_submap, pb.n_pix_submap, 3, sm, lp, hits_ref)
-    np.testing.assert_array_equal(data["hits"].raw, hits_ref)          # bit-exact
-    assert_close_norm(data["invcov"].raw, pb.invcov, what="inverse covariance")
-    assert_close_norm(data["cov"].data, pb.cov, what="covariance")
-    np.testing.assert_array_equal(data["rcond"].raw > 0, pb.rcond > 0)
-    assert np.allclose(data["rcond"].raw, pb.rcond, rtol=1e-10, atol=1e-14)
-    rc = covariance_rcond(data["invcov"], 1.0e-3)
-    np.testing.assert_array_equal(rc.raw, data["rcond"].raw)
-
-    ops.BuildHitMap(pixel_dist="pixel_dist", view="scanning", hits="hits2").apply(data)
-    np.testing.assert_array_equal(data["hits2"].raw, hits_ref)
-    ops.BuildInverseCovariance(pixel_dist="pixel_dist", view="scanning",
-                               inverse_covariance="invcov2").apply(data)
-    assert_close_norm(data["invcov2"].raw, pb.invcov, what="inverse covariance (own operator)")
-
-    binned_ref = O.bin_map(pb_unmasked(pb, obs), ck, obs["signal"], ck.cov_apply_diag)
-    for full in (True, False):
-        ops.BinMap(name=f"bin{int(full)}", pixel_dist="pixel_dist", covariance="cov",
-                   binned="binned", pixel_pointing=pix, stokes_weights=wts,
-                   noise_model="noise_model", full_pointing=full).apply(data)
-        assert_close_norm(data["binned"].data, binned_ref, what=f"BinMap full_pointing={full}")
-
-
-def pb_unmasked(pb, obs):
-    """The oracle problem with the INPUT flags only (BinMap applies no rcond mask of its own;
-    pixels the covariance rejected bin to zero through C = 0)."""
-    in_view = np.zeros(pb.n_samp, dtype=bool)
-    for iv in pb.intervals:
-        in_view[iv["first"]:iv["last"]] = True
-    q = O.Problem(**pb.__dict__)
-    q.solver_flags = (((obs["det_flags"] & 1) != 0) | ((obs["shared_flags"] & 1) != 0)[None, :]
-                      | ~in_view[None, :] | (pb.pixels < 0)).astype(np.uint8)
-    return q
-
-
 def test_scan_mask():
     """ops/scan_map/scan_map.py:216-357 (used by the map-maker for the rcond / pixel masks)."""
     from toast_b200.pixels import PixelData

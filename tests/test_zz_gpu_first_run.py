@@ -1,0 +1,135 @@
+"""GPU tests written AFTER the round's last hardware run.  They have never executed on a device,
+so they REPORT without gating: ``xfail(strict=False)`` -- a pass shows up as XPASS, a failure as
+xfail -- and the file sorts last, so that nothing they might leave behind (a CUDA error is sticky)
+can reach the validated tests.  Their bodies were run on the CPU with the oracle behind the
+kernels (tests/test_operator_host_logic.py, tests/test_mapmaker_host_logic.py hold the same
+assertions there).  Move a test into its regular file, without the marker, once it has passed on
+hardware."""
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import O, S, assert_close_norm
+from toast_b200 import ops
+from toast_b200.data import Data, observation_from_synthetic
+from toast_b200.templates import Offset
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first run on hardware: reports, does not gate")]
+
+
+def _data(name="c1", n_det=4, n_samp=6000, nside=64, **kw):
+    obs = S.make_observation(name, n_det=n_det, n_samp=n_samp, nside=nside, eps_max=0.03, **kw)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    return obs, data
+
+
+def _pointing_ops(obs, view="scanning"):
+    dp = ops.PointingDetectorSimple(view=view, shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    return dp, pix, wts
+
+
+def test_covariance_operators_and_binmap():
+    """CovarianceAndHits / BuildHitMap / BuildInverseCovariance / BinMap / covariance_rcond
+    (mapmaker_utils.py:114-515, 1131-1270; mapmaker_binning.py:27-294; covariance.py:20-306)
+    through the operator mirror on host buffers (the CPU suite runs the same operator code with
+    the oracle behind the kernels: tests/test_operator_host_logic.py)."""
+    from toast_b200.covariance import covariance_rcond
+
+    ck = H.checker()
+    n_det = 6
+    obs, data = _data("c2", n_det, 24000, 64)
+    pb = O.build_problem(obs, ck, rcond_threshold=1.0e-3)
+    dp, pix, wts = _pointing_ops(obs)
+    ops.Pipeline(operators=[pix, wts]).apply(data)
+    ops.CovarianceAndHits(pixel_dist="pixel_dist", view="scanning", hits="hits",
+                          inverse_covariance="invcov", covariance="cov", rcond="rcond",
+                          rcond_threshold=1.0e-3).apply(data)
+    hits_ref = np.zeros(pb.n_local_submap * pb.n_pix_submap, dtype=np.int64)
+    sf0 = ((obs["det_flags"] & 1) != 0) | ((obs["shared_flags"] & 1) != 0)[None, :]
+    for d in range(n_det):
+        for iv in pb.intervals:
+            a, b = int(iv["first"]), int(iv["last"])
+            sm, lp = O.global_to_local(pb.pixels[d, a:b], pb.n_pix_submap, pb.global2local)
+            lp[sf0[d, a:b]] = -1
+            O.cov_accum_diag_hits(pb.n_local_submap, pb.n_pix_submap, 3, sm, lp, hits_ref)
+    np.testing.assert_array_equal(data["hits"].raw, hits_ref)          # bit-exact
+    assert_close_norm(data["invcov"].raw, pb.invcov, what="inverse covariance")
+    assert_close_norm(data["cov"].data, pb.cov, what="covariance")
+    np.testing.assert_array_equal(data["rcond"].raw > 0, pb.rcond > 0)
+    assert np.allclose(data["rcond"].raw, pb.rcond, rtol=1e-10, atol=1e-14)
+    rc = covariance_rcond(data["invcov"], 1.0e-3)
+    np.testing.assert_array_equal(rc.raw, data["rcond"].raw)
+
+    ops.BuildHitMap(pixel_dist="pixel_dist", view="scanning", hits="hits2").apply(data)
+    np.testing.assert_array_equal(data["hits2"].raw, hits_ref)
+    ops.BuildInverseCovariance(pixel_dist="pixel_dist", view="scanning",
+                               inverse_covariance="invcov2").apply(data)
+    assert_close_norm(data["invcov2"].raw, pb.invcov, what="inverse covariance (own operator)")
+
+    binned_ref = O.bin_map(pb_unmasked(pb, obs), ck, obs["signal"], ck.cov_apply_diag)
+    for full in (True, False):
+        ops.BinMap(name=f"bin{int(full)}", pixel_dist="pixel_dist", covariance="cov",
+                   binned="binned", pixel_pointing=pix, stokes_weights=wts,
+                   noise_model="noise_model", full_pointing=full).apply(data)
+        assert_close_norm(data["binned"].data, binned_ref, what=f"BinMap full_pointing={full}")
+
+
+def pb_unmasked(pb, obs):
+    """The oracle problem with the INPUT flags only (BinMap applies no rcond mask of its own;
+    pixels the covariance rejected bin to zero through C = 0)."""
+    in_view = np.zeros(pb.n_samp, dtype=bool)
+    for iv in pb.intervals:
+        in_view[iv["first"]:iv["last"]] = True
+    q = O.Problem(**pb.__dict__)
+    q.solver_flags = (((obs["det_flags"] & 1) != 0) | ((obs["shared_flags"] & 1) != 0)[None, :]
+                      | ~in_view[None, :] | (pb.pixels < 0)).astype(np.uint8)
+    return q
+
+
+def test_two_observations_equal_the_one_they_were_cut_from():
+    """Several observations in one MapMaker call on the device: pass 1 of the second observation
+    ADDS to the map the first one wrote (tb_bx_pass1 accumulate = 1), one reduction / covariance
+    product, pass 2 per observation.  One observation cut in two between views is the same
+    destriping problem (tests/test_mapmaker_host_logic.py runs the same comparison on the CPU)."""
+    from test_mapmaker_host_logic import _split_observation
+
+    obs = S.make_observation("c2", n_det=4, n_samp=12000, nside=64, eps_max=0.03)
+
+    def run(parts):
+        data = Data()
+        for k, o in enumerate(parts):
+            data.obs.append(observation_from_synthetic(o, name=f"obs{k}"))
+        dp, pix, wts = _pointing_ops(obs)
+        binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                             stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+        tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                      noise_model="noise_model")
+        tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+        mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning,
+                              template_matrix=tmat, solve_rcond_threshold=1.0e-3,
+                              map_rcond_threshold=1.0e-3, iter_max=3, iter_min=3,
+                              convergence=1.0e-30)
+        mapper.apply(data)
+        return data, mapper, tmpl
+
+    one, m1, t1 = run([obs])
+    two, m2, t2 = run(_split_observation(obs, 4500))
+    np.testing.assert_array_equal(two["mm_hits"].raw, one["mm_hits"].raw)
+    np.testing.assert_array_equal(t2._amp_flags, t1._amp_flags)
+    assert_close_norm(t2._offsetvar, t1._offsetvar, what="offset variance")
+    assert_close_norm(two["mm_cov"].data, one["mm_cov"].data, what="covariance")
+    assert_close_norm(two["mm_binmap"].data, one["mm_binmap"].data, what="binned map")
+    assert abs(m2.history[0] - m1.history[0]) <= 1e-10 * m1.history[0]
+    np.testing.assert_allclose(m2.history, m1.history, rtol=1e-8)
+    assert_close_norm(two["amplitudes"]["baselines"].local, one["amplitudes"]["baselines"].local,
+                      rtol=1e-8, what="amplitudes")
+    assert_close_norm(two["mm_map"].data, one["mm_map"].data, rtol=1e-8, what="destriped map")
+    cleaned = np.hstack([ob.detdata["signal"].data for ob in two.obs])
+    assert_close_norm(cleaned, one.obs[0].detdata["signal"].data, rtol=1e-8,
+                      what="cleaned timestreams")
