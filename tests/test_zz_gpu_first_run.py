@@ -133,3 +133,80 @@ def test_two_observations_equal_the_one_they_were_cut_from():
     cleaned = np.hstack([ob.detdata["signal"].data for ob in two.obs])
     assert_close_norm(cleaned, one.obs[0].detdata["signal"].data, rtol=1e-8,
                       what="cleaned timestreams")
+
+
+def test_a_cut_detector_is_left_out_and_left_alone():
+    """tests/test_mapmaker_host_logic.py::test_a_cut_detector_is_left_out_and_left_alone with
+    the real kernels: MapMaker on a detector subset (rows gathered to / scattered from the
+    device) against the oracle's problem without the cut detector."""
+    ck = H.checker()
+    n_det, cut = 6, 2
+    obs, data = _data("c2", n_det, 12000, 64)
+    ob = data.obs[0]
+    ob.det_flags[ob.local_detectors[cut]] = 1
+    keep = [d for d in range(n_det) if d != cut]
+    sub = dict(obs)
+    sub["n_det"] = len(keep)
+    for key in ("focalplane", "epsilon", "gamma", "cal", "detweight", "sigma", "det_flags",
+                "signal"):
+        sub[key] = np.ascontiguousarray(obs[key][keep])
+    pb = O.build_problem(sub, ck, rcond_threshold=1.0e-3)
+    dp, pix, wts = _pointing_ops(obs)
+    binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                         stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model")
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+    mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning, template_matrix=tmat,
+                          solve_rcond_threshold=1.0e-3, map_rcond_threshold=1.0e-3, iter_max=3,
+                          iter_min=3, convergence=1.0e-30)
+    mapper.apply(data)
+    assert_close_norm(data["mm_cov"].data, pb.cov, what="covariance")
+    covapply = ck.cov_apply_diag
+    rhs_ref = O.solver_rhs(pb, ck, sub["signal"], covapply)
+    amps_ref, hist_ref = O.solve(pb, ck, rhs_ref, convergence=1e-30, n_iter_max=3, n_iter_min=3,
+                                 covapply=covapply)
+    assert abs(mapper.history[0] - hist_ref[0]) <= 1e-10 * hist_ref[0]
+    amps = data["amplitudes"]["baselines"].local
+    assert_close_norm(amps, amps_ref, rtol=1e-8, what="amplitudes")
+    clean = sub["signal"].copy()
+    O.template_add(pb, O, -amps, clean)
+    got = ob.detdata["signal"].data
+    assert_close_norm(got[keep], clean, what="cleaned timestreams")
+    np.testing.assert_array_equal(got[cut], obs["signal"][cut])       # untouched
+
+
+def test_page_locked_buffers_and_a_long_time_vector():
+    """What the bench's end-to-end leg does and the small tests do not: page-locked detector
+    buffers (the timestream upload then really overlaps the set-up kernels on its own stream) and
+    more than 2^18 time stamps (the sample-rate median is then taken on the device).  Same
+    products as with pageable buffers."""
+    obs = S.make_observation("c4", n_det=2, n_samp=300000, nside=64, eps_max=0.03)
+
+    def run(pinned):
+        data = Data()
+        data.obs.append(observation_from_synthetic(obs, pinned=pinned))
+        dp, pix, wts = _pointing_ops(obs)
+        binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                             stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+        tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                      noise_model="noise_model")
+        tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+        mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning,
+                              template_matrix=tmat, solve_rcond_threshold=1.0e-3,
+                              map_rcond_threshold=1.0e-3, iter_max=3, iter_min=3,
+                              convergence=1.0e-30)
+        mapper.apply(data)
+        return data, mapper, tmpl
+
+    a, ma, ta = run(False)
+    b, mb, tb = run(True)
+    assert ta._obs_rate[0] == tb._obs_rate[0] == 1.0 / float(np.median(np.diff(
+        np.arange(obs["n_samp"], dtype=np.float64) / obs["rate"])))
+    np.testing.assert_array_equal(b["mm_hits"].raw, a["mm_hits"].raw)
+    assert_close_norm(b["mm_cov"].data, a["mm_cov"].data, what="covariance")
+    assert_close_norm(b["mm_binmap"].data, a["mm_binmap"].data, what="binned map")
+    np.testing.assert_allclose(mb.history, ma.history, rtol=1e-8)
+    assert_close_norm(b["mm_map"].data, a["mm_map"].data, rtol=1e-8, what="destriped map")
+    assert_close_norm(b.obs[0].detdata["signal"].data, a.obs[0].detdata["signal"].data,
+                      rtol=1e-8, what="cleaned timestreams")
