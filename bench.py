@@ -923,6 +923,16 @@ def cpu_sample_parity(problem, device):
                                 "cpu_baseline sample (max|a-b| / max|b|)"}
 
 
+def _release_cached_memory():
+    """torch.cuda.empty_cache() for the error paths of the optional legs: must not raise itself."""
+    try:
+        import torch
+
+        torch.cuda.empty_cache()
+    except Exception:
+        pass
+
+
 def main_gpu(args):
     import torch
 
@@ -1021,7 +1031,7 @@ def main_gpu(args):
             r = None
             e2e = dict(e2e_lhs)
             e2e["mapmaker_error"] = repr(exc)[:300]
-            torch.cuda.empty_cache()
+            _release_cached_memory()
     if r is not None:
         tt = torch.tensor([r["seconds"]], dtype=torch.float64, device=device)
         if world > 1:
@@ -1145,7 +1155,7 @@ def main_gpu(args):
                 others[key] = o
             except Exception as exc:  # a sub-run never takes the headline down
                 others[key] = {"error": repr(exc)[:300]}
-                torch.cuda.empty_cache()
+                _release_cached_memory()
         try:
             o = c2_operator_chain(device, lib)
             o["frac_of_peak"] = o["algorithmic_bytes"] / \
@@ -1157,7 +1167,7 @@ def main_gpu(args):
             others["noise_prior"] = noise_prior_sub_run(device, lib, peak)
         except Exception as exc:
             others["noise_prior"] = {"error": repr(exc)[:300]}
-            torch.cuda.empty_cache()
+            _release_cached_memory()
         line["other_workloads"] = others
 
     if rank == 0:
