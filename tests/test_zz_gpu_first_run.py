@@ -210,3 +210,31 @@ def test_page_locked_buffers_and_a_long_time_vector():
     assert_close_norm(b["mm_map"].data, a["mm_map"].data, rtol=1e-8, what="destriped map")
     assert_close_norm(b.obs[0].detdata["signal"].data, a.obs[0].detdata["signal"].data,
                       rtol=1e-8, what="cleaned timestreams")
+
+
+def test_device_table_helpers_of_the_c_abi():
+    """tb_accel_device_ptr / tb_accel_bytes_in_use / tb_device_synchronize (the three entry points
+    of include/toast_b200.h no other test reaches): a registered host buffer has a device
+    address and counts towards the bytes in use until it is deleted."""
+    import ctypes as ct
+
+    from toast_b200 import lib as L
+
+    lib = L.load()
+    buf = np.arange(1000, dtype=np.float64)
+    ptr = ct.c_void_p(buf.ctypes.data)
+    before = lib.tb_accel_bytes_in_use()
+    assert not lib.tb_accel_device_ptr(ptr)
+    L.check(lib.tb_accel_create(ptr, buf.nbytes, b"probe"))
+    try:
+        assert lib.tb_accel_present(ptr, buf.nbytes) == 1
+        assert lib.tb_accel_device_ptr(ptr)
+        assert lib.tb_accel_bytes_in_use() >= before + buf.nbytes
+        L.check(lib.tb_accel_update_device(ptr, buf.nbytes, b"probe"))
+        buf[:] = 0
+        L.check(lib.tb_accel_update_host(ptr, buf.nbytes, b"probe"))
+        L.check(lib.tb_device_synchronize())
+        np.testing.assert_array_equal(buf, np.arange(1000, dtype=np.float64))
+    finally:
+        L.check(lib.tb_accel_delete(ptr, buf.nbytes, b"probe"))
+    assert lib.tb_accel_bytes_in_use() == before and not lib.tb_accel_device_ptr(ptr)
