@@ -186,7 +186,8 @@ class FakeDestriper:
 
     def __init__(self, observations, n_local_submap, n_pix_submap, cov, offset_var, amp_flags,
                  regen=False, device="cpu", prior=None, **unused):
-        assert prior is None
+        self.prior = prior        # an oracle.offset_prior.OraclePrior (install(oracle_prior=True))
+        assert prior is None or len(observations) == 1
         self.obs = list(observations)
         self.n_local_submap, self.n_pix_submap = int(n_local_submap), int(n_pix_submap)
         self.cov = cov if isinstance(cov, torch.Tensor) else torch.from_numpy(np.asarray(cov))
@@ -247,6 +248,12 @@ class FakeDestriper:
 
     def solve(self, rhs, convergence=1.0e-12, n_iter_max=100, n_iter_min=3, x0=None):
         pbs = [self._pb(d) for d in self.obs]
+        if self.prior is not None:
+            # (one observation: _lhs is then O.solver_lhs, which O.solve wraps with the prior)
+            amps, hist = O.solve(pbs[0], O, _np(rhs), convergence=convergence,
+                                 n_iter_max=n_iter_max, n_iter_min=n_iter_min,
+                                 covapply=_covapply, prior=self.prior)
+            return torch.from_numpy(amps), hist
         with _global_dots():
             amps, hist = O._solve(pbs[0], O, _np(rhs), convergence, n_iter_max, n_iter_min,
                                   _covapply, lambda pb, K, a, c=None: self._lhs(pbs, a))
@@ -265,10 +272,30 @@ class _Stream:
         pass
 
 
-def install(monkeypatch):
+def _oracle_build_prior(self, data):
+    """templates.Offset._build_prior with the oracle's restatement of offset.py:356-560 (one
+    observation): the noise prior the stand-in solver applies."""
+    from oracle import offset_prior as OP
+
+    ob = data.obs[0]
+    dets = self._all_dets
+    noise = ob[self.noise_model]
+    t = ob.shared[self.times]
+    self._prior = OP.build_prior(
+        noise.freq(dets[0]), np.array([noise.psd(d) for d in dets]),
+        np.array([noise.detector_weight(d) for d in dets]), self._offsetvar, self._obs_views[0],
+        float(t[-1] - t[0]), self.step_time, self._obs_rate[0], precond_width=self.precond_width)
+
+
+def install(monkeypatch, oracle_prior=False):
     """Route ops.MapMaker(device="cpu") through the stand-ins above."""
     import toast_b200.ops.mapmaker as MM
     import toast_b200.solver as SV
+
+    if oracle_prior:
+        import toast_b200.templates.offset as TO
+
+        monkeypatch.setattr(TO.Offset, "_build_prior", _oracle_build_prior)
 
     for name in ("cov_accum", "cov_invert", "ops_scan_map_float64",
                  "template_offset_project_signal_batch", "template_offset_add_to_signal_batch"):

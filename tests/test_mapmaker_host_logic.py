@@ -233,3 +233,57 @@ def test_two_observations_equal_the_one_they_were_cut_from(monkeypatch):
     assert_close_norm(two["mm_map"].data, one["mm_map"].data, what="destriped map")
     cleaned = np.hstack([ob.detdata["signal"].data for ob in two.obs])
     assert_close_norm(cleaned, one.obs[0].detdata["signal"].data, what="cleaned timestreams")
+
+
+@pytest.mark.parametrize("precond_width,nside,rcond,flags",
+                         [(20, 16, 1.0e-6, False),    # banded: needs unflagged baselines
+                          (1, 32, 1.0e-3, True)])     # Toeplitz: with flagged baselines
+def test_mapmaker_with_the_offset_noise_prior(monkeypatch, precond_width, nside, rcond, flags):
+    """MapMaker(use_noise_prior): baselines span the observation, the view only flags samples
+    (offset.py:136-141), the prior is built from the variance under the FULL solver flags, the
+    LHS gains the inverse amplitude covariance and the preconditioner becomes the banded /
+    Toeplitz solve (mapmaker_solve.py:395-412, offset.py:884-1010) -- against the oracle's PCG
+    with its restatement of the prior.  (The banded form cannot be built with flagged baselines,
+    in the reference as here: 1 / offsetvar = inf fails cholesky_banded, offset.py:520-531.)"""
+    from oracle import offset_prior as OP
+    from toast_b200.data import NoiseModel
+
+    fake_device.install(monkeypatch, oracle_prior=True)
+    obs = S.make_observation("c1", n_det=4, n_samp=6000, nside=nside, eps_max=0.03, flags=flags)
+    data = Data()
+    ob = observation_from_synthetic(obs)
+    data.obs.append(ob)
+    dets = ob.local_detectors
+    psdfreq, psds = OP.analytic_psd(obs["sigma"], obs["rate"], fknee=0.05, fmin=1e-4, alpha=1.5,
+                                    n_freq=300)
+    ob["noise_model"] = NoiseModel({d: float(w) for d, w in zip(dets, obs["detweight"])},
+                                   {d: psdfreq for d in dets},
+                                   {d: psds[i] for i, d in enumerate(dets)})
+    pb = O.build_problem(obs, O, rcond_threshold=rcond)
+    assert (pb.amp_flags != 0).any() == flags
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=obs["nside"], nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                         stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model", use_noise_prior=True, precond_width=precond_width)
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+    mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning, template_matrix=tmat,
+                          solve_rcond_threshold=rcond, map_rcond_threshold=rcond, iter_max=8,
+                          convergence=1.0e-30, device="cpu")
+    signal0 = obs["signal"].copy()
+    mapper.apply(data)
+    np.testing.assert_array_equal(tmpl._offsetvar, pb.offset_var)
+    t = ob.shared["times"]
+    oprior = OP.build_prior(psdfreq, psds, obs["detweight"], pb.offset_var, pb.n_amp_views,
+                            float(t[-1] - t[0]), obs["step_time"], tmpl._obs_rate[0],
+                            precond_width=precond_width)
+    rhs_ref = O.solver_rhs(pb, O, signal0)
+    amps_ref, hist_ref = O.solve(pb, O, rhs_ref, convergence=1e-30, n_iter_max=8, prior=oprior)
+    assert mapper.history == hist_ref
+    np.testing.assert_array_equal(data["amplitudes"]["baselines"].local, amps_ref)
+    # the prior changes the solution (the test is not vacuous)
+    amps_plain, _ = O.solve(pb, O, rhs_ref, convergence=1e-30, n_iter_max=8)
+    assert np.max(np.abs(amps_plain - amps_ref)) > 1e-6 * np.max(np.abs(amps_ref))

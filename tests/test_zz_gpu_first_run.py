@@ -238,3 +238,51 @@ def test_device_table_helpers_of_the_c_abi():
     finally:
         L.check(lib.tb_accel_delete(ptr, buf.nbytes, b"probe"))
     assert lib.tb_accel_bytes_in_use() == before and not lib.tb_accel_device_ptr(ptr)
+
+
+@pytest.mark.parametrize("precond_width,nside,rcond,flags",
+                         [(20, 16, 1.0e-6, False), (1, 32, 1.0e-3, True)])
+def test_mapmaker_with_the_offset_noise_prior(precond_width, nside, rcond, flags):
+    """MapMaker(use_noise_prior=True) end to end on the device (its pieces are held to the
+    oracle in tests/test_gpu_prior.py; the CPU suite runs this comparison with the oracle behind
+    the kernels, tests/test_mapmaker_host_logic.py): residual history and amplitudes of the
+    oracle's PCG with its restatement of the prior."""
+    from oracle import offset_prior as OP
+    from toast_b200.data import NoiseModel
+
+    ck = H.checker()
+    obs = S.make_observation("c1", n_det=4, n_samp=6000, nside=nside, eps_max=0.03, flags=flags)
+    data = Data()
+    ob = observation_from_synthetic(obs)
+    data.obs.append(ob)
+    dets = ob.local_detectors
+    psdfreq, psds = OP.analytic_psd(obs["sigma"], obs["rate"], fknee=0.05, fmin=1e-4, alpha=1.5,
+                                    n_freq=300)
+    ob["noise_model"] = NoiseModel({d: float(w) for d, w in zip(dets, obs["detweight"])},
+                                   {d: psdfreq for d in dets},
+                                   {d: psds[i] for i, d in enumerate(dets)})
+    pb = O.build_problem(obs, ck, rcond_threshold=rcond)
+    dp, pix, wts = _pointing_ops(obs)
+    binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                         stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model", use_noise_prior=True, precond_width=precond_width)
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+    mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning, template_matrix=tmat,
+                          solve_rcond_threshold=rcond, map_rcond_threshold=rcond, iter_max=4,
+                          iter_min=4, convergence=1.0e-30)
+    signal0 = obs["signal"].copy()
+    mapper.apply(data)
+    assert_close_norm(tmpl._offsetvar, pb.offset_var, what="offset variance")
+    t = ob.shared["times"]
+    oprior = OP.build_prior(psdfreq, psds, obs["detweight"], pb.offset_var, pb.n_amp_views,
+                            float(t[-1] - t[0]), obs["step_time"], tmpl._obs_rate[0],
+                            precond_width=precond_width)
+    covapply = ck.cov_apply_diag
+    rhs_ref = O.solver_rhs(pb, ck, signal0, covapply)
+    amps_ref, hist_ref = O.solve(pb, ck, rhs_ref, convergence=1e-30, n_iter_max=4, n_iter_min=4,
+                                 covapply=covapply, prior=oprior)
+    assert abs(mapper.history[0] - hist_ref[0]) <= 1e-10 * hist_ref[0]
+    np.testing.assert_allclose(mapper.history, hist_ref, rtol=1e-6)
+    assert_close_norm(data["amplitudes"]["baselines"].local, amps_ref, rtol=1e-7,
+                      what="amplitudes with the noise prior")
