@@ -287,3 +287,29 @@ def test_mapmaker_with_the_offset_noise_prior(monkeypatch, precond_width, nside,
     # the prior changes the solution (the test is not vacuous)
     amps_plain, _ = O.solve(pb, O, rhs_ref, convergence=1e-30, n_iter_max=8)
     assert np.max(np.abs(amps_plain - amps_ref)) > 1e-6 * np.max(np.abs(amps_ref))
+
+
+def test_without_the_stand_ins_the_operator_refuses_a_cpu():
+    """The product has no CPU path: the same call without tests/fake_device.py fails loudly."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("meaningful on a machine without a device only")
+    obs = S.make_observation("c1", n_det=2, n_samp=2000, nside=16)
+    data = Data()
+    data.obs.append(observation_from_synthetic(obs))
+    dp = ops.PointingDetectorSimple(view="scanning", shared_flags="flags", shared_flag_mask=1)
+    pix = ops.PixelsHealpix(detector_pointing=dp, nside=16, nest=obs["nest"],
+                            create_dist="pixel_dist")
+    wts = ops.StokesWeights(detector_pointing=dp, mode="IQU")
+    binning = ops.BinMap(pixel_dist="pixel_dist", covariance="cov", pixel_pointing=pix,
+                         stokes_weights=wts, noise_model="noise_model", full_pointing=True)
+    tmpl = Offset(name="baselines", step_time=obs["step_time"], times="times",
+                  noise_model="noise_model")
+    tmat = ops.TemplateMatrix(templates=[tmpl], amplitudes="amplitudes")
+    for device in ("cpu", "cuda"):
+        mapper = ops.MapMaker(name="mm", det_data="signal", binning=binning,
+                              template_matrix=tmat, iter_max=2, device=device)
+        with pytest.raises(Exception):
+            mapper.apply(data)
+        assert "mm_map" not in data
