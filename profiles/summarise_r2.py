@@ -159,6 +159,16 @@ def launch_list():
             out.append(f"\"{n}\",{len(v)},{sum(v) / len(v):.1f},{sum(v):.1f},{sum(v) / tot:.3f}")
         out.append(f"\"TOTAL (3 iterations, cold-cache serialised ncu times)\",,,{tot:.1f},1.000")
     open(os.path.join(OUT, "r2_launches_step.csv"), "w").write("\n".join(out) + "\n")
+    # the whole capture (set-up of the C4 shard + RHS + the first iterations; ncu -c 400): what
+    # each set-up kernel costs once per solve
+    agg = collections.OrderedDict()
+    for n, v in seq:
+        agg.setdefault(n[-70:], []).append(v)
+    out = ["kernel,launches,mean_us,total_us"]
+    for n, v in sorted(agg.items(), key=lambda x: -sum(x[1])):
+        if sum(v) >= 100.0:
+            out.append(f"\"{n}\",{len(v)},{sum(v) / len(v):.1f},{sum(v):.1f}")
+    open(os.path.join(OUT, "r2_launches_setup.csv"), "w").write("\n".join(out) + "\n")
 
 
 def copy_lines():
